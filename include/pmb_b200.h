@@ -1,0 +1,156 @@
+/*
+ * pmb_b200.h -- C ABI of the B200-native imagined-rollout library (libpmb_b200.so).
+ *
+ * The reference (mcgillmrl/prob_mbrl) has NO FFI / operator-plugin interface: its seam for this
+ * path is a Python call with duck-typed nn.Module arguments.  This header
+ * is therefore the interface a maintainer would bind from the reference's Python (ctypes stub in
+ * INTEGRATION.md); every entry point names the reference code it replaces (file:line relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers (tensor.data_ptr()), fp32 row-major contiguous tensors;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*), no allocation, no host sync;
+ *   - every function returns 0 on success, a negative PMB_E_* code otherwise
+ *     (pmb_last_error() gives the text); the Python host turns nonzero into RuntimeError, the
+ *     reference's error convention for this path (utils/rollout.py:154-157,
+ *     algorithms/mc_pilco.py:122-131);
+ *   - numerical failure on the device (non positive-definite particle covariance in moment
+ *     matching, reference utils/rollout.py:25) is reported through the int32 status word
+ *     `status_dev` (device memory): 0 = ok, otherwise 1 + index of the first failing step.
+ */
+#ifndef PMB_B200_H
+#define PMB_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMB_ABI_VERSION 1
+#define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
+#define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
+#define PMB_MAX_REWARD_ROWS 4 /* rows of the tip map C */
+#define PMB_MAX_STATE 16      /* D + U <= 16 */
+
+enum {
+    PMB_OK = 0,
+    PMB_E_INVALID = -1,     /* bad descriptor (dims, null pointers) */
+    PMB_E_UNSUPPORTED = -2, /* shape outside the fused path (width > PMB_MAX_WIDTH, ...) */
+    PMB_E_WORKSPACE = -3,   /* workspace too small */
+    PMB_E_CUDA = -4         /* a CUDA runtime call failed (see pmb_last_error) */
+};
+
+/* One MLP, nn.Linear layout.  Mirrors what BSequential.forward walks
+ * (reference models/modules.py:215-232) for the pattern (Linear, ReLU, [B|C]Dropout) x L, Linear. */
+typedef struct pmb_net {
+    int n_linear;                      /* L hidden layers + 1 */
+    int dims[PMB_MAX_LINEAR + 1];      /* dims[0] = inputs, dims[i+1] = outputs of linear i */
+    const float *W[PMB_MAX_LINEAR];    /* [dims[i+1]][dims[i]]  (weight of fc{i} / fc_out) */
+    const float *b[PMB_MAX_LINEAR];    /* [dims[i+1]] or NULL */
+    const float *mask[PMB_MAX_LINEAR]; /* hidden layer i: dropout mask rows [>= N][dims[i+1]] or NULL;
+                                          BDropout.noise (modules.py:61) / CDropout.concrete_noise (modules.py:160) */
+    float keep[PMB_MAX_LINEAR];        /* divisor after the mask: BDropout p = 1 - rate, CDropout 1 */
+    int has_density;                   /* output is (mean, log_std) of a DiagGaussianDensity (densities.py:87-121) */
+    const float *z;                    /* density noise [N][out] (PEGASUS: constant over steps) */
+    long long z_step_stride;           /* floats between consecutive steps' noise (0 = constant) */
+    float max_log_std;                 /* DiagGaussianDensity.max_log_std */
+} pmb_net;
+
+/* One rollout problem = the arguments of utils.rollout(states, dynamics, policy, steps, ...)
+ * (reference utils/rollout.py:62-79) after the host has read the modules. */
+typedef struct pmb_problem {
+    int N;                        /* particles on this device */
+    int H;                        /* horizon (steps) */
+    int D;                        /* state dims */
+    int U;                        /* action dims */
+    pmb_net pol;                  /* Policy.model   (models/core.py:221-248) */
+    pmb_net dyn;                  /* DynamicsModel.model + output_density (models/core.py:265-303) */
+    const float *act_scale;       /* [U] Policy.scale */
+    const float *act_bias;        /* [U] Policy.bias  */
+    const float *mx, *iSx;        /* [D+U] Regressor input scaler (models/core.py:177) */
+    const float *my, *Sy;         /* [D]   Regressor output scaler (densities.py:100-107) */
+    int rew_rows;                 /* rows of C (2 for all reference rewards) */
+    const float *rew_C;           /* [rew_rows][D]   delta = C s' + c0 (envs/cartpole/env.py:54-75) */
+    const float *rew_c0;          /* [rew_rows] */
+    const float *rew_Q;           /* [rew_rows][rew_rows] */
+    const float *rew_R;           /* [U][U] */
+    float rew_scale, rew_offset;  /* r = scale * exp(-cost) + offset */
+    int mm_states, mm_rewards;    /* moment matching flags (utils/rollout.py:121-145) */
+    int mm_groups;                /* 0/1 = one group; G = independent contiguous blocks of N/G rows */
+    const float *z_mm;            /* [>= N][D]  rows 0..N-1 are used, rotated by the step index (rollout.py:53-59) */
+    const float *z_rr;            /* [>= N][1] */
+    int n_global;                 /* reserved for sharded moment matching; set to N */
+} pmb_problem;
+
+/* Tunables (0 = library default). */
+typedef struct pmb_tuning {
+    int particles_per_cta;   /* 1, 2, 4 or 8 */
+    int stream_mode;         /* 0 default (=2), 1 = synchronous copies, 2 = TMA bulk copies + mbarrier ring */
+    int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
+    int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
+                                4 weight gradient); 0 = all */
+} pmb_tuning;
+
+int pmb_abi_version(void);
+const char *pmb_last_error(void);
+
+/* Validate a descriptor without touching the device: PMB_OK, PMB_E_INVALID or PMB_E_UNSUPPORTED. */
+int pmb_check_problem(const pmb_problem *p, const pmb_tuning *tune);
+
+/* Bytes of device workspace pmb_rollout_forward/backward need for `p` (activations kept for the
+ * reverse sweep, packed weights, per-layer deltas, split-K partials). */
+size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune);
+
+/* Number of floats of the flat policy gradient: sum over linear layers of W (+ b when present), in
+ * policy.parameters() order  W0, b0, W1, b1, ... */
+size_t pmb_policy_param_count(const pmb_problem *p);
+
+/* Forward sweep.  Replaces the loop body of utils.rollout (reference utils/rollout.py:93-163):
+ * Policy.forward, DynamicsModel.forward, reward_func, optional mm_resample_, for H steps.
+ *   x0      [N][D]        initial particles
+ *   states  [H+1][N][D]   states[0] = x0
+ *   actions [H][N][U]
+ *   rewards [H][N]
+ * Keeps in `workspace` what pmb_rollout_backward needs. */
+int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const float *x0,
+                        float *states, float *actions, float *rewards,
+                        void *workspace, size_t workspace_bytes, int *status_dev, void *stream);
+
+/* Reverse sweep + batched policy weight gradient.  Replaces loss.backward() through the rollout
+ * (reference algorithms/mc_pilco.py:197) for arbitrary cotangents on the three outputs:
+ *   g_states [H+1][N][D], g_actions [H][N][U], g_rewards [H][N]   (each may be NULL = zeros)
+ *   grad_flat [pmb_policy_param_count]   OVERWRITTEN with dL/dtheta_policy (parameters() order)
+ *   dx0       [N][D] or NULL             dL/dx0
+ * Must follow a pmb_rollout_forward on the same problem/workspace. */
+int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune,
+                         const float *states, const float *actions, const float *rewards,
+                         const float *g_states, const float *g_actions, const float *g_rewards,
+                         float *grad_flat, float *dx0,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* One tensor of the optimiser step (all device pointers, `n` floats each). */
+typedef struct pmb_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    long long n;
+} pmb_adam_tensor;
+
+/* clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step()
+ * (reference algorithms/mc_pilco.py:209-214; Adam set-up examples/deep_pilco_no_mm.py:163-166).
+ *   table_dev   device array of n_tensors descriptors
+ *   max_norm    <= 0 disables clipping
+ *   step        1-based step count of THIS update (bias correction), used when step_dev is NULL
+ *   step_dev    optional device counter: when non-NULL it is incremented on the device and used as
+ *               the step count, so the call can be replayed from a CUDA graph
+ *   scratch_dev device scratch of >= 1024 floats; scratch_dev[0] receives the total grad norm. */
+int pmb_clip_adam_step(const pmb_adam_tensor *table_dev, int n_tensors, float max_norm,
+                       float lr, float beta1, float beta2, float eps, long long step,
+                       long long *step_dev, float *scratch_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMB_B200_H */

@@ -1,0 +1,230 @@
+"""ctypes binding of libpmb_b200.so (C ABI: include/pmb_b200.h).
+
+There is no CPU fallback behind this module: if the library is missing or a call fails, the
+product path raises.  PyTorch only supplies device memory and the stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from .operands import RolloutOperands
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpmb_b200.so")
+
+PMB_MAX_LINEAR = 6
+PMB_MAX_WIDTH = 1024
+PMB_MAX_STATE = 16
+ABI_VERSION = 1
+
+_fp = C.POINTER(C.c_float)
+
+
+class PmbNet(C.Structure):
+    _fields_ = [
+        ("n_linear", C.c_int),
+        ("dims", C.c_int * (PMB_MAX_LINEAR + 1)),
+        ("W", C.c_void_p * PMB_MAX_LINEAR),
+        ("b", C.c_void_p * PMB_MAX_LINEAR),
+        ("mask", C.c_void_p * PMB_MAX_LINEAR),
+        ("keep", C.c_float * PMB_MAX_LINEAR),
+        ("has_density", C.c_int),
+        ("z", C.c_void_p),
+        ("z_step_stride", C.c_longlong),
+        ("max_log_std", C.c_float),
+    ]
+
+
+class PmbProblem(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("H", C.c_int), ("D", C.c_int), ("U", C.c_int),
+        ("pol", PmbNet), ("dyn", PmbNet),
+        ("act_scale", C.c_void_p), ("act_bias", C.c_void_p),
+        ("mx", C.c_void_p), ("iSx", C.c_void_p), ("my", C.c_void_p), ("Sy", C.c_void_p),
+        ("rew_rows", C.c_int),
+        ("rew_C", C.c_void_p), ("rew_c0", C.c_void_p), ("rew_Q", C.c_void_p), ("rew_R", C.c_void_p),
+        ("rew_scale", C.c_float), ("rew_offset", C.c_float),
+        ("mm_states", C.c_int), ("mm_rewards", C.c_int), ("mm_groups", C.c_int),
+        ("z_mm", C.c_void_p), ("z_rr", C.c_void_p),
+        ("n_global", C.c_int),
+    ]
+
+
+class PmbTuning(C.Structure):
+    _fields_ = [
+        ("particles_per_cta", C.c_int), ("stream_mode", C.c_int), ("wgrad_splits", C.c_int),
+        ("reserved", C.c_int * 5),
+    ]
+
+
+class PmbAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("n", C.c_longlong)]
+
+
+EXPORTS = ("pmb_abi_version", "pmb_last_error", "pmb_check_problem", "pmb_workspace_bytes", "pmb_policy_param_count",
+           "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step")
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raise (never fall back) when it is absent or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "prob_mbrl_b200: %s not found -- build it with `python -m prob_mbrl_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback for the fused rollout" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise LibraryMissing("%s does not export %s" % (LIB_PATH, name))
+    lib.pmb_abi_version.restype = C.c_int
+    lib.pmb_last_error.restype = C.c_char_p
+    lib.pmb_check_problem.restype = C.c_int
+    lib.pmb_check_problem.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)]
+    lib.pmb_workspace_bytes.restype = C.c_size_t
+    lib.pmb_workspace_bytes.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)]
+    lib.pmb_policy_param_count.restype = C.c_size_t
+    lib.pmb_policy_param_count.argtypes = [C.POINTER(PmbProblem)]
+    lib.pmb_rollout_forward.restype = C.c_int
+    lib.pmb_rollout_forward.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.pmb_rollout_backward.restype = C.c_int
+    lib.pmb_rollout_backward.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)] + [C.c_void_p] * 9 + \
+                                        [C.c_size_t, C.c_void_p]
+    lib.pmb_clip_adam_step.restype = C.c_int
+    lib.pmb_clip_adam_step.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    if lib.pmb_abi_version() != ABI_VERSION:
+        raise LibraryMissing("ABI version mismatch: library %d, binding %d" % (lib.pmb_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pmb_last_error().decode("utf-8", "replace")
+        raise RuntimeError("libpmb_b200 error %d: %s" % (rc, msg))
+
+
+PMB_E_UNSUPPORTED = -2
+
+
+def check_problem(prob, tune):
+    """Validate a descriptor; shapes outside the fused scope raise NotEligible, the rest RuntimeError."""
+    from .operands import NotEligible
+    lib = load()
+    rc = lib.pmb_check_problem(C.byref(prob), C.byref(tune))
+    if rc == PMB_E_UNSUPPORTED:
+        raise NotEligible(lib.pmb_last_error().decode("utf-8", "replace"))
+    check(rc)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t, what):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA float32 tensor (got %s on %s)" % (what, t.dtype, t.device))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _fill_net(dst, net, n_rows, out_dims, keepalive):
+    L = len(net.W) - 1
+    if L + 1 > PMB_MAX_LINEAR:
+        raise RuntimeError("network has %d linear layers, the fused path supports %d" % (L + 1, PMB_MAX_LINEAR))
+    dst.n_linear = L + 1
+    dst.dims[0] = net.W[0].shape[1]
+    for i, w in enumerate(net.W):
+        w = _f32c(w.detach(), "weight")
+        keepalive.append(w)
+        dst.dims[i + 1] = w.shape[0]
+        dst.W[i] = w.data_ptr()
+        if net.b[i] is not None:
+            b = _f32c(net.b[i].detach(), "bias")
+            keepalive.append(b)
+            dst.b[i] = b.data_ptr()
+        else:
+            dst.b[i] = None
+    for i in range(L):
+        if net.mask[i] is not None:
+            m = _f32c(net.mask[i], "dropout mask")
+            if m.shape[0] < n_rows or m.shape[1] != net.W[i].shape[0]:
+                raise RuntimeError("dropout mask %d has shape %s" % (i, tuple(m.shape)))
+            keepalive.append(m)
+            dst.mask[i] = m.data_ptr()
+        else:
+            dst.mask[i] = None
+        dst.keep[i] = float(net.p[i])
+    dst.has_density = int(net.has_density)
+    if net.has_density:
+        z = _f32c(net.z, "density noise")
+        keepalive.append(z)
+        dst.z = z.data_ptr()
+        if z.dim() == 3:
+            dst.z_step_stride = z.shape[1] * z.shape[2]
+        else:
+            dst.z_step_stride = 0
+        if z.shape[-1] != out_dims or z.shape[-2] < n_rows:
+            raise RuntimeError("density noise has shape %s" % (tuple(z.shape),))
+        if z.dim() == 2 and z.shape[0] != n_rows:
+            # rows beyond N are never read, but the row stride must be out_dims: fine as is
+            pass
+    else:
+        dst.z = None
+        dst.z_step_stride = 0
+    dst.max_log_std = float(net.lmax)
+
+
+def make_problem(ops: RolloutOperands, N, H, mm_states=False, mm_rewards=False, mm_groups=None,
+                 z_mm=None, z_rr=None):
+    """Operand bundle -> (pmb_problem, keepalive list).  Tensors in `keepalive` must outlive the call."""
+    keep = []
+    p = PmbProblem()
+    p.N, p.H, p.D, p.U = int(N), int(H), int(ops.D), int(ops.U)
+    _fill_net(p.pol, ops.pol, N, ops.U, keep)
+    _fill_net(p.dyn, ops.dyn, N, ops.D, keep)
+    for name in ("act_scale", "act_bias", "mx", "iSx", "my", "Sy"):
+        t = _f32c(getattr(ops, name), name)
+        keep.append(t)
+        setattr(p, name, t.data_ptr())
+    p.rew_rows = int(ops.rew.C.shape[0])
+    for name in ("C", "c0", "Q", "R"):
+        t = _f32c(getattr(ops.rew, name), "reward " + name)
+        keep.append(t)
+        setattr(p, "rew_" + name, t.data_ptr())
+    p.rew_scale, p.rew_offset = float(ops.rew.scale), float(ops.rew.offset)
+    p.mm_states, p.mm_rewards = int(bool(mm_states)), int(bool(mm_rewards))
+    p.mm_groups = int(mm_groups) if mm_groups else 0
+    if mm_states:
+        z = _f32c(z_mm, "z_mm")
+        keep.append(z)
+        p.z_mm = z.data_ptr()
+    if mm_rewards:
+        z = _f32c(z_rr, "z_rr")
+        keep.append(z)
+        p.z_rr = z.data_ptr()
+    p.n_global = int(N)
+    return p, keep
+
+
+def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
+    t = PmbTuning()
+    t.reserved[0] = int(phases)
+    t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))
+    t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
+    t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
+    return t
+
+
+def current_stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,415 @@
+// C ABI of libpmb_b200.so (declared in include/pmb_b200.h) + the host-side planner that turns a
+// pmb_problem into the shared-memory carve-up, the weight-stream schedule and the workspace layout
+// of the sweeps.  No allocation, no host synchronisation: everything is enqueued on the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pmb_host.h"
+#include "pmb_internal.cuh"
+
+namespace pmb {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static inline int round4(int x) { return (x + 3) & ~3; }
+static inline long long round32(long long x) { return (x + 31) & ~31LL; }
+
+constexpr int SMEM_LIMIT_FLOATS = 232448 / 4;   // 227 KB opt-in dynamic shared memory per CTA
+constexpr int STAGE_FLOATS_MAX = 8192;          // 32 KB per ring stage
+
+struct WGrad {
+    long long delta_off;   // workspace floats
+    int lda, M;
+    long long inp_off;     // workspace floats, -1 = the states trajectory
+    int ldb, Nc;
+    long long w_off, b_off;   // offsets inside the flat gradient (b_off = -1: no bias)
+};
+
+struct Plan {
+    int P, nsplit, stream_mode;
+    SweepParams fwd, bwd;
+    PackJobs jobs;            // dst pointers are workspace float OFFSETS until resolved
+    long long job_dst_off[MAX_PACK_JOBS];
+    long long wpack_fwd_off, wpack_bwd_off;
+    long long part_off;
+    long long nparam;
+    long long ws_floats;
+    int smem_fwd_bytes, smem_bwd_bytes;
+    int n_wg;
+    WGrad wg[MAXL];
+};
+
+struct Alloc {
+    long long top = 0;
+    long long take(long long n) {
+        long long o = top;
+        top += round32(n);
+        return o;
+    }
+};
+
+static int check_net(const pmb_net &n, int nin, int nout, const char *what) {
+    if (n.n_linear < 1 || n.n_linear > MAXL) return fail(PMB_E_UNSUPPORTED, "%s: n_linear=%d outside [1,%d]", what, n.n_linear, MAXL);
+    if (n.dims[0] != nin) return fail(PMB_E_INVALID, "%s: dims[0]=%d, expected %d", what, n.dims[0], nin);
+    if (n.dims[n.n_linear] != nout) return fail(PMB_E_INVALID, "%s: output size %d, expected %d", what, n.dims[n.n_linear], nout);
+    for (int l = 0; l < n.n_linear; ++l) {
+        if (!n.W[l]) return fail(PMB_E_INVALID, "%s: W[%d] is NULL", what, l);
+        if (n.dims[l + 1] < 1) return fail(PMB_E_INVALID, "%s: dims[%d] < 1", what, l + 1);
+        if (l + 1 < n.n_linear && n.dims[l + 1] > PMB_MAX_WIDTH)
+            return fail(PMB_E_UNSUPPORTED, "%s: hidden width %d > %d", what, n.dims[l + 1], PMB_MAX_WIDTH);
+        if (l + 1 < n.n_linear && !(n.keep[l] > 0.f)) return fail(PMB_E_INVALID, "%s: keep[%d] must be > 0", what, l);
+    }
+    if (n.has_density && !n.z) return fail(PMB_E_INVALID, "%s: density noise z is NULL", what);
+    return PMB_OK;
+}
+
+// Fill the fwd/bwd layer tables of one net, its pack jobs and workspace regions.
+static void plan_net(const pmb_net &net, int N, int H, bool is_policy, NetSweep &F, NetSweep &B, Plan &pl,
+                     Alloc &wf, Alloc &wb, Alloc &ws, long long region_base[2]) {
+    (void)region_base;
+    const int L = net.n_linear - 1;
+    int npad[MAXL];
+    for (int l = 0; l < L; ++l) npad[l] = round4(net.dims[l + 1]);
+    memset(&F, 0, sizeof(F));
+    memset(&B, 0, sizeof(B));
+    F.nlin = B.nlin = net.n_linear;
+    F.nout = B.nout = net.dims[net.n_linear];
+    F.nin = B.nin = net.dims[0];
+    F.has_density = B.has_density = net.has_density;
+    F.lmax = B.lmax = net.max_log_std;
+    F.z = B.z = net.z;
+    F.zstride = B.zstride = net.z_step_stride;
+    auto add_job = [&](const float *src, long long dst_off, int R, int C, int SR, int SC, int ld, int tr, int area) {
+        PackJob &j = pl.jobs.job[pl.jobs.n];
+        j.src = src; j.dst = nullptr; j.R = R; j.C = C; j.SR = SR; j.SC = SC; j.src_ld = ld; j.transpose = tr;
+        pl.job_dst_off[pl.jobs.n] = dst_off | ((long long)area << 60);
+        ++pl.jobs.n;
+    };
+    for (int l = 0; l <= L; ++l) {
+        Lin &f = F.lin[l];
+        Lin &b = B.lin[l];
+        const int out_l = net.dims[l + 1], in_l = net.dims[l];
+        // ---------------- forward ----------------
+        if (l < L) {
+            f.kind = 0; f.K = (l == 0) ? in_l : npad[l - 1]; f.Nout = out_l; f.Npad = npad[l]; f.streamed = (l >= 1);
+            f.goff = wf.take((long long)f.K * f.Npad);
+            add_job(net.W[l], f.goff, f.K, f.Npad, out_l, in_l, in_l, 1, 0);
+        } else {
+            f.kind = 1; f.K = (L == 0) ? in_l : npad[L - 1]; f.Nout = out_l; f.Npad = out_l; f.streamed = 0;
+            f.goff = wf.take((long long)f.Nout * f.K);
+            add_job(net.W[l], f.goff, f.Nout, f.K, out_l, in_l, in_l, 0, 0);
+        }
+        f.boff = -1;
+        if (net.b[l]) {
+            f.boff = ws.take(f.Npad);
+            add_job(net.b[l], f.boff, 1, f.Npad, 1, out_l, out_l, 0, 2);
+        }
+        // ---------------- backward ----------------
+        if (l >= 1) {
+            b.kind = 0; b.K = (l == L) ? out_l : npad[l]; b.Nout = in_l; b.Npad = npad[l - 1]; b.streamed = (l < L);
+            b.goff = wb.take((long long)b.K * b.Npad);
+            add_job(net.W[l], b.goff, b.K, b.Npad, out_l, in_l, in_l, 0, 1);
+        } else {
+            b.kind = 1; b.K = (L == 0) ? out_l : npad[0]; b.Nout = in_l; b.Npad = in_l; b.streamed = 0;
+            b.goff = wb.take((long long)b.Nout * b.K);
+            add_job(net.W[l], b.goff, b.Nout, b.K, out_l, in_l, in_l, 1, 1);
+        }
+        b.boff = -1;
+    }
+    for (int l = 0; l < L; ++l) {
+        F.keep[l] = B.keep[l] = net.keep[l];
+        F.mask_off[l] = B.mask_off[l] = -1;
+        if (net.mask[l]) {
+            long long o = ws.take((long long)N * npad[l]);
+            F.mask_off[l] = B.mask_off[l] = o;
+            add_job(net.mask[l], o, N, npad[l], N, net.dims[l + 1], net.dims[l + 1], 0, 2);
+        }
+        long long o = ws.take((long long)H * N * npad[l]);
+        F.saved_off[l] = B.saved_off[l] = o;
+        if (is_policy) {
+            long long d = ws.take((long long)H * N * npad[l]);
+            F.delta_off[l] = B.delta_off[l] = d;
+        }
+    }
+    {
+        long long o = ws.take((long long)H * N * F.nout);
+        F.outsaved_off = B.outsaved_off = o;
+        if (is_policy) {
+            long long d = ws.take((long long)H * N * F.nout);
+            F.delta_off[L] = B.delta_off[L] = d;
+        }
+    }
+}
+
+// shared-memory carve-up + stream schedule of one sweep
+static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, int P, int stream_mode) {
+    int off = 0;
+    S.nres = 0;
+    int tile_rows = 4;
+    S.nsched = 0;
+    for (int n = 0; n < 2; ++n) {
+        NetSweep &net = const_cast<NetSweep &>(*order[n]);
+        for (int l = 0; l < net.nlin; ++l) {
+            Lin &L = net.lin[l];
+            tile_rows = max(tile_rows, max(L.K, L.Npad));
+            if (!L.streamed) {
+                int nfl = (L.kind == 0) ? L.K * L.Npad : L.Nout * L.K;
+                nfl = (nfl + 3) & ~3;
+                L.soff = off;
+                S.res_goff[S.nres] = L.goff;
+                S.res_soff[S.nres] = off;
+                S.res_n[S.nres] = nfl;
+                ++S.nres;
+                off += (nfl + 31) & ~31;
+            }
+        }
+    }
+    S.res_floats = off;
+    S.hmax_pad = tile_rows;
+    S.off_act0 = off; off += ((tile_rows * P) + 31) & ~31;
+    S.off_act1 = off; off += ((tile_rows * P) + 31) & ~31;
+    S.off_red = off;  off += 1024 * P;
+    S.off_misc = off; off += 128 * P;
+    S.off_stage = off;
+    // streamed layers in consumption order
+    int max_npad = 0;
+    for (int n = 0; n < 2; ++n) {
+        const NetSweep &net = *order[n];
+        for (int i = 0; i < net.nlin; ++i) {
+            int l = reverse ? net.nlin - 1 - i : i;
+            if (net.lin[l].streamed) max_npad = max(max_npad, net.lin[l].Npad);
+        }
+    }
+    S.stream_mode = stream_mode;
+    if (max_npad == 0) {
+        S.nstages = 1; S.stage_floats = 0; S.chunks_per_step = 0;
+    } else {
+        int avail = SMEM_LIMIT_FLOATS - off;
+        int ns = 4;
+        int sf = 0;
+        for (; ns >= 2; --ns) {
+            sf = min(STAGE_FLOATS_MAX, avail / ns) & ~31;
+            if (sf >= 4 * max_npad) break;
+        }
+        if (ns < 2) {
+            ns = 2;
+            sf = (avail / ns) & ~31;
+            if (sf < max_npad) return fail(PMB_E_UNSUPPORTED, "network too wide for the shared-memory ring");
+        }
+        S.nstages = ns; S.stage_floats = sf;
+        int cps = 0;
+        for (int n = 0; n < 2; ++n) {
+            NetSweep &net = const_cast<NetSweep &>(*order[n]);
+            for (int i = 0; i < net.nlin; ++i) {
+                int l = reverse ? net.nlin - 1 - i : i;
+                Lin &L = net.lin[l];
+                if (!L.streamed) continue;
+                L.kc = min(L.K, sf / L.Npad);
+                L.nchunks = (L.K + L.kc - 1) / L.kc;
+                StreamItem &it = S.sched[S.nsched++];
+                it.goff = L.goff; it.kc = L.kc; it.nchunks = L.nchunks; it.K = L.K; it.Npad = L.Npad;
+                cps += L.nchunks;
+            }
+        }
+        S.chunks_per_step = cps;
+        off += ns * sf;
+    }
+    if (off > SMEM_LIMIT_FLOATS) return fail(PMB_E_UNSUPPORTED, "shared-memory plan needs %d bytes > 227 KB", off * 4);
+    return off * 4;
+}
+
+static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
+    if (!p) return fail(PMB_E_INVALID, "problem is NULL");
+    if (p->N < 1 || p->H < 1 || p->D < 1 || p->U < 1) return fail(PMB_E_INVALID, "N, H, D, U must be >= 1");
+    if (p->D + p->U > PMB_MAX_STATE) return fail(PMB_E_UNSUPPORTED, "D+U=%d > %d", p->D + p->U, PMB_MAX_STATE);
+    if (p->rew_rows < 1 || p->rew_rows > PMB_MAX_REWARD_ROWS) return fail(PMB_E_INVALID, "rew_rows=%d", p->rew_rows);
+    if (!p->act_scale || !p->act_bias || !p->mx || !p->iSx || !p->my || !p->Sy || !p->rew_C || !p->rew_c0 ||
+        !p->rew_Q || !p->rew_R)
+        return fail(PMB_E_INVALID, "a scaler / reward pointer is NULL");
+    int rc;
+    if ((rc = check_net(p->pol, p->D, p->pol.has_density ? 2 * p->U : p->U, "policy"))) return rc;
+    if ((rc = check_net(p->dyn, p->D + p->U, p->dyn.has_density ? 2 * p->D : p->D, "dynamics"))) return rc;
+    if (p->mm_states || p->mm_rewards) return fail(PMB_E_UNSUPPORTED, "moment matching is not built into this library version");
+
+    memset(&pl, 0, sizeof(pl));
+    int P = tune && tune->particles_per_cta ? tune->particles_per_cta : 0;
+    if (P == 0) P = (p->N > 8 * 148) ? 8 : 4;
+    if (P != 1 && P != 2 && P != 4 && P != 8) return fail(PMB_E_INVALID, "particles_per_cta must be 1, 2, 4 or 8");
+    pl.P = P;
+    pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
+    if (pl.stream_mode != 1 && pl.stream_mode != 2) return fail(PMB_E_INVALID, "stream_mode must be 1 or 2");
+    pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : 64;
+    if (pl.nsplit < 1 || pl.nsplit > 1024) return fail(PMB_E_INVALID, "wgrad_splits outside [1,1024]");
+
+    Alloc wf, wb, ws;
+    long long dummy[2] = {0, 0};
+    SweepParams &F = pl.fwd, &B = pl.bwd;
+    plan_net(p->pol, p->N, p->H, true, F.pol, B.pol, pl, wf, wb, ws, dummy);
+    plan_net(p->dyn, p->N, p->H, false, F.dyn, B.dyn, pl, wf, wb, ws, dummy);
+    // packed weight areas live after the generic regions
+    pl.wpack_fwd_off = ws.take(wf.top);
+    pl.wpack_bwd_off = ws.take(wb.top);
+    // flat gradient layout + weight-gradient jobs
+    long long np = 0;
+    pl.n_wg = p->pol.n_linear;
+    const int L = p->pol.n_linear - 1;
+    for (int l = 0; l <= L; ++l) {
+        WGrad &g = pl.wg[l];
+        const int out_l = p->pol.dims[l + 1], in_l = p->pol.dims[l];
+        g.delta_off = F.pol.delta_off[l];
+        g.lda = (l < L) ? round4(out_l) : out_l;
+        g.M = out_l;
+        g.inp_off = (l == 0) ? -1 : F.pol.saved_off[l - 1];
+        g.ldb = (l == 0) ? in_l : round4(in_l);
+        g.Nc = in_l;
+        g.w_off = np; np += (long long)out_l * in_l;
+        g.b_off = -1;
+        if (p->pol.b[l]) { g.b_off = np; np += out_l; }
+    }
+    pl.nparam = np;
+    pl.part_off = ws.take((long long)pl.nsplit * np);
+    pl.ws_floats = ws.top;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        SweepParams &S = pass ? B : F;
+        S.N = p->N; S.H = p->H; S.D = p->D; S.U = p->U;
+        S.act_scale = p->act_scale; S.act_bias = p->act_bias;
+        S.mx = p->mx; S.iSx = p->iSx; S.my = p->my; S.Sy = p->Sy;
+        S.KR = p->rew_rows; S.rew_C = p->rew_C; S.rew_c0 = p->rew_c0; S.rew_Q = p->rew_Q; S.rew_R = p->rew_R;
+        S.rew_scale = p->rew_scale; S.rew_offset = p->rew_offset;
+    }
+    const NetSweep *fo[2] = {&F.pol, &F.dyn};
+    const NetSweep *bo[2] = {&B.dyn, &B.pol};
+    if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode)) < 0) return rc;
+    pl.smem_fwd_bytes = rc;
+    if ((rc = plan_sweep(B, bo, true, P, pl.stream_mode)) < 0) return rc;
+    pl.smem_bwd_bytes = rc;
+    return PMB_OK;
+}
+
+static void resolve(Plan &pl, float *ws) {
+    for (int i = 0; i < pl.jobs.n; ++i) {
+        long long v = pl.job_dst_off[i];
+        int area = (int)(v >> 60);
+        long long off = v & ((1LL << 60) - 1);
+        long long base = area == 0 ? pl.wpack_fwd_off : area == 1 ? pl.wpack_bwd_off : 0;
+        pl.jobs.job[i].dst = ws + base + off;
+    }
+    pl.fwd.ws = pl.bwd.ws = ws;
+    pl.fwd.wpack = ws + pl.wpack_fwd_off;
+    pl.bwd.wpack = ws + pl.wpack_bwd_off;
+}
+
+}  // namespace pmb
+
+using namespace pmb;
+
+#define PMB_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return fail(PMB_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+int pmb_abi_version(void) { return PMB_ABI_VERSION; }
+
+const char *pmb_last_error(void) { return g_err; }
+
+int pmb_check_problem(const pmb_problem *p, const pmb_tuning *tune) {
+    Plan pl;
+    return build_plan(p, tune, pl);
+}
+
+size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune) {
+    Plan pl;
+    if (build_plan(p, tune, pl) != PMB_OK) return 0;
+    return (size_t)pl.ws_floats * sizeof(float);
+}
+
+size_t pmb_policy_param_count(const pmb_problem *p) {
+    if (!p) return 0;
+    size_t n = 0;
+    for (int l = 0; l < p->pol.n_linear; ++l) {
+        n += (size_t)p->pol.dims[l + 1] * p->pol.dims[l];
+        if (p->pol.b[l]) n += p->pol.dims[l + 1];
+    }
+    return n;
+}
+
+int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const float *x0, float *states,
+                        float *actions, float *rewards, void *workspace, size_t workspace_bytes,
+                        int *status_dev, void *stream) {
+    Plan pl;
+    int rc = build_plan(p, tune, pl);
+    if (rc != PMB_OK) return rc;
+    if (!x0 || !states || !actions || !rewards || !workspace) return fail(PMB_E_INVALID, "NULL tensor argument");
+    if (workspace_bytes < (size_t)pl.ws_floats * sizeof(float))
+        return fail(PMB_E_WORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, (size_t)pl.ws_floats * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    resolve(pl, (float *)workspace);
+    const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 1 pack, 2 sweep
+    if (status_dev) PMB_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
+    if (phases & 1) PMB_CUDA(launch_pack(pl.jobs, st));
+    SweepParams &F = pl.fwd;
+    F.x0 = x0; F.states = states; F.actions = actions; F.rewards = rewards; F.status = status_dev;
+    if (phases & 2) PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
+    return PMB_OK;
+}
+
+int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const float *states, const float *actions,
+                         const float *rewards, const float *g_states, const float *g_actions,
+                         const float *g_rewards, float *grad_flat, float *dx0, void *workspace,
+                         size_t workspace_bytes, void *stream) {
+    Plan pl;
+    int rc = build_plan(p, tune, pl);
+    if (rc != PMB_OK) return rc;
+    if (!states || !actions || !rewards || !grad_flat || !workspace) return fail(PMB_E_INVALID, "NULL tensor argument");
+    if (workspace_bytes < (size_t)pl.ws_floats * sizeof(float))
+        return fail(PMB_E_WORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, (size_t)pl.ws_floats * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    float *ws = (float *)workspace;
+    resolve(pl, ws);
+    SweepParams &B = pl.bwd;
+    B.states = const_cast<float *>(states); B.actions = const_cast<float *>(actions);
+    B.rewards = const_cast<float *>(rewards);
+    B.g_states = g_states; B.g_actions = g_actions; B.g_rewards = g_rewards; B.dx0 = dx0;
+    const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
+    if (phases & 2) PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));
+    if (!(phases & 4)) return PMB_OK;
+    // batched policy weight gradient over the (H*N) axis
+    const long long R = (long long)p->H * p->N;
+    float *part = ws + pl.part_off;
+    for (int l = 0; l < pl.n_wg; ++l) {
+        const WGrad &g = pl.wg[l];
+        const float *A = ws + g.delta_off;
+        const float *Bm = g.inp_off < 0 ? states : ws + g.inp_off;
+        PMB_CUDA(launch_wgrad(A, g.lda, g.M, Bm, g.ldb, g.Nc, R, pl.nsplit, part + g.w_off, pl.nparam, st));
+        if (g.b_off >= 0)
+            PMB_CUDA(launch_wgrad(A, g.lda, g.M, nullptr, 0, 1, R, pl.nsplit, part + g.b_off, pl.nparam, st));
+    }
+    PMB_CUDA(launch_reduce_partials(part, pl.nparam, pl.nsplit, grad_flat, st));
+    return PMB_OK;
+}
+
+int pmb_clip_adam_step(const pmb_adam_tensor *table_dev, int n_tensors, float max_norm, float lr, float beta1,
+                       float beta2, float eps, long long step, long long *step_dev, float *scratch_dev,
+                       void *stream) {
+    if (!table_dev || n_tensors < 1 || !scratch_dev || (!step_dev && step < 1))
+        return fail(PMB_E_INVALID, "bad optimiser arguments");
+    PMB_CUDA(launch_clip_adam(table_dev, n_tensors, max_norm, lr, beta1, beta2, eps, step, step_dev, scratch_dev,
+                              (cudaStream_t)stream));
+    return PMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// Host-side declarations shared by the translation units of libpmb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/pmb_b200.h"
+
+namespace pmb {
+
+struct SweepParams;
+
+struct PackJob {
+    const float *src;   // source matrix [SR][src_ld]
+    float *dst;         // destination [R][C], zero padded
+    int R, C, SR, SC, src_ld, transpose;
+};
+constexpr int MAX_PACK_JOBS = 64;
+struct PackJobs {
+    int n;
+    PackJob job[MAX_PACK_JOBS];
+};
+
+cudaError_t launch_pack(const PackJobs &jobs, cudaStream_t stream);
+cudaError_t launch_rollout_fwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb, int Nc, long long R, int nsplit,
+                         float *part, long long part_stride, cudaStream_t stream);
+cudaError_t launch_reduce_partials(const float *part, long long n, int nsplit, float *out, cudaStream_t stream);
+cudaError_t launch_clip_adam(const pmb_adam_tensor *tab, int nt, float max_norm, float lr, float beta1, float beta2,
+                             float eps, long long step, long long *step_dev, float *scratch, cudaStream_t stream);
+
+}  // namespace pmb

@@ -1,0 +1,436 @@
+"""Drop-in replacement for ``prob_mbrl.algorithms.mc_pilco`` (reference algorithms/mc_pilco.py:13-267).
+
+Same keyword list and the same per-iteration semantics (PEGASUS noise management, x0 perturbation,
+rollout, discounted return, backward, clip, optimiser step, x0 re-sampling, RuntimeError => resample
+and skip), with the rollout + back-propagation-through-time executed by the sm_100a library.
+
+Two execution paths:
+  * ``FusedIteration`` (default flag set of the deep_pilco examples: known reward, no value function,
+    no CVaR, torch.optim.Adam): the whole iteration -- weight packing, forward sweep, reverse sweep,
+    batched weight gradient, [NCCL all-reduce when torch.distributed is initialised], gradient clip
+    and Adam -- stays on the device with static buffers and no host synchronisation other than the
+    progress-bar read of the loss the reference does as well (algorithms/mc_pilco.py:215-216);
+  * the generic path: fused rollout as an autograd.Function + torch autograd for the loss variants
+    (value_func tail, CVaR subset, regulariser, arbitrary optimisers).
+"""
+import ctypes as C
+import os
+import weakref
+from collections import defaultdict
+
+import numpy as np
+import torch
+import tqdm
+
+from . import _lib, dist, operands
+from .operands import NotEligible
+from .rollout import backend, fused_rollout_tensors, rollout
+
+policy_update_counter = defaultdict(lambda: 0)   # persists across calls like the reference's (mc_pilco.py:8)
+_ENGINES = {}   # fused-iteration engines survive across mc_pilco calls (the examples call it once per episode)
+
+
+def tile(tensor, n):
+    """Repeat every row n times contiguously (reference utils/core.py:188-190)."""
+    return tensor.repeat_interleave(n, dim=0)
+
+
+def _discount_fn(discount, steps):
+    if discount is None:
+        return lambda i: 1.0 / steps
+    if callable(discount):
+        return discount
+    return lambda i: discount ** i
+
+
+class FusedIteration:
+    """Device-resident state of the fused policy-gradient iteration for one (N, H, module pair)."""
+
+    def __init__(self, dynamics, policy, x0, H, opt, g_rewards, clip_grad, mm=None, grad_sync=None):
+        self.lib = _lib.load()
+        N = x0.shape[0]
+        self.dynamics, self.policy, self.N, self.H = dynamics, policy, int(N), int(H)
+        self.opt, self.clip = opt, (float(clip_grad) if clip_grad is not None else 0.0)
+        self.mm = mm or dict(mm_states=False, mm_rewards=False, mm_groups=None, z_mm=None, z_rr=None)
+        self.grad_sync = grad_sync
+        self.params = [p for p in policy.parameters() if p.requires_grad]
+        self.dev = self.params[0].device
+        self.g_rewards = g_rewards.to(self.dev, torch.float32).contiguous()
+        self.tune = _lib.make_tuning()
+        self.static = {}
+        self.prob = None
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.x0 = x0.detach().to(**f32).clone()
+        self.refresh()
+        D, U = self.ops.D, self.ops.U
+        self.states = torch.empty(H + 1, N, D, **f32)
+        self.actions = torch.empty(H, N, U, **f32)
+        self.rewards = torch.empty(H, N, **f32)
+        self.weighted = torch.empty(H, N, **f32)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.nbytes = self.lib.pmb_workspace_bytes(C.byref(self.prob), C.byref(self.tune))
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev)
+        self.nparam = int(self.lib.pmb_policy_param_count(C.byref(self.prob)))
+        self.grad_flat = torch.zeros(self.nparam, **f32)
+        self.dx0 = torch.empty(N, D, **f32)
+        self.scratch = torch.zeros(1024, **f32)
+        self.loss = torch.zeros((), **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        # p.grad become views of the flat gradient (what NCCL reduces and clip+Adam consume)
+        off = 0
+        self.grad_views = []
+        for p in self.params:
+            self.grad_views.append(self.grad_flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        if off != self.nparam:
+            raise RuntimeError("policy has %d trainable scalars, the library expects %d" % (off, self.nparam))
+        self._init_adam()
+
+    # -- operands ------------------------------------------------------------------------------
+    def _static_copy(self, key, t):
+        """Masks / noise are re-assigned (``.data =``) by the modules on resample (reference
+        models/modules.py:44, densities.py:85): keep device-stable copies so captured graphs and the
+        problem descriptor stay valid."""
+        buf = self.static.get(key)
+        if buf is None or buf.shape != t.shape:
+            buf = torch.empty_like(t, memory_format=torch.contiguous_format)
+            self.static[key] = buf
+            self.prob = None
+        buf.copy_(t)
+        return buf
+
+    def refresh(self):
+        """(Re)read the modules after a resample(); rebuilds the descriptor only when a pointer moved."""
+        N = self.N
+        try:
+            ops = operands.extract(self.dynamics, self.policy, N)
+        except NotEligible as e:
+            if "buffer" not in str(e):
+                raise
+            operands.materialize_noise(self.dynamics, self.policy, self.x0)
+            ops = operands.extract(self.dynamics, self.policy, N)
+        for tag, net in (("pol", ops.pol), ("dyn", ops.dyn)):
+            for i, m in enumerate(net.mask):
+                if m is not None:
+                    net.mask[i] = self._static_copy("%s_mask%d" % (tag, i), m[:N])
+            if net.z is not None:
+                net.z = self._static_copy(tag + "_z", net.z[:N])
+        mm = dict(self.mm)
+        for k in ("z_mm", "z_rr"):
+            if mm.get(k) is not None:
+                mm[k] = self._static_copy(k, mm[k][:N])
+        self.ops = ops
+        if self.prob is None:
+            self.prob, self.keep = _lib.make_problem(ops, N, self.H, **mm)
+            _lib.check_problem(self.prob, self.tune)
+            self.graph = None
+
+    # -- optimiser -----------------------------------------------------------------------------
+    def _init_adam(self):
+        opt = self.opt
+        g = opt.param_groups[0]
+        self.lr, (self.b1, self.b2), self.eps = float(g["lr"]), g["betas"], float(g["eps"])
+        entries = (_lib.PmbAdamTensor * len(self.params))()
+        for i, p in enumerate(self.params):
+            st = opt.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            entries[i].param = p.data_ptr()
+            entries[i].grad = self.grad_views[i].data_ptr()
+            entries[i].exp_avg = st["exp_avg"].data_ptr()
+            entries[i].exp_avg_sq = st["exp_avg_sq"].data_ptr()
+            entries[i].n = p.numel()
+        raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).clone()
+        self.adam_table = raw.to(self.dev)
+        self.adam_step = int(float(opt.state[self.params[0]]["step"]))
+        self.step_dev.fill_(self.adam_step)
+        self._adam_ptr0 = opt.state[self.params[0]]["exp_avg"].data_ptr()
+
+    @staticmethod
+    def adam_is_plain(opt, params):
+        if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+            return False
+        g = opt.param_groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+            return False
+        if g.get("capturable", False) or g.get("differentiable", False) or g.get("fused", None):
+            return False
+        if torch.is_tensor(g["lr"]):
+            return False
+        return [id(p) for p in g["params"]] == [id(p) for p in params]
+
+    # -- one iteration -------------------------------------------------------------------------
+    def _enqueue(self):
+        lib, st = self.lib, _lib.current_stream_ptr()
+        pb, tb = C.byref(self.prob), C.byref(self.tune)
+        _lib.check(lib.pmb_rollout_forward(pb, tb, self.x0.data_ptr(), self.states.data_ptr(),
+                                           self.actions.data_ptr(), self.rewards.data_ptr(), self.ws.data_ptr(),
+                                           self.nbytes, self.status.data_ptr(), st))
+        _lib.check(lib.pmb_rollout_backward(pb, tb, self.states.data_ptr(), self.actions.data_ptr(),
+                                            self.rewards.data_ptr(), None, None, self.g_rewards.data_ptr(),
+                                            self.grad_flat.data_ptr(), self.dx0.data_ptr(), self.ws.data_ptr(),
+                                            self.nbytes, st))
+        torch.mul(self.rewards, self.g_rewards, out=self.weighted)
+        torch.sum(self.weighted.view(-1), 0, out=self.loss)
+        if self.grad_sync is not None:
+            self.grad_sync(self.grad_flat, self.loss)
+        _lib.check(lib.pmb_clip_adam_step(self.adam_table.data_ptr(), len(self.params), self.clip, self.lr,
+                                          self.b1, self.b2, self.eps, 0, self.step_dev.data_ptr(),
+                                          self.scratch.data_ptr(), st))
+
+    def step(self, x0):
+        """Run one iteration from particles ``x0`` (device tensor [N, D]); returns the loss tensor."""
+        self.x0.copy_(x0, non_blocking=True)
+        use_graph = os.environ.get("PMB_CUDA_GRAPH", "1") != "0" and self.grad_sync is None
+        if use_graph:
+            if self.graph is None:
+                # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
+                self._sync_adam_counter()
+                saved = [t.clone() for t in self._mutable_state()]
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._enqueue()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                for t, v in zip(self._mutable_state(), saved):
+                    t.copy_(v)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._enqueue()
+                for t, v in zip(self._mutable_state(), saved):
+                    t.copy_(v)
+            self.graph.replay()
+        else:
+            self._enqueue()
+        self.adam_step += 1
+        for p, gview in zip(self.params, self.grad_views):
+            p.grad = gview
+            self.opt.state[p]["step"] += 1
+        return self.loss
+
+    def _mutable_state(self):
+        out = [self.step_dev]
+        for p in self.params:
+            st = self.opt.state[p]
+            out += [p.data, st["exp_avg"], st["exp_avg_sq"]]
+        return out
+
+    def _sync_adam_counter(self):
+        self.step_dev.fill_(self.adam_step)
+
+    def resync(self):
+        """Re-attach to the modules / optimiser at the start of another mc_pilco call."""
+        self.refresh()
+        st = self.opt.state[self.params[0]]
+        if len(st) == 0 or st["exp_avg"].data_ptr() != self._adam_ptr0:
+            self._init_adam()        # optimiser state was reset or reloaded
+            self.graph = None
+        self.adam_step = int(float(self.opt.state[self.params[0]]["step"]))
+        self._sync_adam_counter()
+
+
+def _on_device_loop_ok(value_func, cvar_eps, reg_weight, prioritized_replay, opt, policy, on_rollout, debug,
+                       rollout_kwargs):
+    if value_func is not None or prioritized_replay or reg_weight > 0 or debug or rollout_kwargs:
+        return False
+    if cvar_eps > -1.0 and cvar_eps < 1.0 and cvar_eps != 0:
+        return False
+    if callable(on_rollout):
+        return False   # runs between rollout and backward in the reference
+    params = [p for p in policy.parameters() if p.requires_grad]
+    return FusedIteration.adam_is_plain(opt, params)
+
+
+def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters=1000, value_func=None,
+             pegasus=True, mm_states=False, mm_rewards=False, mm_groups=None, maximize=True, clip_grad=1.0,
+             cvar_eps=0.0, reg_weight=0.0, discount=None, on_rollout=None, on_iteration=None,
+             step_idx_to_sample=None, init_state_noise=0.0, resampling_period=99, prioritized_replay=False,
+             priority_alpha=0.6, priority_eps=1e-8, init_priority_beta=1.0, priority_beta_increase=0.0,
+             debug=False, rollout_kwargs={}):
+    """MC-PILCO policy search: ``opt_iters`` policy-gradient iterations on imagined particle rollouts."""
+    global policy_update_counter
+    if prioritized_replay:
+        raise NotEligible("prioritized_replay needs per-step action-gradient hooks (reference "
+                          "algorithms/mc_pilco.py:184-188); use the reference loop for it")
+    dynamics.eval()
+    policy.train()
+    H = int(steps)
+    disc = _discount_fn(discount, H)
+    msg = "Pred. Cumm. rewards: %f" if maximize else "Pred. Cumm. costs: %f"
+    if opt is None:
+        opt = torch.optim.Adam([p for p in policy.parameters() if p.requires_grad])
+    dev, dt = dynamics.X.device, dynamics.X.dtype
+    D = init_states.shape[-1]
+    # noise tables for moment matching: drawn on the host generator like the reference (mc_pilco.py:57-62)
+    z_mm = torch.randn(H + init_states.shape[0], *init_states.shape[1:]).reshape(-1, D).to(dev, dt)
+    z_rr = torch.randn(H + init_states.shape[0], 1).reshape(-1, 1).to(dev, dt)
+
+    def resample():
+        seed = torch.randint(2 ** 32, [1])
+        dynamics.resample(seed=seed)
+        policy.resample(seed=seed)
+        if value_func is not None:
+            value_func.resample(seed=seed)
+        z_mm.normal_()
+        z_rr.normal_()
+
+    resample()
+    x0 = init_states
+    N_particles = init_states.shape[0]
+    n_opt_steps = policy_update_counter[policy]
+    mode = backend()
+    rank, world = dist.world()
+    sharder = None
+    if world > 1:
+        if mm_states or mm_rewards:
+            raise NotEligible("moment matching across ranks needs a per-step reduction (SURVEY.md 8e/8f)")
+        sharder = dist.ShardedNoise(dynamics, policy, N_particles, rank, world)
+    fast = (mode != "eager" and dev.type == "cuda"
+            and _on_device_loop_ok(value_func, cvar_eps, reg_weight, prioritized_replay, opt, policy,
+                                   on_rollout, debug, rollout_kwargs))
+    engine = None
+    pbar = tqdm.tqdm(range(opt_iters), total=opt_iters, disable=os.environ.get("PMB_NO_PBAR") == "1")
+    pbar_every = max(1, int(os.environ.get("PMB_PBAR_EVERY", "1")))
+    sign = -1.0 if maximize else 1.0
+
+    for i in pbar:
+        need_resample = (not pegasus) or n_opt_steps % resampling_period == 0
+        if need_resample:
+            if sharder is not None:
+                sharder.widen()
+            resample()
+        x0_ = x0
+        if mm_groups is not None and x0_.shape[0] == mm_groups:
+            x0_ = tile(x0_, int(N_particles / mm_groups))
+        x0_ = x0_.to(dev, dt)
+        x0_ = x0_ + init_state_noise * torch.randn_like(x0_)
+        if sharder is not None:
+            # every rank holds the full-N noise (identical seeds); take this rank's rows of everything
+            if sharder.full is None:
+                try:
+                    operands.extract(dynamics, policy, x0_.shape[0])
+                except NotEligible as e:
+                    if "buffer" not in str(e):
+                        raise
+                    operands.materialize_noise(dynamics, policy, x0_.detach())
+                sharder.narrow()
+            x0_ = x0_[sharder.row0:sharder.row0 + sharder.n]
+        Nloc = x0_.shape[0]
+        try:
+            if fast and pegasus:
+                if engine is None or engine.N != Nloc:
+                    weights = tuple(sign * disc(t) for t in range(H))
+                    key = (id(policy), id(dynamics), id(opt), Nloc, H, clip_grad, weights, world,
+                           bool(mm_states), bool(mm_rewards), mm_groups)
+                    hit = _ENGINES.get(key)
+                    if hit is not None and hit[0]() is policy and hit[1]() is opt:
+                        engine = hit[2]
+                        engine.mm.update(z_mm=z_mm if mm_states else None, z_rr=z_rr if mm_rewards else None)
+                        engine.x0.copy_(x0_)
+                        engine.resync()
+                    else:
+                        g_r = torch.tensor(weights, dtype=torch.float32, device=dev)
+                        g_r = (g_r / (Nloc * world))[:, None].expand(H, Nloc).contiguous()
+                        sync = dist.allreduce_gradient if world > 1 else None
+                        engine = FusedIteration(dynamics, policy, x0_, H, opt, g_r, clip_grad,
+                                                dict(mm_states=mm_states, mm_rewards=mm_rewards, mm_groups=mm_groups,
+                                                     z_mm=z_mm if mm_states else None,
+                                                     z_rr=z_rr if mm_rewards else None), sync)
+                        if len(_ENGINES) > 8:
+                            _ENGINES.clear()
+                        _ENGINES[key] = (weakref.ref(policy), weakref.ref(opt), engine)
+                elif need_resample:
+                    engine.refresh()
+                loss = engine.step(x0_)
+                S, A, R = engine.states, engine.actions, engine.rewards
+                if mm_states or mm_rewards:
+                    bad = int(engine.status.item())
+                    if bad:
+                        raise RuntimeError("moment matching: covariance not positive-definite at step %d" % (bad - 1))
+            else:
+                policy.zero_grad()
+                dynamics.zero_grad()
+                opt.zero_grad()
+                if mode == "eager":
+                    traj = rollout(x0_, dynamics, policy, H, resample_state_noise=not pegasus,
+                                   resample_action_noise=not pegasus, mm_states=mm_states, mm_rewards=mm_rewards,
+                                   z_mm=z_mm if pegasus else None, z_rr=z_rr if pegasus else None,
+                                   mm_groups=mm_groups, **rollout_kwargs)
+                    S, A = torch.stack(traj[0]), torch.stack(traj[1])
+                    R = torch.stack(traj[2]).squeeze(-1)
+                    lists = traj
+                else:
+                    S, A, R, status = fused_rollout_tensors(
+                        x0_, dynamics, policy, H, mm_states, mm_rewards, z_mm if pegasus else None,
+                        z_rr if pegasus else None, mm_groups, not pegasus, not pegasus)
+                    lists = None
+                    if (mm_states or mm_rewards) and int(status.item()):
+                        raise RuntimeError("moment matching: covariance not positive-definite at step %d"
+                                           % (int(status.item()) - 1))
+                if callable(on_rollout):
+                    lists = lists or _as_lists(S, A, R)
+                    on_rollout(i, lists[0], lists[1], lists[2], disc)
+                w = torch.tensor([disc(t) for t in range(R.shape[0])], dtype=R.dtype, device=R.device)
+                total = (R * w[:, None]).sum(0)
+                if value_func is not None:
+                    Vend = value_func(S[-1], resample=False, return_samples=True)
+                    total = total + disc(H) * Vend.reshape(-1)
+                returns = -total if maximize else total
+                if cvar_eps > -1.0 and cvar_eps < 1.0 and cvar_eps != 0:
+                    rd = returns.detach().cpu().numpy()
+                    if cvar_eps > 0:
+                        returns = returns[torch.as_tensor(rd < np.quantile(rd, cvar_eps), device=returns.device)]
+                    else:
+                        returns = returns[torch.as_tensor(rd > np.quantile(rd, -cvar_eps), device=returns.device)]
+                loss = returns.mean()
+                if reg_weight > 0:
+                    loss = loss + reg_weight * policy.regularization_loss()
+                loss.backward()
+                if world > 1:
+                    for p in policy.parameters():
+                        if p.grad is not None:
+                            torch.distributed.all_reduce(p.grad)
+                            p.grad /= world
+                if clip_grad is not None:
+                    torch.nn.utils.clip_grad_norm_(policy.parameters(), clip_grad)
+                opt.step()
+        except RuntimeError:
+            import traceback
+            traceback.print_exc()
+            print("RuntimeError")
+            if sharder is not None:
+                sharder.widen()
+            resample()
+            if sharder is not None:
+                sharder.narrow()
+            if engine is not None:
+                engine.refresh()
+            policy.zero_grad()
+            dynamics.zero_grad()
+            opt.zero_grad()
+            continue
+        n_opt_steps += 1
+        if (i + 1) % pbar_every == 0 or i + 1 == opt_iters:
+            pbar.set_description((msg % float(R.detach().sum(0).mean())) + " [{0}]".format(R.shape[0]))
+        if callable(on_iteration):
+            lists = _as_lists(S, A, R)
+            on_iteration(i, loss, lists[0], lists[1], lists[2], disc)
+        if exp is not None:
+            nsamp = mm_groups if mm_groups is not None else N_particles
+            x0 = exp.sample_states(nsamp, timestep=step_idx_to_sample).to(dev, dt)
+            init_states = x0
+        else:
+            x0 = init_states.detach()
+
+    if sharder is not None:
+        sharder.widen()
+    policy.eval()
+    dynamics.eval()
+    policy_update_counter[policy] = n_opt_steps
+
+
+def _as_lists(S, A, R):
+    return [list(S.unbind(0)), list(A.unbind(0)), list(R.unsqueeze(-1).unbind(0))]

@@ -27,8 +27,11 @@ from typing import List, Optional
 import torch
 
 
-class NotEligible(RuntimeError):
-    """The module graph / flag combination is outside the fused rollout's scope."""
+class NotEligible(ValueError):
+    """The module graph / flag combination is outside the fused rollout's scope.
+
+    Deliberately NOT a RuntimeError: ``mc_pilco`` treats RuntimeError as a numerical failure of one
+    iteration (reference algorithms/mc_pilco.py:122-131) and would silently skip every iteration."""
 
 
 @dataclass

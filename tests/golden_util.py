@@ -35,3 +35,44 @@ def rel_l2(a, b):
     a = torch.cat([x.reshape(-1).double() for x in a]) if isinstance(a, (list, tuple)) else a.reshape(-1).double()
     b = torch.cat([x.reshape(-1).double() for x in b]) if isinstance(b, (list, tuple)) else b.reshape(-1).double()
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def modules_from_ops(ops, device="cpu"):
+    """Rebuild (dynamics, policy) mirror modules whose tensors equal a fixture's operand bundle."""
+    from prob_mbrl_b200 import models, rewards
+    D, U = int(ops["D"]), int(ops["U"])
+    Lp, Ld = int(ops["pol_L"]), int(ops["dyn_L"])
+    hid_p = [ops["pol_W%d" % i].shape[0] for i in range(Lp)]
+    hid_d = [ops["dyn_W%d" % i].shape[0] for i in range(Ld)]
+    from functools import partial
+    reward = rewards.CartpoleReward() if D == 5 else rewards.DoubleCartpoleReward()
+    dyn_net = models.mlp(D + U, 2 * D, hid_d, dropout_layers=[models.CDropout(0.1 * torch.ones(h)) for h in hid_d])
+    dyn = models.DynamicsModel(dyn_net, reward_func=reward, output_density=models.DiagGaussianDensity(D)).float()
+    pol_net = models.mlp(D, 2 * U, hid_p, dropout_layers=[models.BDropout(1.0 - float(ops["pol_p%d" % i])) for i in range(Lp)],
+                         output_nonlin=partial(models.DiagGaussianDensity, U))
+    maxU = (ops["act_scale"] + ops["act_bias"]).numpy()
+    minU = (ops["act_bias"] - ops["act_scale"]).numpy()
+    pol = models.Policy(pol_net, maxU, minU).float()
+    with torch.no_grad():
+        for tag, net, L in (("pol", pol.model, Lp), ("dyn", dyn.model, Ld)):
+            for i in range(L + 1):
+                fc = getattr(net, "fc%d" % i) if i < L else net.fc_out
+                fc.weight.copy_(ops["%s_W%d" % (tag, i)])
+                fc.bias.copy_(ops["%s_b%d" % (tag, i)])
+        for i in range(Lp):
+            drop = getattr(pol.model, "drop%d" % i)
+            drop.noise.data = ops["pol_mask%d" % i].clone()
+        for i in range(Ld):
+            drop = getattr(dyn.model, "drop%d" % i)
+            drop.noise.data = torch.rand_like(ops["dyn_mask%d" % i])
+            drop.concrete_noise = ops["dyn_mask%d" % i].clone()
+        pol.model.fc_nonlin.z.data = ops["pol_z"].clone()
+        dyn.output_density.z.data = ops["dyn_z"].clone()
+        for k in ("mx", "iSx", "my", "Sy"):
+            getattr(dyn, k).data = ops[k].reshape(1, -1).clone()
+        dyn.Sx.data = dyn.iSx.reciprocal()
+        dyn.iSy.data = dyn.Sy.reciprocal()
+        dyn.X.data = torch.zeros(1, D + U)
+    dyn.eval()
+    pol.train()
+    return dyn.to(device), pol.to(device)

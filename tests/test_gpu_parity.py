@@ -1,0 +1,217 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, entered through the C ABI
+(libpmb_b200.so via ctypes), against (a) the golden fixtures produced by the unmodified reference and
+(b) the CPU oracle on the same seeded inputs.  Tolerances are the fp32 budgets of SURVEY.md App. C.3
+(no-mm H<=40: states/rewards atol 2e-6, actions atol 2e-5, loss rtol 1e-6, policy-grad rel-L2 1e-5;
+H=400 bounded fixture: grad rel-L2 1e-4)."""
+import os
+
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import rollout_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops_cuda(ops):
+    from prob_mbrl_b200.operands import RolloutOperands
+    return RolloutOperands.from_flat(ops, device="cuda")
+
+
+def _run(ops, x0, H, cot="loss", env=None, gen_seed=0):
+    """forward + backward through the fused autograd.Function; returns dict of cpu tensors."""
+    from prob_mbrl_b200.rollout import FusedRolloutFunction
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        o = _ops_cuda(ops)
+        params = [p.requires_grad_(True) for p in o.policy_parameters()]
+        x = x0.cuda().clone().requires_grad_(True)
+        N = x.shape[0]
+        mm = dict(mm_states=False, mm_rewards=False, mm_groups=None, z_mm=None, z_rr=None)
+        S, A, R, status = FusedRolloutFunction.apply(x, (o, N, H, mm), *params)
+        if cot == "loss":
+            obj = -(R.sum(0) / H).mean()
+            cots = None
+        else:
+            g = torch.Generator().manual_seed(gen_seed)
+            gS = torch.randn(H + 1, N, o.D, generator=g, dtype=torch.float64)
+            gA = torch.randn(H, N, o.U, generator=g, dtype=torch.float64)
+            gR = torch.randn(H, N, generator=g, dtype=torch.float64)
+            obj = (S * gS.float().cuda()).sum() + (A * gA.float().cuda()).sum() + (R * gR.float().cuda()).sum()
+            cots = (gS, gA, gR)
+        grads = torch.autograd.grad(obj, params + [x])
+        torch.cuda.synchronize()
+        return {"S": S.detach().cpu(), "A": A.detach().cpu(), "R": R.detach().cpu(), "obj": obj.detach().cpu(),
+                "grads": [g.cpu() for g in grads[:-1]], "dx0": grads[-1].cpu(), "cots": cots}
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["cartpole_200x2_n25_h40", "dcartpole_48x3_n24_h30", "cartpole_37x2_n7_h12"])
+def test_rollout_and_gradient_match_reference_golden(name):
+    ops, g = gu.load(name)
+    H = int(g["H"])
+    r = _run(ops, g["x0"], H)
+    assert (r["S"] - g["nomm_states"]).abs().max() < 2e-6
+    assert (r["A"] - g["nomm_actions"]).abs().max() < 2e-5
+    assert (r["R"] - g["nomm_rewards"]).abs().max() < 2e-6
+    assert abs(float(r["obj"]) - float(g["nomm_loss"])) <= 1e-6 * abs(float(g["nomm_loss"])) + 1e-8
+    assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
+    assert gu.rel_l2(r["dx0"], g["nomm_dx0"]) < 1e-5
+
+
+def test_c2_full_size_matches_reference_golden():
+    """BASELINE.json configs[1]: Cartpole 2x[200], 100 particles, H=400."""
+    ops, g = gu.load("cartpole_200x2_n100_h400")
+    H, thin = int(g["H"]), int(g["thin"])
+    r = _run(ops, g["x0"], H)
+    assert (r["S"][::thin] - g["nomm_states"]).abs().max() < 5e-5
+    assert abs(float(r["obj"]) - float(g["nomm_loss"])) <= 1e-6 * abs(float(g["nomm_loss"]))
+    assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-4
+    # error budget against the fp64 oracle: within a small multiple of the reference's own fp32 error
+    ops64, g64 = gu.load("cartpole_200x2_n100_h400", torch.float64)
+    r64 = orc.loss_and_grads(ops64, g64["x0"], H)
+    keys = orc.policy_param_keys(ops64)
+    assert gu.rel_l2(r["grads"], [r64["grads"][k] for k in keys]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["cartpole_37x2_n7_h12", "dcartpole_48x3_n24_h30"])
+def test_generic_cotangents_match_oracle_autograd(name):
+    """Arbitrary cotangents on states/actions/rewards (value-function tails, CVaR, callbacks)."""
+    ops, g = gu.load(name)
+    H = int(g["H"])
+    r = _run(ops, g["x0"], H, cot="generic")
+    ops64, g64 = gu.load(name, torch.float64)
+    keys = orc.policy_param_keys(ops64)
+    d = dict(ops64)
+    for k in keys:
+        d[k] = d[k].clone().requires_grad_(True)
+    x0 = g64["x0"].clone().requires_grad_(True)
+    S, A, R = orc.rollout(d, x0, H)
+    gS, gA, gR = r["cots"]
+    obj = (torch.stack(S) * gS).sum() + (torch.stack(A) * gA).sum() + (torch.stack(R).squeeze(-1) * gR).sum()
+    auto = torch.autograd.grad(obj, [d[k] for k in keys] + [x0])
+    assert gu.rel_l2(r["grads"], list(auto[:-1])) < 2e-5
+    assert gu.rel_l2(r["dx0"], auto[-1]) < 2e-5
+
+
+def test_stream_modes_are_bitwise_identical():
+    """TMA bulk-copy ring (mode 2) and synchronous copies (mode 1) feed the same arithmetic."""
+    ops, g = gu.load("cartpole_200x2_n25_h40")
+    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_STREAM_MODE": 1})
+    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_STREAM_MODE": 2})
+    assert torch.equal(a["S"], b["S"]) and torch.equal(a["R"], b["R"])
+    for x, y in zip(a["grads"], b["grads"]):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_particles_per_cta_variants(P):
+    ops, g = gu.load("cartpole_37x2_n7_h12")   # N=7: ragged last CTA for every P > 1
+    r = _run(ops, g["x0"], int(g["H"]), env={"PMB_PARTICLES_PER_CTA": P})
+    assert (r["S"] - g["nomm_states"]).abs().max() < 2e-6
+    assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
+
+
+def test_determinism():
+    ops, g = gu.load("cartpole_200x2_n25_h40")
+    a = _run(ops, g["x0"], int(g["H"]))
+    b = _run(ops, g["x0"], int(g["H"]))
+    for x, y in zip(a["grads"], b["grads"]):
+        assert torch.equal(x, y)
+
+
+def test_clip_adam_matches_torch():
+    import ctypes as C
+    from prob_mbrl_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    shapes = [(200, 5), (200,), (200, 200), (200,), (2, 200), (2,)]
+    ps = [torch.randn(s, device="cuda") for s in shapes]
+    gs = [torch.randn(s, device="cuda") * 3 for s in shapes]
+    ref_p = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.Adam(ref_p, lr=1e-3)
+    m = [torch.zeros_like(p) for p in ps]
+    v = [torch.zeros_like(p) for p in ps]
+    entries = (_lib.PmbAdamTensor * len(ps))()
+    for i in range(len(ps)):
+        entries[i].param, entries[i].grad = ps[i].data_ptr(), gs[i].data_ptr()
+        entries[i].exp_avg, entries[i].exp_avg_sq, entries[i].n = m[i].data_ptr(), v[i].data_ptr(), ps[i].numel()
+    table = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).clone().cuda()
+    scratch = torch.zeros(1024, device="cuda")
+    for step in range(1, 4):
+        for rp, g in zip(ref_p, gs):
+            rp.grad = g.clone()
+        norm = torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        opt.step()
+        _lib.check(lib.pmb_clip_adam_step(table.data_ptr(), len(ps), 1.0, 1e-3, 0.9, 0.999, 1e-8, step, None,
+                                          scratch.data_ptr(), _lib.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert abs(float(scratch[0]) - float(norm)) < 1e-3 * float(norm)
+        for p, rp in zip(ps, ref_p):
+            assert (p - rp.detach()).abs().max() < 2e-6
+        # clip scales .grad in place, like clip_grad_norm_: re-arm the gradients for the next step
+        for g, rp in zip(gs, ref_p):
+            g.copy_(torch.randn_like(g) * 3)
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+def test_mc_pilco_iterations_match_reference_golden(graph):
+    """The on-device iteration (rollout + BPTT + wgrad + clip + Adam) against the reference's own
+    algorithms.mc_pilco on identical noise: final parameters after 6 iterations."""
+    import prob_mbrl_b200 as pm
+    ops, g = gu.load("mcpilco_cartpole_32x2_n16_h10")
+    dyn, pol = gu.modules_from_ops(ops, "cuda")
+    opt = torch.optim.Adam(pol.parameters(), float(g["lr"]))
+    eng_env = {"PMB_CUDA_GRAPH": graph, "PMB_NO_PBAR": "1"}
+    old = {k: os.environ.get(k) for k in eng_env}
+    os.environ.update(eng_env)
+    try:
+        H, N = int(g["H"]), int(g["N"])
+        g_r = torch.full((H, N), -1.0 / (H * N), device="cuda")
+        eng = pm.FusedIteration(dyn, pol, g["x0"].cuda(), H, opt, g_r, 1.0)
+        losses = []
+        for _ in range(int(g["iters"])):
+            losses.append(float(eng.step(g["x0"].cuda())))
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert torch.allclose(torch.tensor(losses, dtype=torch.float64), g["losses"].double(), rtol=0, atol=5e-7)
+    for i, p in enumerate(pol.parameters()):
+        assert (p.detach().cpu() - g["final%d" % i]).abs().max() < 2e-6
+    assert int(float(opt.state[next(iter(pol.parameters()))]["step"])) == int(g["iters"])
+
+
+def test_drop_in_rollout_api_lists_and_autograd():
+    """rollout() keeps the reference's return convention and is differentiable end to end."""
+    import prob_mbrl_b200 as pm
+    ops, g = gu.load("cartpole_200x2_n25_h40")
+    dyn, pol = gu.modules_from_ops(ops, "cuda")
+    H = int(g["H"])
+    x0 = g["x0"].cuda().requires_grad_(True)
+    S, A, R = pm.rollout(x0, dyn, pol, H, resample_state_noise=False, resample_action_noise=False)
+    assert len(S) == H + 1 and len(A) == H and len(R) == H and R[0].shape == (25, 1)
+    loss = -(torch.stack(R).sum(0) / H).mean()
+    loss.backward()
+    grads = [p.grad.cpu() for p in pol.parameters()]
+    assert abs(float(loss) - float(g["nomm_loss"])) < 1e-7
+    assert gu.rel_l2(grads, gu.policy_grad_list(g, "nomm", ops)) < 1e-5
+    assert gu.rel_l2(x0.grad.cpu(), g["nomm_dx0"]) < 1e-5
+
+
+def test_unfused_configuration_raises_not_silently_falls_back():
+    import prob_mbrl_b200 as pm
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    dyn, pol = gu.modules_from_ops(ops, "cuda")
+    with pytest.raises(pm.NotEligible):
+        pm.rollout(g["x0"].cuda(), dyn, pol, 3, resample_model=True)
+    with pytest.raises(pm.NotEligible):
+        pm.rollout(g["x0"], dyn, pol, 3, resample_state_noise=False, resample_action_noise=False)  # CPU tensor
