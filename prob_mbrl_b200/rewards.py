@@ -39,8 +39,8 @@ class TipQuadraticReward(nn.Module):
     def tip_quadratic_form(self):
         M, norm = self.tip_matrix()
         M = M.to(self.Q.dtype)
-        tgt = to_complex(self.target, self.angle_dims) @ M.t()
-        return M / norm, (-tgt / norm).reshape(-1), self.Q.detach(), self.R.detach()
+        tgt = to_complex(self.target.detach().cpu(), self.angle_dims) @ M.t()
+        return M / norm, (-tgt / norm).reshape(-1), self.Q.detach().cpu(), self.R.detach().cpu()
 
     def forward(self, x, u):
         x = torch.as_tensor(x).to(device=self.Q.device, dtype=self.Q.dtype)
