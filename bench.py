@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--impl", default="fused", choices=["fused", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="value + per-kernel times only (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = args.config
@@ -263,6 +264,11 @@ def main():
     ms = float(t.item())
     value = n_global * H * args.steps / (ms * 1e-3)
     loss_val = float(eng.loss)
+
+    if args.quick:
+        print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "n_gpus": world,
+                          "tuning": {k: os.environ.get(k) for k in ("PMB_STREAM_MODE", "PMB_PARTICLES_PER_CTA")}}))
+        return
 
     # ---------------- e2e: public API, host buffers, H2D + D2H inside the timed region ----------------
     class HostStates:

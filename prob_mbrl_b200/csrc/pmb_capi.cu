@@ -152,77 +152,113 @@ static void plan_net(const pmb_net &net, int N, int H, bool is_policy, NetSweep 
 }
 
 // shared-memory carve-up + stream schedule of one sweep
-static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, int P, int stream_mode) {
+static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, int P, int stream_mode,
+                      int nstages_req) {
     int off = 0;
     S.nres = 0;
-    int tile_rows = 4;
     S.nsched = 0;
+    S.off_cst = off; off += (C_TOTAL + 31) & ~31;
+    int tile_rows = 4;
+    int max_npad = 0;
+    auto add_res = [&](long long goff, int soff, int n, int kind) {
+        S.res_goff[S.nres] = goff; S.res_soff[S.nres] = soff; S.res_n[S.nres] = n; S.res_ws[S.nres] = kind;
+        ++S.nres;
+    };
+    // resident weights + biases
     for (int n = 0; n < 2; ++n) {
         NetSweep &net = const_cast<NetSweep &>(*order[n]);
         for (int l = 0; l < net.nlin; ++l) {
             Lin &L = net.lin[l];
             tile_rows = max(tile_rows, max(L.K, L.Npad));
+            if (L.streamed) max_npad = max(max_npad, L.Npad);
             if (!L.streamed) {
                 int nfl = (L.kind == 0) ? L.K * L.Npad : L.Nout * L.K;
                 nfl = (nfl + 3) & ~3;
                 L.soff = off;
-                S.res_goff[S.nres] = L.goff;
-                S.res_soff[S.nres] = off;
-                S.res_n[S.nres] = nfl;
-                ++S.nres;
+                add_res(L.goff, off, nfl, 0);
+                off += (nfl + 31) & ~31;
+            }
+            L.bias_soff = -1;
+            if (!reverse && L.boff >= 0) {
+                int nfl = (L.Npad + 3) & ~3;
+                L.bias_soff = off;
+                add_res(L.boff, off, nfl, 1);
                 off += (nfl + 31) & ~31;
             }
         }
     }
-    S.res_floats = off;
-    S.hmax_pad = tile_rows;
     S.off_act0 = off; off += ((tile_rows * P) + 31) & ~31;
     S.off_act1 = off; off += ((tile_rows * P) + 31) & ~31;
     S.off_red = off;  off += 1024 * P;
-    S.off_misc = off; off += 128 * P;
-    S.off_stage = off;
-    // streamed layers in consumption order
-    int max_npad = 0;
+    S.off_misc = off; off += 320 * P;
+    // backward: two buffers for the stored hidden activations of a step
+    S.off_sav = off;
+    S.sav_floats = 0;
+    if (reverse) {
+        int sf = 0;
+        for (int n = 0; n < 2; ++n) {
+            NetSweep &net = const_cast<NetSweep &>(*order[n]);
+            for (int h = 0; h + 1 < net.nlin; ++h) {
+                net.sav_soff[h] = sf;
+                sf += P * net.lin[h + 1].Npad;      // bwd lin[h+1].Npad = padded width of hidden h
+            }
+        }
+        S.sav_floats = (sf + 31) & ~31;
+        off += 2 * S.sav_floats;
+    }
+    // dropout-mask rows of this CTA: resident when they leave room for a useful ring
+    int mask_floats = 0;
     for (int n = 0; n < 2; ++n) {
         const NetSweep &net = *order[n];
-        for (int i = 0; i < net.nlin; ++i) {
-            int l = reverse ? net.nlin - 1 - i : i;
-            if (net.lin[l].streamed) max_npad = max(max_npad, net.lin[l].Npad);
+        for (int h = 0; h + 1 < net.nlin; ++h) {
+            const int npad = reverse ? net.lin[h + 1].Npad : net.lin[h].Npad;
+            if (net.mask_off[h] >= 0) mask_floats += ((P * npad) + 31) & ~31;
         }
     }
+    const int ring_min = max_npad ? 2 * 16 * max_npad : 0;
+    const bool masks_resident = off + mask_floats + ring_min <= SMEM_LIMIT_FLOATS;
+    for (int n = 0; n < 2; ++n) {
+        NetSweep &net = const_cast<NetSweep &>(*order[n]);
+        for (int h = 0; h + 1 < net.nlin; ++h) {
+            net.mask_soff[h] = -1;
+            if (net.mask_off[h] >= 0 && masks_resident) {
+                const int npad = reverse ? net.lin[h + 1].Npad : net.lin[h].Npad;
+                net.mask_soff[h] = off;
+                add_res(net.mask_off[h], off, P * npad, npad);
+                off += ((P * npad) + 31) & ~31;
+            }
+        }
+    }
+    S.off_stage = off;
     S.stream_mode = stream_mode;
     if (max_npad == 0) {
         S.nstages = 1; S.stage_floats = 0; S.chunks_per_step = 0;
     } else {
-        int avail = SMEM_LIMIT_FLOATS - off;
-        int ns = 4;
-        int sf = 0;
-        for (; ns >= 2; --ns) {
-            sf = min(STAGE_FLOATS_MAX, avail / ns) & ~31;
-            if (sf >= 4 * max_npad) break;
-        }
-        if (ns < 2) {
-            ns = 2;
-            sf = (avail / ns) & ~31;
-            if (sf < max_npad) return fail(PMB_E_UNSUPPORTED, "network too wide for the shared-memory ring");
-        }
-        S.nstages = ns; S.stage_floats = sf;
-        int cps = 0;
+        const int avail = SMEM_LIMIT_FLOATS - off;
+        int ns = nstages_req >= 2 && nstages_req <= MAXS ? nstages_req : 2;
+        int sf = (avail / ns) & ~31;
+        while (ns > 2 && sf < 8 * max_npad) { --ns; sf = (avail / ns) & ~31; }
+        if (sf < max_npad) return fail(PMB_E_UNSUPPORTED, "network too wide for the shared-memory ring");
+        S.nstages = ns;
+        int cps = 0, sf_used = 0;
         for (int n = 0; n < 2; ++n) {
             NetSweep &net = const_cast<NetSweep &>(*order[n]);
             for (int i = 0; i < net.nlin; ++i) {
                 int l = reverse ? net.nlin - 1 - i : i;
                 Lin &L = net.lin[l];
                 if (!L.streamed) continue;
-                L.kc = min(L.K, sf / L.Npad);
-                L.nchunks = (L.K + L.kc - 1) / L.kc;
+                const int kcmax = sf / L.Npad;
+                L.nchunks = (L.K + kcmax - 1) / kcmax;
+                L.kc = (L.K + L.nchunks - 1) / L.nchunks;       // balanced chunks
+                sf_used = max(sf_used, L.kc * L.Npad);
                 StreamItem &it = S.sched[S.nsched++];
                 it.goff = L.goff; it.kc = L.kc; it.nchunks = L.nchunks; it.K = L.K; it.Npad = L.Npad;
                 cps += L.nchunks;
             }
         }
+        S.stage_floats = (sf_used + 31) & ~31;
         S.chunks_per_step = cps;
-        off += ns * sf;
+        off += ns * S.stage_floats;
     }
     if (off > SMEM_LIMIT_FLOATS) return fail(PMB_E_UNSUPPORTED, "shared-memory plan needs %d bytes > 227 KB", off * 4);
     return off * 4;
@@ -290,9 +326,10 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     const NetSweep *fo[2] = {&F.pol, &F.dyn};
     const NetSweep *bo[2] = {&B.dyn, &B.pol};
-    if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode)) < 0) return rc;
+    const int nst = tune ? tune->reserved[1] : 0;
+    if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode, nst)) < 0) return rc;
     pl.smem_fwd_bytes = rc;
-    if ((rc = plan_sweep(B, bo, true, P, pl.stream_mode)) < 0) return rc;
+    if ((rc = plan_sweep(B, bo, true, P, pl.stream_mode, nst)) < 0) return rc;
     pl.smem_bwd_bytes = rc;
     return PMB_OK;
 }

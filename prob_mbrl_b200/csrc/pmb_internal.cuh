@@ -4,9 +4,11 @@
 // shared memory between layers or steps.  Per step the CTA walks the policy MLP, the action
 // squashing, the dynamics MLP, the Gaussian output densities and the reward (forward sweep,
 // pmb_rollout_fwd.cu) or their adjoints in reverse (pmb_rollout_bwd.cu).  The hidden x hidden
-// weight matrices do not fit next to the tile, so they are streamed from L2 every step as
+// weight matrices do not fit next to the tile, so they are streamed from L2 every step as large
 // k-chunks through a ring of shared-memory stages filled by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx); the skinny first/last layers stay resident.
+// (cp.async.bulk + mbarrier complete_tx); the skinny first/last layers, the biases, the CTA's rows of
+// the dropout masks and every per-step constant stay resident in shared memory.
+// Inner products run on the packed FP32 pipe (fma.rn.f32x2, SASS FFMA2 -- new on sm_100).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,9 +19,9 @@ namespace pmb {
 constexpr int NT = 256;              // threads per CTA of the sweeps
 constexpr int NWARP = NT / 32;
 constexpr int MAXL = PMB_MAX_LINEAR; // linear layers per net
-constexpr int MAXS = 8;              // ring stages (max)
-constexpr int MAXKS = 8;             // max k-split of a wide layer
+constexpr int MAXS = 4;              // ring stages (max)
 constexpr int MAXSCHED = 2 * MAXL;   // streamed layers per step
+constexpr int SD = PMB_MAX_STATE;    // row stride of the small per-particle buffers (D + U <= 16)
 
 // One linear op as executed inside a sweep.
 //   wide  : out[p][0..Npad) = sum_{k<K} in[k][p] * Wm[k][0..Npad)   (Wm rows of Npad floats)
@@ -33,8 +35,9 @@ struct Lin {
     int kc;          // rows per chunk (streamed)
     int nchunks;     // chunks per layer (streamed)
     int soff;        // resident: float offset inside the resident smem area
+    int bias_soff;   // float offset of the padded bias in the resident area, -1 = none (forward only)
     long long goff;  // float offset of the matrix inside the packed weight area of this sweep
-    long long boff;  // float offset (workspace) of the padded bias, -1 = none (forward only)
+    long long boff;  // float offset (workspace) of the padded bias, -1 = none
 };
 
 struct NetSweep {
@@ -43,7 +46,9 @@ struct NetSweep {
     int nin;                    // inputs of the first
     Lin lin[MAXL];              // indexed by linear layer l = 0..nlin-1
     long long mask_off[MAXL];   // hidden layer l: packed mask [N][Npad_l] (workspace floats), -1 = none
+    int mask_soff[MAXL];        // hidden layer l: this CTA's [P][Npad_l] rows in smem, -1 = read from global
     long long saved_off[MAXL];  // hidden layer l: post-dropout activations [H][N][Npad_l]
+    int sav_soff[MAXL];         // backward: offset of the layer inside the per-step saved tile in smem
     long long delta_off[MAXL];  // policy only: adjoint of linear l's output [H][N][Npad_l or nout]
     long long outsaved_off;     // raw output of the last linear layer [H][N][nout]
     float keep[MAXL];
@@ -57,6 +62,10 @@ struct StreamItem {
     long long goff;  // float offset in packed area
     int kc, nchunks, K, Npad;
 };
+
+// layout of the constants block in shared memory (floats)
+constexpr int C_MX = 0, C_ISX = 16, C_MY = 32, C_SY = 48, C_LSY = 64, C_SCALE = 80, C_BIAS = 96, C_C0 = 112,
+              C_C = 128, C_Q = 192, C_QS = 208, C_R = 224, C_RS = 480, C_TOTAL = 736;
 
 struct SweepParams {
     int N, H, D, U;
@@ -81,20 +90,19 @@ struct SweepParams {
     int chunks_per_step;
     StreamItem sched[MAXSCHED];
     // shared memory carve-up (float offsets from the dynamic smem base)
-    int res_floats;             // resident weights
-    long long res_goff_unused;
-    int off_act0, off_act1, off_red, off_misc, off_stage;
+    int off_cst, off_act0, off_act1, off_red, off_misc, off_sav, off_stage;
+    int sav_floats;             // backward: floats of one saved-activation tile buffer (two buffers)
     int stage_floats, nstages;
-    int hmax_pad;
-    // resident copy list: (goff -> soff, n floats)
+    // resident copy list: (source -> smem offset, n floats); src_ws = 1: workspace offset, 0: wpack offset
     int nres;
-    long long res_goff[2 * MAXL];
-    int res_soff[2 * MAXL];
-    int res_n[2 * MAXL];
+    long long res_goff[4 * MAXL];
+    int res_soff[4 * MAXL];
+    int res_n[4 * MAXL];
+    int res_ws[4 * MAXL];
 };
 
 // ----------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (global -> shared), see the Blackwell guide "Guideline 15".
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -152,27 +160,26 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 
 // ----------------------------------------------------------------------------------------
 // The weight stream: a ring of `nstages` smem stages consumed in a fixed cyclic schedule.
-// All threads call consume() in lockstep; thread 0 issues the copies `nstages-1` chunks ahead.
+// All threads call acquire() in lockstep; thread 0 issues the copies `nstages-1` chunks ahead.
 // ----------------------------------------------------------------------------------------
 struct Stream {
     const SweepParams *prm;
     float *stage_base;
     uint64_t *full;         // [nstages] mbarriers (mode 2)
-    unsigned q;             // next chunk to consume (uniform)
-    // issue cursor (thread 0 only)
-    unsigned issued;
-    unsigned total;
-    int is_item, is_chunk;
+    int c_stage;            // consumer cursor (uniform)
+    uint32_t c_parity;
+    // producer cursor (thread 0 only)
+    int p_stage, p_item, p_chunk;
+    unsigned p_left;
 
     __device__ __forceinline__ void init(const SweepParams *p, float *smem, uint64_t *bars) {
         prm = p;
         stage_base = smem + p->off_stage;
         full = bars;
-        q = 0;
-        issued = 0;
-        total = (unsigned)p->H * (unsigned)p->chunks_per_step;
-        is_item = 0;
-        is_chunk = 0;
+        c_stage = 0;
+        c_parity = 0;
+        p_stage = p_item = p_chunk = 0;
+        p_left = (unsigned)p->H * (unsigned)p->chunks_per_step;
         if (p->stream_mode == 2) {
             if (threadIdx.x == 0) {
                 for (int s = 0; s < p->nstages; ++s) mbar_init(&full[s], 1);
@@ -188,57 +195,58 @@ struct Stream {
 
     // thread 0: issue the next chunk of the cyclic schedule into its stage
     __device__ __forceinline__ void issue_next() {
-        if (issued >= total) return;
-        const StreamItem &it = prm->sched[is_item];
-        int row0 = is_chunk * it.kc;
-        int rows = min(it.kc, it.K - row0);
-        uint32_t bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
-        int st = issued % prm->nstages;
+        if (p_left == 0) return;
+        const StreamItem &it = prm->sched[p_item];
+        const int row0 = p_chunk * it.kc;
+        const int rows = min(it.kc, it.K - row0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
         const float *src = prm->wpack + it.goff + (long long)row0 * it.Npad;
-        mbar_expect_tx(&full[st], bytes);
-        tma_bulk_g2s(stage_base + (size_t)st * prm->stage_floats, src, bytes, &full[st]);
-        ++issued;
-        if (++is_chunk == it.nchunks) {
-            is_chunk = 0;
-            if (++is_item == prm->nsched) is_item = 0;
+        mbar_expect_tx(&full[p_stage], bytes);
+        tma_bulk_g2s(stage_base + (size_t)p_stage * prm->stage_floats, src, bytes, &full[p_stage]);
+        --p_left;
+        if (++p_stage == prm->nstages) p_stage = 0;
+        if (++p_chunk == it.nchunks) {
+            p_chunk = 0;
+            if (++p_item == prm->nsched) p_item = 0;
         }
     }
 
-    // Make chunk q of the schedule readable in its stage; returns the stage pointer.
-    // Contains one __syncthreads() before any stage is overwritten, so callers may rely on it as the
-    // barrier that publishes the previous layer's shared-memory writes.
+    // Make the next chunk of the schedule readable; returns its stage pointer.  Contains one
+    // __syncthreads() before any stage is overwritten, so callers may rely on it as the barrier that
+    // publishes the previous layer's shared-memory writes.
     __device__ __forceinline__ const float *acquire(const StreamItem &it, int chunk) {
-        const int ns = prm->nstages;
-        __syncthreads();   // everyone is done with chunk q-1 -> its stage may be refilled
-        const float *st = stage_base + (size_t)(q % ns) * prm->stage_floats;
+        __syncthreads();   // everyone is done with the previous chunk -> its stage may be refilled
+        const float *st = stage_base + (size_t)c_stage * prm->stage_floats;
         if (prm->stream_mode == 2) {
             if (threadIdx.x == 0) issue_next();
-            mbar_wait(&full[q % ns], (q / ns) & 1u);
+            mbar_wait(&full[c_stage], c_parity);
         } else {
-            int row0 = chunk * it.kc;
-            int rows = min(it.kc, it.K - row0);
-            int n4 = rows * it.Npad / 4;
+            const int row0 = chunk * it.kc;
+            const int rows = min(it.kc, it.K - row0);
+            const int n4 = rows * it.Npad / 4;
             const float4 *src = reinterpret_cast<const float4 *>(prm->wpack + it.goff + (long long)row0 * it.Npad);
             float4 *dst = reinterpret_cast<float4 *>(const_cast<float *>(st));
             for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldg(src + i);
             __syncthreads();
         }
-        ++q;
+        if (++c_stage == prm->nstages) {
+            c_stage = 0;
+            c_parity ^= 1u;
+        }
         return st;
     }
 };
 
 // ----------------------------------------------------------------------------------------
-// wide layer: thread = (column quad cq, k-split group g)
+// wide layer: thread = (column quad cq, k-split group g); ks is a power of two
 // ----------------------------------------------------------------------------------------
 struct WideMap {
-    int cq, g, ks, active;
+    int cq, g, ks, ks_log2, active;
     __device__ __forceinline__ void set(int npad) {
-        int cqn = npad >> 2;
-        int gs = (cqn + 31) & ~31;          // threads per k-split group (warp multiple)
-        ks = NT / gs;
-        if (ks > MAXKS) ks = MAXKS;
-        if (ks < 1) ks = 1;
+        const int cqn = npad >> 2;
+        const int gs = (cqn + 31) & ~31;      // threads per k-split group (warp multiple)
+        ks_log2 = gs <= 32 ? 3 : gs <= 64 ? 2 : gs <= 128 ? 1 : 0;
+        ks = 1 << ks_log2;
         g = threadIdx.x / gs;
         cq = threadIdx.x - g * gs;
         active = (g < ks) && (cq < cqn);
@@ -262,73 +270,85 @@ __device__ __forceinline__ void load_act(float (&a)[P], const float *src) {
     }
 }
 
-// acc[p][0..3] += sum over rows r = g, g+ks, ... < rows of act[r][p] * w[r][4cq..4cq+3]
+// acc[p][0..1] (column pairs) += act[r][p] * w[r][4cq..4cq+3] over this thread's rows r = g, g+ks, ...
+// Packed FP32 FMA (FFMA2): two columns per instruction.
 template <int P>
-__device__ __forceinline__ void wide_accum(float (&acc)[P][4], const float *__restrict__ w, int rows, int npad,
+__device__ __forceinline__ void wide_accum(float2 (&acc)[P][2], const float *__restrict__ w, int rows, int npad,
                                            const float *__restrict__ act, const WideMap &m) {
-    const float *wp = w + 4 * m.cq;
+    const int n = (rows - m.g + m.ks - 1) >> m.ks_log2;
+    const float *wp = w + 4 * m.cq + (size_t)m.g * npad;
+    const float *ap = act + m.g * P;
+    const int wstride = npad << m.ks_log2;
+    const int astride = P << m.ks_log2;
 #pragma unroll 4
-    for (int r = m.g; r < rows; r += m.ks) {
-        float4 wv = *reinterpret_cast<const float4 *>(wp + (size_t)r * npad);
+    for (int i = 0; i < n; ++i) {
+        const float4 wv = *reinterpret_cast<const float4 *>(wp);
         float a[P];
-        load_act<P>(a, act + r * P);
+        load_act<P>(a, ap);
+        wp += wstride;
+        ap += astride;
+        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            acc[p][0] = fmaf(a[p], wv.x, acc[p][0]);
-            acc[p][1] = fmaf(a[p], wv.y, acc[p][1]);
-            acc[p][2] = fmaf(a[p], wv.z, acc[p][2]);
-            acc[p][3] = fmaf(a[p], wv.w, acc[p][3]);
+            const float2 a2 = make_float2(a[p], a[p]);
+            acc[p][0] = __ffma2_rn(a2, w01, acc[p][0]);
+            acc[p][1] = __ffma2_rn(a2, w23, acc[p][1]);
         }
     }
 }
 
-// Sum the k-split partials into group 0.  Contains one __syncthreads().
-template <int P>
-__device__ __forceinline__ void wide_reduce(float (&acc)[P][4], float *red, int npad, const WideMap &m) {
-    if (m.ks > 1) {
-        if (m.active && m.g > 0) {
+// Accumulate a whole wide layer (resident or streamed), combine the k-split partials and hand every
+// finished (particle p, 4 columns) tuple to `epi(p, float4 sums)`.  The k-split groups share the
+// epilogue work: group g finishes particles p = g, g+ks, ...  Starts with a __syncthreads(); contains a
+// second one when ks > 1.  `act` is the [K][P] input tile.
+template <int P, typename Epi>
+__device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item, const float *res,
+                                           const float *act, float *red, Stream &S, const WideMap &m,
+                                           Epi epi) {
+    float2 acc[P][2];
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                *reinterpret_cast<float4 *>(red + ((size_t)((m.g - 1) * P + p) * npad) + 4 * m.cq) =
-                    make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-        }
-        __syncthreads();
-        if (m.active && m.g == 0) {
-            for (int gg = 1; gg < m.ks; ++gg) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    float4 v = *reinterpret_cast<const float4 *>(red + ((size_t)((gg - 1) * P + p) * npad) + 4 * m.cq);
-                    acc[p][0] += v.x; acc[p][1] += v.y; acc[p][2] += v.z; acc[p][3] += v.w;
-                }
-            }
-        }
-    }
-}
-
-// Accumulate a whole wide layer (resident or streamed) into acc.  `act` is the [K][P] input tile.
-// On return group-0 threads hold the full sums.  Always starts with a __syncthreads().
-template <int P>
-__device__ __forceinline__ void wide_layer(float (&acc)[P][4], const Lin &L, const StreamItem *item,
-                                           const float *res, const float *act, float *red, Stream &S,
-                                           const WideMap &m) {
-#pragma unroll
-    for (int p = 0; p < P; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+    for (int p = 0; p < P; ++p) acc[p][0] = acc[p][1] = make_float2(0.f, 0.f);
     if (L.streamed) {
         for (int c = 0; c < L.nchunks; ++c) {
             const float *w = S.acquire(*item, c);
-            int row0 = c * L.kc;
-            int rows = min(L.kc, L.K - row0);
+            const int row0 = c * L.kc;
+            const int rows = min(L.kc, L.K - row0);
             if (m.active) wide_accum<P>(acc, w, rows, L.Npad, act + (size_t)row0 * P, m);
         }
     } else {
         __syncthreads();
         if (m.active) wide_accum<P>(acc, res + L.soff, L.K, L.Npad, act, m);
     }
-    wide_reduce<P>(acc, red, L.Npad, m);
+    if (m.ks == 1) {
+        if (m.active) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) epi(p, make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y));
+        }
+        return;
+    }
+    const int npad = L.Npad;
+    if (m.active) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            *reinterpret_cast<float4 *>(red + ((size_t)(m.g * P + p) * npad) + 4 * m.cq) =
+                make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
+    }
+    __syncthreads();
+    if (m.active) {
+        for (int p = m.g; p < P; p += m.ks) {
+            float4 s = *reinterpret_cast<const float4 *>(red + ((size_t)p * npad) + 4 * m.cq);
+            for (int gg = 1; gg < m.ks; ++gg) {
+                const float4 v = *reinterpret_cast<const float4 *>(red + ((size_t)(gg * P + p) * npad) + 4 * m.cq);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            epi(p, s);
+        }
+    }
 }
 
-// narrow layer: out[p][j] = sum_k act[k][p] * w[j][k] (+ bias[j]); one warp per output, lanes split k.
-// Starts with a __syncthreads(); results are visible after the caller's next barrier.
+// narrow layer: out[p][j] = sum_k act[k][p] * w[j][k] (+ bias[j]).  One warp per group of up to 4
+// outputs (4 independent dot products in flight), lanes split k.  Starts with a __syncthreads();
+// results are visible after the caller's next barrier.
 template <int P>
 __device__ __forceinline__ void narrow_layer(const Lin &L, const float *res, const float *act, float *out,
                                              const float *bias) {
@@ -336,22 +356,86 @@ __device__ __forceinline__ void narrow_layer(const Lin &L, const float *res, con
     const float *w = res + L.soff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nout = P * L.Nout;
-    for (int o = warp; o < nout; o += NWARP) {
-        int p = o / L.Nout, j = o - p * L.Nout;
-        const float *wj = w + (size_t)j * L.K;
-        float s = 0.f;
-        for (int k = lane; k < L.K; k += 32) s = fmaf(act[k * P + p], wj[k], s);
-        s = warp_sum(s);
-        if (lane == 0) out[p * L.Nout + j] = s + (bias ? bias[j] : 0.f);
+    const int K = L.K;
+    for (int o0 = warp * 4; o0 < nout; o0 += NWARP * 4) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        int pj[4], wj[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int o = min(o0 + q, nout - 1);
+            int p = o / L.Nout;
+            pj[q] = p;
+            wj[q] = (o - p * L.Nout) * K;
+        }
+        for (int k = lane; k < K; k += 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = fmaf(act[k * P + pj[q]], w[wj[q] + k], s[q]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        }
+        if (lane < 4 && o0 + lane < nout) {
+            const int o = o0 + lane;
+            const int j = o - (o / L.Nout) * L.Nout;
+            const float v = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
+            out[o] = v + (bias ? bias[j] : 0.f);
+        }
     }
 }
 
-// cooperative copy of the resident weights into shared memory
-__device__ __forceinline__ void load_resident(const SweepParams &prm, float *res) {
+// cooperative copy of the resident blocks (weights, biases, this CTA's mask rows) into shared memory.
+// res_ws: 0 = offset into the packed weights, 1 = offset into the workspace, >= 4 = dropout-mask rows of
+// this CTA (value = row length Npad; res_n = P * Npad; row p is particle min(n0 + p, N - 1)).
+__device__ __forceinline__ void load_resident(const SweepParams &prm, float *smem, int n0) {
     for (int i = 0; i < prm.nres; ++i) {
-        const float4 *src = reinterpret_cast<const float4 *>(prm.wpack + prm.res_goff[i]);
-        float4 *dst = reinterpret_cast<float4 *>(res + prm.res_soff[i]);
-        for (int k = threadIdx.x; k < prm.res_n[i] / 4; k += NT) dst[k] = __ldg(src + k);
+        float4 *dst = reinterpret_cast<float4 *>(smem + prm.res_soff[i]);
+        if (prm.res_ws[i] >= 4) {
+            const int row4 = prm.res_ws[i] / 4;
+            const int n4 = prm.res_n[i] / 4;
+            for (int k = threadIdx.x; k < n4; k += NT) {
+                const int p = k / row4, c = k - p * row4;
+                const int n = min(n0 + p, prm.N - 1);
+                dst[k] = __ldg(reinterpret_cast<const float4 *>(prm.ws + prm.res_goff[i] + (long long)n * row4 * 4) + c);
+            }
+        } else {
+            const float *src = (prm.res_ws[i] == 0 ? prm.wpack : prm.ws) + prm.res_goff[i];
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            for (int k = threadIdx.x; k < prm.res_n[i] / 4; k += NT) dst[k] = __ldg(s4 + k);
+        }
+    }
+}
+
+// constants block: scalers, squashing, reward matrices (+ symmetrised copies for the adjoint)
+__device__ __forceinline__ void load_constants(const SweepParams &prm, float *cst) {
+    const int D = prm.D, U = prm.U, KR = prm.KR;
+    for (int i = threadIdx.x; i < C_TOTAL; i += NT) cst[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < D + U; i += NT) {
+        cst[C_MX + i] = prm.mx[i];
+        cst[C_ISX + i] = prm.iSx[i];
+    }
+    for (int i = threadIdx.x; i < D; i += NT) {
+        cst[C_MY + i] = prm.my[i];
+        cst[C_SY + i] = prm.Sy[i];
+        cst[C_LSY + i] = logf(prm.Sy[i]);          // Sy.log(), recomputed every step by the reference
+    }
+    for (int i = threadIdx.x; i < U; i += NT) {
+        cst[C_SCALE + i] = prm.act_scale[i];
+        cst[C_BIAS + i] = prm.act_bias[i];
+    }
+    for (int i = threadIdx.x; i < KR; i += NT) cst[C_C0 + i] = prm.rew_c0[i];
+    for (int i = threadIdx.x; i < KR * D; i += NT) cst[C_C + (i / D) * SD + (i % D)] = prm.rew_C[i];
+    for (int i = threadIdx.x; i < KR * KR; i += NT) {
+        int a = i / KR, b = i % KR;
+        cst[C_Q + a * 4 + b] = prm.rew_Q[a * KR + b];
+        cst[C_QS + a * 4 + b] = prm.rew_Q[a * KR + b] + prm.rew_Q[b * KR + a];
+    }
+    for (int i = threadIdx.x; i < U * U; i += NT) {
+        int a = i / U, b = i % U;
+        cst[C_R + a * SD + b] = prm.rew_R[a * U + b];
+        cst[C_RS + a * SD + b] = prm.rew_R[a * U + b] + prm.rew_R[b * U + a];
     }
 }
 

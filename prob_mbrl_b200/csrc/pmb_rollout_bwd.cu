@@ -7,210 +7,305 @@
 // SURVEY.md App. D-4).  Replaces loss.backward() through utils.rollout (reference
 // algorithms/mc_pilco.py:197); adjoint formulas are those of oracle/rollout_oracle.py::manual_backward,
 // which tests/test_oracle_backward.py checks against autograd.
+//
+// Everything that depends only on forward values (reward adjoint, density / tanh derivative factors,
+// direct cotangents) is computed ONE STEP AHEAD into a double-buffered "pre" block in shared memory,
+// from global loads issued at the top of the previous step, and the stored hidden activations of the
+// step arrive by TMA bulk copies issued one step ahead: the serial chain only touches shared memory.
 #include "pmb_internal.cuh"
 
 namespace pmb {
 
-constexpr int SD = PMB_MAX_STATE;
+// float offsets inside the per-particle scratch block (`misc`), P-scaled
+constexpr int M_GS = 0, M_GSP = 1, M_OBUF = 2, M_STG_S1 = 3, M_STG_A = 4, M_PRE = 5;   // x P*SD
+constexpr int PRE_RS = 0, PRE_RA = 1, PRE_FD = 2, PRE_TP = 3, PRE_FP = 4, PRE_GS0 = 5, PRE_N = 6;
 
 // Backward through one net.  `in` holds the adjoint of the net's raw outputs as a [nout][P] tile.
 // Wide layers l = nlin-1 .. 1 (weights W_l as stored, [out][in]) produce the adjoint of hidden l-1,
 // gated by the stored activation; the final narrow layer (W_0^T) leaves d(input)[p][nin] in obuf.
-// If `store_delta`, every linear layer's output adjoint is written to global for the weight gradient.
+// With kStoreDelta every hidden adjoint is also written to global for the weight gradient.
 template <int P, bool kStoreDelta>
 __device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSweep &net, int &sched_i,
-                                             float *&in, float *&out, float *obuf, const float *res,
-                                             float *red, Stream &S, int t, int n0) {
+                                             float *&in, float *&out, float *obuf, float *smem, float *red,
+                                             const float *sav, Stream &S, int t, int n0) {
     const int N = prm.N;
     for (int l = net.nlin - 1; l >= 1; --l) {
         const Lin &L = net.lin[l];      // wide: K = outputs of linear l (padded), Npad = width of hidden l-1
         const int h = l - 1;            // hidden layer whose adjoint we produce
         WideMap m;
         m.set(L.Npad);
-        const bool epi = m.active && m.g == 0;
-        float4 mk[P], sv[P];
-        if (epi) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                int n = min(n0 + p, N - 1);
-                mk[p] = net.mask_off[h] >= 0
-                            ? __ldg(reinterpret_cast<const float4 *>(prm.ws + net.mask_off[h] + (size_t)n * L.Npad) + m.cq)
-                            : make_float4(1.f, 1.f, 1.f, 1.f);
-                sv[p] = __ldg(reinterpret_cast<const float4 *>(prm.ws + net.saved_off[h] +
-                                                               ((size_t)t * N + n) * L.Npad) + m.cq);
+        const int col = 4 * m.cq;
+        const int npad = L.Npad;
+        const float *mask_s = net.mask_soff[h] >= 0 ? smem + net.mask_soff[h] + col : nullptr;
+        const float *mask_g = (!mask_s && net.mask_off[h] >= 0) ? prm.ws + net.mask_off[h] + col : nullptr;
+        const float *sv = sav + net.sav_soff[h] + col;
+        const float keep = net.keep[h];
+        float *dl = prm.ws + net.delta_off[h] + ((size_t)t * N + n0) * npad + col;
+        float *dst = out + col * P;
+        wide_layer<P>(L, L.streamed ? &prm.sched[sched_i] : nullptr, smem, in, red, S, m, [&](int p, float4 v) {
+            float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad);
+            else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad));
+            const float4 hh = *reinterpret_cast<const float4 *>(sv + p * npad);
+            // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
+            if (keep != 1.f) {
+                v.x = v.x / keep; v.y = v.y / keep; v.z = v.z / keep; v.w = v.w / keep;
             }
-        }
-        float acc[P][4];
-        wide_layer<P>(acc, L, L.streamed ? &prm.sched[sched_i] : nullptr, res, in, red, S, m);
+            v.x = hh.x != 0.f ? v.x * mk.x : 0.f;
+            v.y = hh.y != 0.f ? v.y * mk.y : 0.f;
+            v.z = hh.z != 0.f ? v.z * mk.z : 0.f;
+            v.w = hh.w != 0.f ? v.w * mk.w : 0.f;
+            dst[p] = v.x;
+            dst[P + p] = v.y;
+            dst[2 * P + p] = v.z;
+            dst[3 * P + p] = v.w;
+            if (kStoreDelta && n0 + p < N) *reinterpret_cast<float4 *>(dl + (size_t)p * npad) = v;
+        });
         if (L.streamed) ++sched_i;
-        if (epi) {
-            const float keep = net.keep[h];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float mm[4] = {mk[p].x, mk[p].y, mk[p].z, mk[p].w};
-                const float hh[4] = {sv[p].x, sv[p].y, sv[p].z, sv[p].w};
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];
-                    // y != 0 <=> pre > 0 and mask != 0
-                    float x = acc[p][j];
-                    if (keep != 1.f) x = x / keep;
-                    x = hh[j] != 0.f ? x * mm[j] : 0.f;
-                    v[j] = x;
-                    out[(4 * m.cq + j) * P + p] = x;
-                }
-                if (kStoreDelta && n0 + p < N)
-                    *reinterpret_cast<float4 *>(prm.ws + net.delta_off[h] + ((size_t)t * N + n0 + p) * L.Npad +
-                                                4 * m.cq) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-        }
         float *tmp = in; in = out; out = tmp;
     }
-    narrow_layer<P>(net.lin[0], res, in, obuf, nullptr);
+    narrow_layer<P>(net.lin[0], smem, in, obuf, nullptr);
 }
 
 template <int P>
 __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constant__ SweepParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[MAXS];
+    __shared__ __align__(8) uint64_t sbar[2];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
-    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
-    float *res = smem;
+    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, KR = prm.KR;
+    const NetSweep &pol = prm.pol;
+    const NetSweep &dyn = prm.dyn;
+    float *cst = smem + prm.off_cst;
     float *act0 = smem + prm.off_act0;
     float *act1 = smem + prm.off_act1;
     float *red = smem + prm.off_red;
     float *misc = smem + prm.off_misc;
-    float *gs = misc;                 // [P][SD] dL/ds_{t+1}
-    float *gsp = misc + P * SD;       // [P][SD] dL/ds_t under construction
-    float *ga = misc + 2 * P * SD;    // [P][SD] dL/da_t
-    float *obuf = misc + 3 * P * SD;  // [P][<=SD] narrow outputs
+    float *savb = smem + prm.off_sav;
+    constexpr int BL = P * SD;   // one [P][SD] block
+    float *gs = misc + M_GS * BL, *gsp = misc + M_GSP * BL, *obuf = misc + M_OBUF * BL;
+    float *stg_s1 = misc + M_STG_S1 * BL, *stg_a = misc + M_STG_A * BL;
+    float *pre0 = misc + M_PRE * BL;                    // two buffers of PRE_N blocks
+    float *stg_w = pre0 + 2 * PRE_N * BL;               // [P]
 
-    load_resident(prm, res);
-    for (int i = tid; i < P * D; i += NT) {
-        int p = i / D, d = i - p * D;
-        int n = min(n0 + p, N - 1);
-        gs[p * SD + d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + n) * D + d) : 0.f;
+    // ---- thread roles (fixed for the whole horizon) ----
+    const bool roleA = tid < P * U;                       // (particle, action dim)
+    const int a_p = roleA ? tid / U : 0, a_u = roleA ? tid - a_p * U : 0;
+    const int a_n = min(n0 + a_p, N - 1);
+    const bool roleB = tid >= 128 && tid - 128 < P * D;   // (particle, state dim)
+    const int b_p = roleB ? (tid - 128) / D : 0, b_d = roleB ? (tid - 128) - b_p * D : 0;
+    const int b_n = min(n0 + b_p, N - 1);
+    const bool roleX = tid < P * (D + U);                 // (particle, dynamics-input dim)
+    const int x_p = roleX ? tid / (D + U) : 0, x_k = roleX ? tid - x_p * (D + U) : 0;
+    const bool roleR = tid >= 224 && tid - 224 < P;       // particle (reward weight)
+    const int r_p = roleR ? tid - 224 : 0;
+    const int r_n = min(n0 + r_p, N - 1);
+
+    load_constants(prm, cst);
+    load_resident(prm, smem, n0);
+    if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
+    if (tid == 0 && prm.stream_mode == 2) {
+        mbar_init(&sbar[0], 1);
+        mbar_init(&sbar[1], 1);
     }
     Stream S;
-    S.init(&prm, smem, bars);
+    S.init(&prm, smem, bars);    // fences the mbarrier inits and synchronises the CTA (mode 2)
     __syncthreads();
 
-    const NetSweep &pol = prm.pol;
-    const NetSweep &dyn = prm.dyn;
-    for (int t = H - 1; t >= 0; --t) {
-        int sched_i = 0;
-        float *in = act0, *out = act1;
-        // ---- reward adjoint: r = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset ----
-        if (tid < P) {
-            const int p = tid;
-            const int n = min(n0 + p, N - 1);
-            float gr = prm.g_rewards ? __ldg(prm.g_rewards + (size_t)t * N + n) : 0.f;
-            float e = __ldg(prm.rewards + (size_t)t * N + n) - prm.rew_offset;
-            float w = -0.5f * gr * e;
-            const float *s1 = prm.states + ((size_t)(t + 1) * N + n) * D;
-            const float *a = prm.actions + ((size_t)t * N + n) * U;
-            float dl[PMB_MAX_REWARD_ROWS], qd[PMB_MAX_REWARD_ROWS];
-            for (int i = 0; i < prm.KR; ++i) {
-                float s = __ldg(prm.rew_c0 + i);
-                for (int d = 0; d < D; ++d) s = fmaf(__ldg(prm.rew_C + i * D + d), __ldg(s1 + d), s);
+    // prefetch registers of the one-step-ahead precompute
+    float pf_s1 = 0.f, pf_ls = 0.f, pf_zd = 0.f, pf_gs = 0.f;                 // role B
+    float pf_a = 0.f, pf_mu = 0.f, pf_lsp = 0.f, pf_zp = 0.f, pf_ga = 0.f;    // role A
+    float pf_r = 0.f, pf_gr = 0.f;                                            // role R
+    auto prefetch = [&](int tt) {
+        if (roleB) {
+            pf_s1 = __ldg(prm.states + ((size_t)(tt + 1) * N + b_n) * D + b_d);
+            if (dyn.has_density) {
+                pf_ls = __ldg(prm.ws + dyn.outsaved_off + ((size_t)tt * N + b_n) * dyn.nout + D + b_d);
+                pf_zd = __ldg(dyn.z + (size_t)tt * dyn.zstride + (size_t)b_n * D + b_d);
+            }
+            pf_gs = prm.g_states ? __ldg(prm.g_states + ((size_t)tt * N + b_n) * D + b_d) : 0.f;
+        }
+        if (roleA) {
+            const float *op = prm.ws + pol.outsaved_off + ((size_t)tt * N + a_n) * pol.nout;
+            pf_a = __ldg(prm.actions + ((size_t)tt * N + a_n) * U + a_u);
+            pf_mu = __ldg(op + a_u);
+            if (pol.has_density) {
+                pf_lsp = __ldg(op + U + a_u);
+                pf_zp = __ldg(pol.z + (size_t)tt * pol.zstride + (size_t)a_n * U + a_u);
+            }
+            pf_ga = prm.g_actions ? __ldg(prm.g_actions + ((size_t)tt * N + a_n) * U + a_u) : 0.f;
+        }
+        if (roleR) {
+            pf_r = __ldg(prm.rewards + (size_t)tt * N + r_n);
+            pf_gr = prm.g_rewards ? __ldg(prm.g_rewards + (size_t)tt * N + r_n) : 0.f;
+        }
+    };
+    // first half of the precompute: factors that need no cross-thread data (+ staging of s', a, w)
+    auto precompute_a = [&](float *pre) {
+        if (roleB) {
+            stg_s1[b_p * SD + b_d] = pf_s1;
+            float fd = 0.f;
+            if (dyn.has_density) {
+                const float lst = clamp_logstd(pf_ls, dyn.lmax) + cst[C_LSY + b_d];
+                fd = pf_zd * expf(lst) * sigmoid_f(dyn.lmax - pf_ls);     // d s' / d log_std (raw)
+            }
+            pre[PRE_FD * BL + b_p * SD + b_d] = fd;
+            pre[PRE_GS0 * BL + b_p * SD + b_d] = pf_gs;
+        }
+        if (roleA) {
+            stg_a[a_p * SD + a_u] = pf_a;
+            const float sc = cst[C_SCALE + a_u];
+            float tp, fp = 0.f;
+            if (pol.has_density) {
+                const float el = expf(clamp_logstd(pf_lsp, pol.lmax));
+                const float th = tanhf(pf_mu + pf_zp * el);
+                tp = sc * (1.f - th * th);                                  // d a / d u
+                fp = pf_zp * el * sigmoid_f(pol.lmax - pf_lsp);             // d u / d log_std (raw)
+            } else {
+                const float th = tanhf(pf_mu);
+                tp = sc * (1.f - th * th);
+            }
+            pre[PRE_TP * BL + a_p * SD + a_u] = tp;
+            pre[PRE_FP * BL + a_p * SD + a_u] = fp;
+        }
+        if (roleR) stg_w[r_p] = -0.5f * pf_gr * (pf_r - prm.rew_offset);   // g_r * d r / d cost, r - off = scale*exp(-cost)
+    };
+    // second half: reward adjoint on (s', a):  w * C^T (Q+Q^T) delta  and  g_a + w * (R+R^T) a
+    auto precompute_b = [&](float *pre) {
+        if (roleB) {
+            float dl[PMB_MAX_REWARD_ROWS];
+            for (int i = 0; i < KR; ++i) {
+                float s = cst[C_C0 + i];
+                for (int d = 0; d < D; ++d) s = fmaf(cst[C_C + i * SD + d], stg_s1[b_p * SD + d], s);
                 dl[i] = s;
             }
-            for (int i = 0; i < prm.KR; ++i) {   // (Q + Q^T) d
-                float s = 0.f;
-                for (int j = 0; j < prm.KR; ++j)
-                    s = fmaf(__ldg(prm.rew_Q + i * prm.KR + j) + __ldg(prm.rew_Q + j * prm.KR + i), dl[j], s);
-                qd[i] = s;
+            float acc = 0.f;
+            for (int i = 0; i < KR; ++i) {
+                float qd = 0.f;
+                for (int j = 0; j < KR; ++j) qd = fmaf(cst[C_QS + i * 4 + j], dl[j], qd);
+                acc = fmaf(qd, cst[C_C + i * SD + b_d], acc);
             }
-            for (int d = 0; d < D; ++d) {
-                float s = 0.f;
-                for (int i = 0; i < prm.KR; ++i) s = fmaf(qd[i], __ldg(prm.rew_C + i * D + d), s);
-                gs[p * SD + d] += w * s;
-            }
-            for (int u = 0; u < U; ++u) {
-                float s = 0.f;
-                for (int v = 0; v < U; ++v)
-                    s = fmaf(__ldg(prm.rew_R + u * U + v) + __ldg(prm.rew_R + v * U + u), __ldg(a + v), s);
-                float g0 = prm.g_actions ? __ldg(prm.g_actions + ((size_t)t * N + n) * U + u) : 0.f;
-                ga[p * SD + u] = g0 + w * s;
+            pre[PRE_RS * BL + b_p * SD + b_d] = stg_w[b_p] * acc;
+        }
+        if (roleA) {
+            float s = 0.f;
+            for (int v = 0; v < U; ++v) s = fmaf(cst[C_RS + a_u * SD + v], stg_a[a_p * SD + v], s);
+            pre[PRE_RA * BL + a_p * SD + a_u] = pf_ga + stg_w[a_p] * s;
+        }
+    };
+    // stored hidden activations of step tt -> sav buffer `b` (TMA bulk copies, one per hidden layer)
+    auto issue_saved = [&](int tt, int b) {
+        uint32_t total = 0;
+        for (int n = 0; n < 2; ++n) {
+            const NetSweep &net = n ? pol : dyn;
+            for (int h = 0; h + 1 < net.nlin; ++h) total += (uint32_t)(P * net.lin[h + 1].Npad) * 4u;
+        }
+        if (total == 0) return;
+        mbar_expect_tx(&sbar[b], total);
+        for (int n = 0; n < 2; ++n) {
+            const NetSweep &net = n ? pol : dyn;
+            for (int h = 0; h + 1 < net.nlin; ++h) {
+                const int npad = net.lin[h + 1].Npad;
+                tma_bulk_g2s(savb + (size_t)b * prm.sav_floats + net.sav_soff[h],
+                             prm.ws + net.saved_off[h] + ((size_t)tt * N + n0) * npad, (uint32_t)(P * npad) * 4u,
+                             &sbar[b]);
             }
         }
-        __syncthreads();
-        // ---- dynamics density adjoint: s' = s + mu*Sy + my + z*exp(lstd) ----
-        for (int i = tid; i < P * D; i += NT) {
-            int p = i / D, d = i - p * D;
-            int n = min(n0 + p, N - 1);
-            float g = gs[p * SD + d];
-            float sy = __ldg(prm.Sy + d);
-            gsp[p * SD + d] = g;
-            in[d * P + p] = g * sy;
-            if (dyn.has_density) {
-                float ls = __ldg(prm.ws + dyn.outsaved_off + ((size_t)t * N + n) * dyn.nout + D + d);
-                float lst = clamp_logstd(ls, dyn.lmax) + logf(sy);
-                float z = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)n * D + d);
-                in[(D + d) * P + p] = g * z * expf(lst) * sigmoid_f(dyn.lmax - ls);
+    };
+    auto copy_saved = [&](int tt, int b) {   // stream_mode 1: plain cooperative copy
+        for (int n = 0; n < 2; ++n) {
+            const NetSweep &net = n ? pol : dyn;
+            for (int h = 0; h + 1 < net.nlin; ++h) {
+                const int npad = net.lin[h + 1].Npad;
+                const float4 *src = reinterpret_cast<const float4 *>(prm.ws + net.saved_off[h] + ((size_t)tt * N + n0) * npad);
+                float4 *dst = reinterpret_cast<float4 *>(savb + (size_t)b * prm.sav_floats + net.sav_soff[h]);
+                for (int i = tid; i < P * npad / 4; i += NT) dst[i] = __ldg(src + i);
             }
         }
-        net_backward<P, false>(prm, dyn, sched_i, in, out, obuf, res, red, S, t, n0);
-        __syncthreads();
-        // ---- through the input scaler: d[s;a] = dx * iSx ----
-        for (int i = tid; i < P * (D + U); i += NT) {
-            int p = i / (D + U), k = i - p * (D + U);
-            float v = obuf[p * dyn.nin + k] * __ldg(prm.iSx + k);
-            if (k < D) gsp[p * SD + k] += v;
-            else ga[p * SD + (k - D)] += v;
-        }
-        __syncthreads();
-        // ---- tanh squash + policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
-        for (int i = tid; i < P * U; i += NT) {
-            int p = i / U, u = i - p * U;
-            int n = min(n0 + p, N - 1);
-            const float *op = prm.ws + pol.outsaved_off + ((size_t)t * N + n) * pol.nout;
-            float sc = __ldg(prm.act_scale + u);
-            float g = ga[p * SD + u];
-            float du, dls = 0.f;
-            if (pol.has_density) {
-                float mu = __ldg(op + u), ls = __ldg(op + U + u);
-                float lst = clamp_logstd(ls, pol.lmax);
-                float z = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)n * U + u);
-                float el = expf(lst);
-                float th = tanhf(mu + z * el);
-                du = g * sc * (1.f - th * th);
-                dls = du * z * el * sigmoid_f(pol.lmax - ls);
-                out[(U + u) * P + p] = dls;
+    };
+    const bool has_sav = (pol.nlin > 1) || (dyn.nlin > 1);
+
+    // ---- prologue: everything step H-1 needs ----
+    int cur = 0;
+    uint32_t spar[2] = {0u, 0u};
+    if (prm.stream_mode == 2) {
+        if (tid == 0) issue_saved(H - 1, cur);
+    } else {
+        copy_saved(H - 1, cur);
+    }
+    prefetch(H - 1);
+    precompute_a(pre0 + cur * PRE_N * BL);
+    __syncthreads();
+    precompute_b(pre0 + cur * PRE_N * BL);
+    __syncthreads();
+
+    for (int t = H - 1; t >= 0; --t) {
+        const int nxt = cur ^ 1;
+        float *pre = pre0 + cur * PRE_N * BL;
+        float *pren = pre0 + nxt * PRE_N * BL;
+        int sched_i = 0;
+        float *in = act0, *out = act1;
+        // ---- one step ahead: stored activations + scalars of step t-1 ----
+        if (t > 0) {
+            if (prm.stream_mode == 2) {
+                if (tid == 0) issue_saved(t - 1, nxt);
             } else {
-                float th = tanhf(__ldg(op + u));
-                du = g * sc * (1.f - th * th);
+                copy_saved(t - 1, nxt);
             }
-            out[u * P + p] = du;
-            if (n0 + p < N) {
-                float *dd = prm.ws + pol.delta_off[pol.nlin - 1] + ((size_t)t * N + n0 + p) * pol.nout;
-                dd[u] = du;
-                if (pol.has_density) dd[U + u] = dls;
+            prefetch(t - 1);
+        }
+        // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
+        //      s' = s + mu*Sy + my + z*exp(lstd) ----
+        if (roleB) {
+            const float g = gs[b_p * SD + b_d] + pre[PRE_RS * BL + b_p * SD + b_d];
+            gsp[b_p * SD + b_d] = g;
+            in[b_d * P + b_p] = g * cst[C_SY + b_d];
+            if (dyn.has_density) in[(D + b_d) * P + b_p] = g * pre[PRE_FD * BL + b_p * SD + b_d];
+        }
+        if (prm.stream_mode == 2 && has_sav) {
+            mbar_wait(&sbar[cur], spar[cur]);
+            spar[cur] ^= 1u;
+        }
+        const float *sav = savb + (size_t)cur * prm.sav_floats;
+        net_backward<P, false>(prm, dyn, sched_i, in, out, obuf, smem, red, sav, S, t, n0);
+        __syncthreads();
+        // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash + policy
+        //      density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
+        if (roleX) {
+            const float v = obuf[x_p * dyn.nin + x_k] * cst[C_ISX + x_k];
+            if (x_k < D) {
+                gsp[x_p * SD + x_k] += v;
+            } else {
+                const int u = x_k - D;
+                const float ga = pre[PRE_RA * BL + x_p * SD + u] + v;
+                const float du = ga * pre[PRE_TP * BL + x_p * SD + u];
+                out[u * P + x_p] = du;
+                float dls = 0.f;
+                if (pol.has_density) {
+                    dls = du * pre[PRE_FP * BL + x_p * SD + u];
+                    out[(U + u) * P + x_p] = dls;
+                }
+                if (n0 + x_p < N) {
+                    float *dd = prm.ws + pol.delta_off[pol.nlin - 1] + ((size_t)t * N + n0 + x_p) * pol.nout;
+                    dd[u] = du;
+                    if (pol.has_density) dd[U + u] = dls;
+                }
             }
         }
+        if (t > 0) precompute_a(pren);
         {
             float *tmp = in; in = out; out = tmp;
         }
-        net_backward<P, true>(prm, pol, sched_i, in, out, obuf, res, red, S, t, n0);
+        net_backward<P, true>(prm, pol, sched_i, in, out, obuf, smem, red, sav, S, t, n0);
         __syncthreads();
         // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
-        for (int i = tid; i < P * D; i += NT) {
-            int p = i / D, d = i - p * D;
-            int n = min(n0 + p, N - 1);
-            float g = gsp[p * SD + d] + obuf[p * pol.nin + d];
-            if (prm.g_states) g += __ldg(prm.g_states + ((size_t)t * N + n) * D + d);
-            gs[p * SD + d] = g;
-        }
+        if (roleB) gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + obuf[b_p * pol.nin + b_d] + pre[PRE_GS0 * BL + b_p * SD + b_d];
+        if (t > 0) precompute_b(pren);
         __syncthreads();
+        cur = nxt;
     }
-    if (prm.dx0) {
-        for (int i = tid; i < P * D; i += NT) {
-            int p = i / D, d = i - p * D;
-            if (n0 + p < N) prm.dx0[(size_t)(n0 + p) * D + d] = gs[p * SD + d];
-        }
-    }
+    if (prm.dx0 && roleB && n0 + b_p < N) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];
 }
 
 cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream) {
