@@ -89,7 +89,9 @@ typedef struct pmb_tuning {
     int stream_mode;         /* 0 default (=2), 1 = synchronous copies, 2 = TMA bulk copies + mbarrier ring */
     int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
-                                4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default */
+                                4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default.
+                                reserved[2..3]: low/high half of a device pointer to >= 64 int64 that receives
+                                clock64() timeline marks of one step (profiling aid), 0 = off */
 } pmb_tuning;
 
 int pmb_abi_version(void);

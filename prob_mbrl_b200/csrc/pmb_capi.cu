@@ -258,6 +258,7 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
         }
         S.stage_floats = (sf_used + 31) & ~31;
         S.chunks_per_step = cps;
+        if (cps > MAXCHUNKS) return fail(PMB_E_UNSUPPORTED, "weight stream needs %d chunks per step (> %d)", cps, MAXCHUNKS);
         off += ns * S.stage_floats;
     }
     if (off > SMEM_LIMIT_FLOATS) return fail(PMB_E_UNSUPPORTED, "shared-memory plan needs %d bytes > 227 KB", off * 4);
@@ -279,7 +280,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
 
     memset(&pl, 0, sizeof(pl));
     int P = tune && tune->particles_per_cta ? tune->particles_per_cta : 0;
-    if (P == 0) P = (p->N > 8 * 148) ? 8 : 4;
+    if (P == 0) P = (p->N > 8 * 148) ? 8 : (p->N > 2 * 148) ? 4 : 2;   // few particles: spread over more SMs
     if (P != 1 && P != 2 && P != 4 && P != 8) return fail(PMB_E_INVALID, "particles_per_cta must be 1, 2, 4 or 8");
     pl.P = P;
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
@@ -400,6 +401,7 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     if (phases & 1) PMB_CUDA(launch_pack(pl.jobs, st));
     SweepParams &F = pl.fwd;
     F.x0 = x0; F.states = states; F.actions = actions; F.rewards = rewards; F.status = status_dev;
+    F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     if (phases & 2) PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
     return PMB_OK;
 }
@@ -421,6 +423,7 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     B.states = const_cast<float *>(states); B.actions = const_cast<float *>(actions);
     B.rewards = const_cast<float *>(rewards);
     B.g_states = g_states; B.g_actions = g_actions; B.g_rewards = g_rewards; B.dx0 = dx0;
+    B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
     if (phases & 2) PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));
     if (!(phases & 4)) return PMB_OK;

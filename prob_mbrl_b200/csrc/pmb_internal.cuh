@@ -85,6 +85,7 @@ struct SweepParams {
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
     int *status;
+    long long *dbg;             // profiling aid: clock64() marks of CTA 0 / thread 0 at step H/2 (nullable)
     // streaming schedule for one step, in consumption order
     int nsched;
     int chunks_per_step;
@@ -146,6 +147,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
         : "memory");
 }
 
+// timeline marks (profiling aid; compiled in, a predicated store when enabled)
+#define PMB_MARK(i) do { if (dbg_on) prm.dbg[(i)] = clock64(); } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -162,72 +166,92 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // The weight stream: a ring of `nstages` smem stages consumed in a fixed cyclic schedule.
 // All threads call acquire() in lockstep; thread 0 issues the copies `nstages-1` chunks ahead.
 // ----------------------------------------------------------------------------------------
+struct ChunkDesc {
+    const float *src;
+    uint32_t bytes;
+    uint32_t pad;
+};
+constexpr int MAXCHUNKS = 64;   // chunks per step (planner guarantees chunks_per_step <= MAXCHUNKS)
+
 struct Stream {
     const SweepParams *prm;
     float *stage_base;
     uint64_t *full;         // [nstages] mbarriers (mode 2)
+    ChunkDesc *tab;         // [chunks_per_step] in shared memory, the cyclic schedule of one step
     int c_stage;            // consumer cursor (uniform)
     uint32_t c_parity;
+    int c_idx;              // consumer position inside the step's schedule (mode 1)
     // producer cursor (thread 0 only)
-    int p_stage, p_item, p_chunk;
+    int p_stage, p_idx;
     unsigned p_left;
+    long long *dbgp;        // profiling aid: when non-null, acquire() appends clock64() marks
 
-    __device__ __forceinline__ void init(const SweepParams *p, float *smem, uint64_t *bars) {
+    __device__ __forceinline__ void init(const SweepParams *p, float *smem, uint64_t *bars, ChunkDesc *table) {
         prm = p;
         stage_base = smem + p->off_stage;
         full = bars;
+        tab = table;
         c_stage = 0;
         c_parity = 0;
-        p_stage = p_item = p_chunk = 0;
+        c_idx = 0;
+        dbgp = nullptr;
+        p_stage = p_idx = 0;
         p_left = (unsigned)p->H * (unsigned)p->chunks_per_step;
-        if (p->stream_mode == 2) {
-            if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            int k = 0;
+            for (int i = 0; i < p->nsched; ++i) {
+                const StreamItem &it = p->sched[i];
+                for (int c = 0; c < it.nchunks; ++c, ++k) {
+                    const int row0 = c * it.kc;
+                    const int rows = min(it.kc, it.K - row0);
+                    tab[k].src = p->wpack + it.goff + (long long)row0 * it.Npad;
+                    tab[k].bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
+                }
+            }
+            if (p->stream_mode == 2) {
                 for (int s = 0; s < p->nstages; ++s) mbar_init(&full[s], 1);
                 fence_mbar_init();
                 fence_proxy_async();
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int s = 0; s + 1 < p->nstages; ++s) issue_next();
-            }
+        }
+        __syncthreads();
+        if (p->stream_mode == 2 && threadIdx.x == 0) {
+            for (int s = 0; s + 1 < p->nstages; ++s) issue_next();
         }
     }
 
     // thread 0: issue the next chunk of the cyclic schedule into its stage
     __device__ __forceinline__ void issue_next() {
         if (p_left == 0) return;
-        const StreamItem &it = prm->sched[p_item];
-        const int row0 = p_chunk * it.kc;
-        const int rows = min(it.kc, it.K - row0);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
-        const float *src = prm->wpack + it.goff + (long long)row0 * it.Npad;
-        mbar_expect_tx(&full[p_stage], bytes);
-        tma_bulk_g2s(stage_base + (size_t)p_stage * prm->stage_floats, src, bytes, &full[p_stage]);
+        const ChunkDesc d = tab[p_idx];
+        mbar_expect_tx(&full[p_stage], d.bytes);
+        tma_bulk_g2s(stage_base + (size_t)p_stage * prm->stage_floats, d.src, d.bytes, &full[p_stage]);
         --p_left;
         if (++p_stage == prm->nstages) p_stage = 0;
-        if (++p_chunk == it.nchunks) {
-            p_chunk = 0;
-            if (++p_item == prm->nsched) p_item = 0;
-        }
+        if (++p_idx == prm->chunks_per_step) p_idx = 0;
     }
 
     // Make the next chunk of the schedule readable; returns its stage pointer.  Contains one
     // __syncthreads() before any stage is overwritten, so callers may rely on it as the barrier that
     // publishes the previous layer's shared-memory writes.
-    __device__ __forceinline__ const float *acquire(const StreamItem &it, int chunk) {
+    __device__ __forceinline__ const float *acquire() {
+        if (dbgp) *dbgp++ = clock64();
         __syncthreads();   // everyone is done with the previous chunk -> its stage may be refilled
+        if (dbgp) *dbgp++ = clock64();
         const float *st = stage_base + (size_t)c_stage * prm->stage_floats;
         if (prm->stream_mode == 2) {
             if (threadIdx.x == 0) issue_next();
+            if (dbgp) *dbgp++ = clock64();
             mbar_wait(&full[c_stage], c_parity);
+            if (dbgp) *dbgp++ = clock64();
         } else {
-            const int row0 = chunk * it.kc;
-            const int rows = min(it.kc, it.K - row0);
-            const int n4 = rows * it.Npad / 4;
-            const float4 *src = reinterpret_cast<const float4 *>(prm->wpack + it.goff + (long long)row0 * it.Npad);
+            const ChunkDesc d = tab[c_idx];
+            const int n4 = d.bytes / 16;
+            const float4 *src = reinterpret_cast<const float4 *>(d.src);
             float4 *dst = reinterpret_cast<float4 *>(const_cast<float *>(st));
             for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldg(src + i);
             __syncthreads();
+            if (++c_idx == prm->chunks_per_step) c_idx = 0;
         }
         if (++c_stage == prm->nstages) {
             c_stage = 0;
@@ -244,12 +268,13 @@ struct WideMap {
     int cq, g, ks, ks_log2, active;
     __device__ __forceinline__ void set(int npad) {
         const int cqn = npad >> 2;
-        const int gs = (cqn + 31) & ~31;      // threads per k-split group (warp multiple)
-        ks_log2 = gs <= 32 ? 3 : gs <= 64 ? 2 : gs <= 128 ? 1 : 0;
+        // threads per k-split group: power of two >= number of column quads, at least one warp
+        const int gs_log2 = cqn <= 32 ? 5 : cqn <= 64 ? 6 : cqn <= 128 ? 7 : 8;
+        ks_log2 = 8 - gs_log2;               // NT = 256 threads
         ks = 1 << ks_log2;
-        g = threadIdx.x / gs;
-        cq = threadIdx.x - g * gs;
-        active = (g < ks) && (cq < cqn);
+        g = threadIdx.x >> gs_log2;
+        cq = threadIdx.x & ((1 << gs_log2) - 1);
+        active = cq < cqn;
     }
 };
 
@@ -304,20 +329,28 @@ __device__ __forceinline__ void wide_accum(float2 (&acc)[P][2], const float *__r
 template <int P, typename Epi>
 __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item, const float *res,
                                            const float *act, float *red, Stream &S, const WideMap &m,
-                                           Epi epi) {
+                                           Epi epi, long long *dbg = nullptr) {
     float2 acc[P][2];
+    int dbi = 0;
+#define PMB_WMARK() do { if (dbg) dbg[dbi++] = clock64(); } while (0)
+    PMB_WMARK();
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[p][0] = acc[p][1] = make_float2(0.f, 0.f);
     if (L.streamed) {
+#pragma unroll 1
         for (int c = 0; c < L.nchunks; ++c) {
-            const float *w = S.acquire(*item, c);
+            const float *w = S.acquire();
+            PMB_WMARK();
             const int row0 = c * L.kc;
             const int rows = min(L.kc, L.K - row0);
             if (m.active) wide_accum<P>(acc, w, rows, L.Npad, act + (size_t)row0 * P, m);
+            PMB_WMARK();
         }
     } else {
         __syncthreads();
+        PMB_WMARK();
         if (m.active) wide_accum<P>(acc, res + L.soff, L.K, L.Npad, act, m);
+        PMB_WMARK();
     }
     if (m.ks == 1) {
         if (m.active) {
@@ -333,8 +366,11 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
             *reinterpret_cast<float4 *>(red + ((size_t)(m.g * P + p) * npad) + 4 * m.cq) =
                 make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
     }
+    PMB_WMARK();
     __syncthreads();
+    PMB_WMARK();
     if (m.active) {
+#pragma unroll 1
         for (int p = m.g; p < P; p += m.ks) {
             float4 s = *reinterpret_cast<const float4 *>(red + ((size_t)p * npad) + 4 * m.cq);
             for (int gg = 1; gg < m.ks; ++gg) {
@@ -344,44 +380,91 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
             epi(p, s);
         }
     }
+    PMB_WMARK();
+#undef PMB_WMARK
 }
 
-// narrow layer: out[p][j] = sum_k act[k][p] * w[j][k] (+ bias[j]).  One warp per group of up to 4
-// outputs (4 independent dot products in flight), lanes split k.  Starts with a __syncthreads();
-// results are visible after the caller's next barrier.
-template <int P>
-__device__ __forceinline__ void narrow_layer(const Lin &L, const float *res, const float *act, float *out,
-                                             const float *bias) {
+// thin-K wide layer (first layers, K = D / D+U; output-layer adjoints, K = 2D / 2U): one thread per
+// output column, all P particles, no k-split and no reduction.  epi(j, acc[P]) finishes column j.
+// Starts with a __syncthreads().
+template <int P, typename Epi>
+__device__ __forceinline__ void thin_layer(const Lin &L, const float *res, const float *act, Epi epi) {
     __syncthreads();
     const float *w = res + L.soff;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nout = P * L.Nout;
-    const int K = L.K;
-    for (int o0 = warp * 4; o0 < nout; o0 += NWARP * 4) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        int pj[4], wj[4];
+    const int K = L.K, npad = L.Npad;
+#pragma unroll 1
+    for (int j = threadIdx.x; j < L.Nout; j += NT) {
+        float acc[P];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int o = min(o0 + q, nout - 1);
-            int p = o / L.Nout;
-            pj[q] = p;
-            wj[q] = (o - p * L.Nout) * K;
-        }
-        for (int k = lane; k < K; k += 32) {
+        for (int p = 0; p < P; ++p) acc[p] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float wv = w[k * npad + j];
+            float a[P];
+            load_act<P>(a, act + k * P);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) s[q] = fmaf(act[k * P + pj[q]], w[wj[q] + k], s[q]);
+            for (int p = 0; p < P; ++p) acc[p] = fmaf(a[p], wv, acc[p]);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        epi(j, acc);
+    }
+}
+
+// narrow layer: out[p][j] = sum_k act[k][p] * w[j][k] (+ bias[j]) for P*Nout <= 256 outputs.
+// Outputs across lanes, the reduction axis k split across the warps that share an output: with
+// R = 256 / pow2ceil(P*Nout) k-slices per output, thread = (slice r, output o); partials meet in `red`.
+// The thread mapping is fixed for the whole horizon: NarrowMap is computed once per kernel.
+struct NarrowMap {
+    int active;      // this thread owns an (output, k-slice)
+    int final;       // this thread sums the slices of output o
+    int o, j, ol2, R;
+    int k0, k1;
+    int woff;        // j * K
+    int aoff;        // particle index p
+    template <int P>
+    __device__ __forceinline__ void set(const Lin &L) {
+        const int K = L.K, nout = L.Nout;
+        const int no = P * nout;
+        ol2 = no <= 32 ? 5 : no <= 64 ? 6 : no <= 128 ? 7 : 8;
+        R = NT >> ol2;
+        o = threadIdx.x & ((1 << ol2) - 1);
+        const int r = threadIdx.x >> ol2;
+        const int kper = (K + R - 1) / R;
+        k0 = min(K, r * kper);
+        k1 = min(K, k0 + kper);
+        active = o < no;
+        final = active && r == 0;
+        const int p = active ? o / nout : 0;
+        j = active ? o - p * nout : 0;
+        woff = j * K;
+        aoff = p;
+    }
+};
+
+// Starts with a __syncthreads() and contains a second one; results are visible after the caller's next
+// barrier.
+template <int P>
+__device__ __forceinline__ void narrow_layer(const Lin &L, const NarrowMap &nm, const float *res, const float *act,
+                                             float *out, const float *bias, float *red) {
+    __syncthreads();
+    if (nm.active) {
+        const float *wj = res + L.soff + nm.woff;
+        const float *ap = act + nm.aoff;
+        float s = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int k = nm.k0;
+        for (; k + 4 <= nm.k1; k += 4) {
+            s = fmaf(ap[k * P], wj[k], s);
+            s1 = fmaf(ap[(k + 1) * P], wj[k + 1], s1);
+            s2 = fmaf(ap[(k + 2) * P], wj[k + 2], s2);
+            s3 = fmaf(ap[(k + 3) * P], wj[k + 3], s3);
         }
-        if (lane < 4 && o0 + lane < nout) {
-            const int o = o0 + lane;
-            const int j = o - (o / L.Nout) * L.Nout;
-            const float v = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
-            out[o] = v + (bias ? bias[j] : 0.f);
-        }
+        for (; k < nm.k1; ++k) s = fmaf(ap[k * P], wj[k], s);
+        red[((threadIdx.x >> nm.ol2) << nm.ol2) + nm.o] = (s + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    if (nm.final) {
+        float v = red[nm.o];
+        for (int rr = 1; rr < nm.R; ++rr) v += red[(rr << nm.ol2) + nm.o];
+        out[nm.o] = v + (bias ? bias[nm.j] : 0.f);
     }
 }
 

@@ -24,47 +24,69 @@ constexpr int PRE_RS = 0, PRE_RA = 1, PRE_FD = 2, PRE_TP = 3, PRE_FP = 4, PRE_GS
 // Wide layers l = nlin-1 .. 1 (weights W_l as stored, [out][in]) produce the adjoint of hidden l-1,
 // gated by the stored activation; the final narrow layer (W_0^T) leaves d(input)[p][nin] in obuf.
 // With kStoreDelta every hidden adjoint is also written to global for the weight gradient.
-template <int P, bool kStoreDelta>
-__device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSweep &net, int &sched_i,
-                                             float *&in, float *&out, float *obuf, float *smem, float *red,
-                                             const float *sav, Stream &S, int t, int n0) {
+template <int P>
+__device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSweep &net, bool kStoreDelta,
+                                             int &sched_i, float *&in, float *&out, float *obuf, float *smem,
+                                             float *red, const float *sav, Stream &S, const NarrowMap &nm, int t,
+                                             int n0) {
     const int N = prm.N;
+#pragma unroll 1
     for (int l = net.nlin - 1; l >= 1; --l) {
         const Lin &L = net.lin[l];      // wide: K = outputs of linear l (padded), Npad = width of hidden l-1
         const int h = l - 1;            // hidden layer whose adjoint we produce
-        WideMap m;
-        m.set(L.Npad);
-        const int col = 4 * m.cq;
         const int npad = L.Npad;
-        const float *mask_s = net.mask_soff[h] >= 0 ? smem + net.mask_soff[h] + col : nullptr;
-        const float *mask_g = (!mask_s && net.mask_off[h] >= 0) ? prm.ws + net.mask_off[h] + col : nullptr;
-        const float *sv = sav + net.sav_soff[h] + col;
-        const float keep = net.keep[h];
-        float *dl = prm.ws + net.delta_off[h] + ((size_t)t * N + n0) * npad + col;
-        float *dst = out + col * P;
-        wide_layer<P>(L, L.streamed ? &prm.sched[sched_i] : nullptr, smem, in, red, S, m, [&](int p, float4 v) {
-            float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad);
-            else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad));
-            const float4 hh = *reinterpret_cast<const float4 *>(sv + p * npad);
-            // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
-            if (keep != 1.f) {
-                v.x = v.x / keep; v.y = v.y / keep; v.z = v.z / keep; v.w = v.w / keep;
+        const float *mask_s = net.mask_soff[h] >= 0 ? smem + net.mask_soff[h] : nullptr;
+        const float *mask_g = (!mask_s && net.mask_off[h] >= 0) ? prm.ws + net.mask_off[h] : nullptr;
+        const float *sv = sav + net.sav_soff[h];
+        // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
+        const float inv_keep = 1.f / net.keep[h];
+        float *dl = prm.ws + net.delta_off[h] + ((size_t)t * N + n0) * npad;
+        if (!L.streamed) {
+            // adjoint of the output projection: K = 2D / 2U rows
+            thin_layer<P>(L, smem, in, [&](int j, float (&acc)[P]) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float mk = 1.f;
+                    if (mask_s) mk = mask_s[p * npad + j];
+                    else if (mask_g) mk = __ldg(mask_g + (size_t)min(n0 + p, N - 1) * npad + j);
+                    const float hh = sv[p * npad + j];
+                    const float x = hh != 0.f ? acc[p] * inv_keep * mk : 0.f;
+                    out[j * P + p] = x;
+                    if (kStoreDelta && n0 + p < N) dl[(size_t)p * npad + j] = x;
+                }
+            });
+            for (int j = L.Nout + threadIdx.x; j < npad; j += NT) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    out[j * P + p] = 0.f;
+                    if (kStoreDelta && n0 + p < N) dl[(size_t)p * npad + j] = 0.f;
+                }
             }
-            v.x = hh.x != 0.f ? v.x * mk.x : 0.f;
-            v.y = hh.y != 0.f ? v.y * mk.y : 0.f;
-            v.z = hh.z != 0.f ? v.z * mk.z : 0.f;
-            v.w = hh.w != 0.f ? v.w * mk.w : 0.f;
-            dst[p] = v.x;
-            dst[P + p] = v.y;
-            dst[2 * P + p] = v.z;
-            dst[3 * P + p] = v.w;
-            if (kStoreDelta && n0 + p < N) *reinterpret_cast<float4 *>(dl + (size_t)p * npad) = v;
-        });
-        if (L.streamed) ++sched_i;
+        } else {
+            WideMap m;
+            m.set(npad);
+            const int col = 4 * m.cq;
+            float *dst = out + col * P;
+            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v) {
+                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad + col);
+                else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad + col));
+                const float4 hh = *reinterpret_cast<const float4 *>(sv + p * npad + col);
+                v.x = hh.x != 0.f ? v.x * inv_keep * mk.x : 0.f;
+                v.y = hh.y != 0.f ? v.y * inv_keep * mk.y : 0.f;
+                v.z = hh.z != 0.f ? v.z * inv_keep * mk.z : 0.f;
+                v.w = hh.w != 0.f ? v.w * inv_keep * mk.w : 0.f;
+                dst[p] = v.x;
+                dst[P + p] = v.y;
+                dst[2 * P + p] = v.z;
+                dst[3 * P + p] = v.w;
+                if (kStoreDelta && n0 + p < N) *reinterpret_cast<float4 *>(dl + (size_t)p * npad + col) = v;
+            });
+            ++sched_i;
+        }
         float *tmp = in; in = out; out = tmp;
     }
-    narrow_layer<P>(net.lin[0], smem, in, obuf, nullptr);
+    narrow_layer<P>(net.lin[0], nm, smem, in, obuf, nullptr, red);
 }
 
 template <int P>
@@ -72,6 +94,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[MAXS];
     __shared__ __align__(8) uint64_t sbar[2];
+    __shared__ __align__(16) ChunkDesc chunk_tab[MAXCHUNKS];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, KR = prm.KR;
@@ -102,6 +125,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     const int r_p = roleR ? tid - 224 : 0;
     const int r_n = min(n0 + r_p, N - 1);
 
+    for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
+    __syncthreads();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
@@ -109,8 +134,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
         mbar_init(&sbar[0], 1);
         mbar_init(&sbar[1], 1);
     }
+    NarrowMap nm_pol, nm_dyn;
+    nm_pol.set<P>(pol.lin[0]);
+    nm_dyn.set<P>(dyn.lin[0]);
     Stream S;
-    S.init(&prm, smem, bars);    // fences the mbarrier inits and synchronises the CTA (mode 2)
+    S.init(&prm, smem, bars, chunk_tab);    // fences the mbarrier inits and synchronises the CTA (mode 2)
     __syncthreads();
 
     // prefetch registers of the one-step-ahead precompute
@@ -240,7 +268,10 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     precompute_b(pre0 + cur * PRE_N * BL);
     __syncthreads();
 
+#pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
+        const bool dbg_on = prm.dbg != nullptr && blockIdx.x == 0 && tid == 0 && t == H / 2;
+        PMB_MARK(32);
         const int nxt = cur ^ 1;
         float *pre = pre0 + cur * PRE_N * BL;
         float *pren = pre0 + nxt * PRE_N * BL;
@@ -268,41 +299,51 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
             spar[cur] ^= 1u;
         }
         const float *sav = savb + (size_t)cur * prm.sav_floats;
-        net_backward<P, false>(prm, dyn, sched_i, in, out, obuf, smem, red, sav, S, t, n0);
-        __syncthreads();
-        // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash + policy
-        //      density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
-        if (roleX) {
-            const float v = obuf[x_p * dyn.nin + x_k] * cst[C_ISX + x_k];
-            if (x_k < D) {
-                gsp[x_p * SD + x_k] += v;
+        PMB_MARK(33);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const NetSweep &net = which ? pol : dyn;
+            net_backward<P>(prm, net, which == 1, sched_i, in, out, obuf, smem, red, sav, S, which ? nm_pol : nm_dyn, t,
+                            n0);
+            PMB_MARK(34 + 3 * which);
+            __syncthreads();
+            PMB_MARK(35 + 3 * which);
+            if (which == 0) {
+                // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
+                //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
+                if (roleX) {
+                    const float v = obuf[x_p * dyn.nin + x_k] * cst[C_ISX + x_k];
+                    if (x_k < D) {
+                        gsp[x_p * SD + x_k] += v;
+                    } else {
+                        const int u = x_k - D;
+                        const float ga = pre[PRE_RA * BL + x_p * SD + u] + v;
+                        const float du = ga * pre[PRE_TP * BL + x_p * SD + u];
+                        out[u * P + x_p] = du;
+                        float dls = 0.f;
+                        if (pol.has_density) {
+                            dls = du * pre[PRE_FP * BL + x_p * SD + u];
+                            out[(U + u) * P + x_p] = dls;
+                        }
+                        if (n0 + x_p < N) {
+                            float *dd = prm.ws + pol.delta_off[pol.nlin - 1] + ((size_t)t * N + n0 + x_p) * pol.nout;
+                            dd[u] = du;
+                            if (pol.has_density) dd[U + u] = dls;
+                        }
+                    }
+                }
+                if (t > 0) precompute_a(pren);
+                float *tmp = in; in = out; out = tmp;
             } else {
-                const int u = x_k - D;
-                const float ga = pre[PRE_RA * BL + x_p * SD + u] + v;
-                const float du = ga * pre[PRE_TP * BL + x_p * SD + u];
-                out[u * P + x_p] = du;
-                float dls = 0.f;
-                if (pol.has_density) {
-                    dls = du * pre[PRE_FP * BL + x_p * SD + u];
-                    out[(U + u) * P + x_p] = dls;
-                }
-                if (n0 + x_p < N) {
-                    float *dd = prm.ws + pol.delta_off[pol.nlin - 1] + ((size_t)t * N + n0 + x_p) * pol.nout;
-                    dd[u] = du;
-                    if (pol.has_density) dd[U + u] = dls;
-                }
+                // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
+                if (roleB)
+                    gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + obuf[b_p * pol.nin + b_d] + pre[PRE_GS0 * BL + b_p * SD + b_d];
+                if (t > 0) precompute_b(pren);
             }
+            PMB_MARK(36 + 3 * which);
         }
-        if (t > 0) precompute_a(pren);
-        {
-            float *tmp = in; in = out; out = tmp;
-        }
-        net_backward<P, true>(prm, pol, sched_i, in, out, obuf, smem, red, sav, S, t, n0);
         __syncthreads();
-        // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
-        if (roleB) gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + obuf[b_p * pol.nin + b_d] + pre[PRE_GS0 * BL + b_p * SD + b_d];
-        if (t > 0) precompute_b(pren);
-        __syncthreads();
+        PMB_MARK(40);
         cur = nxt;
     }
     if (prm.dx0 && roleB && n0 + b_p < N) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];

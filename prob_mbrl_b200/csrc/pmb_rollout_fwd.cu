@@ -16,64 +16,84 @@ namespace pmb {
 template <int P>
 __device__ __forceinline__ void net_forward(const SweepParams &prm, const NetSweep &net, int &sched_i,
                                             float *&in, float *&out, float *obuf, float *smem, float *red,
-                                            Stream &S, int t, int n0) {
+                                            Stream &S, const NarrowMap &nm, int t, int n0, bool dbg_on, int mark0) {
     const int N = prm.N;
+#pragma unroll 1
     for (int l = 0; l + 1 < net.nlin; ++l) {
         const Lin &L = net.lin[l];
-        WideMap m;
-        m.set(L.Npad);
-        const int col = 4 * m.cq;
-        const float *bias_s = L.bias_soff >= 0 ? smem + L.bias_soff + col : nullptr;
-        const float *mask_s = net.mask_soff[l] >= 0 ? smem + net.mask_soff[l] + col : nullptr;
-        const float *mask_g = (!mask_s && net.mask_off[l] >= 0) ? prm.ws + net.mask_off[l] + col : nullptr;
-        const float keep = net.keep[l];
-        float *sv = prm.ws + net.saved_off[l] + ((size_t)t * N + n0) * L.Npad + col;
-        float *dst = out + col * P;
         const int npad = L.Npad;
-        wide_layer<P>(L, L.streamed ? &prm.sched[sched_i] : nullptr, smem, in, red, S, m, [&](int p, float4 v) {
-            if (bias_s) {
-                const float4 b = *reinterpret_cast<const float4 *>(bias_s);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        const float *bias_s = L.bias_soff >= 0 ? smem + L.bias_soff : nullptr;
+        const float *mask_s = net.mask_soff[l] >= 0 ? smem + net.mask_soff[l] : nullptr;
+        const float *mask_g = (!mask_s && net.mask_off[l] >= 0) ? prm.ws + net.mask_off[l] : nullptr;
+        // relu, x * noise[:N] (modules.py:61,160), / p (BDropout only; multiplied by the fp32 reciprocal,
+        // <= 1 ulp from the reference's division)
+        const float inv_keep = 1.f / net.keep[l];
+        float *sv = prm.ws + net.saved_off[l] + ((size_t)t * N + n0) * npad;
+        if (!L.streamed) {
+            // first layer: K = D or D+U
+            thin_layer<P>(L, smem, in, [&](int j, float (&acc)[P]) {
+                const float b = bias_s ? bias_s[j] : 0.f;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float x = acc[p] + b;
+                    float mk = 1.f;
+                    if (mask_s) mk = mask_s[p * npad + j];
+                    else if (mask_g) mk = __ldg(mask_g + (size_t)min(n0 + p, N - 1) * npad + j);
+                    x = (x < 0.f ? 0.f : x) * mk * inv_keep;
+                    out[j * P + p] = x;
+                    if (n0 + p < N) sv[(size_t)p * npad + j] = x;
+                }
+            });
+            for (int j = L.Nout + threadIdx.x; j < npad; j += NT) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) out[j * P + p] = 0.f;
             }
-            float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad);
-            else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad));
-            // relu (NaN propagates like torch), x * noise[:N] (modules.py:61,160), ... / p (BDropout only)
-            v.x = (v.x < 0.f ? 0.f : v.x) * mk.x;
-            v.y = (v.y < 0.f ? 0.f : v.y) * mk.y;
-            v.z = (v.z < 0.f ? 0.f : v.z) * mk.z;
-            v.w = (v.w < 0.f ? 0.f : v.w) * mk.w;
-            if (keep != 1.f) {
-                v.x = v.x / keep; v.y = v.y / keep; v.z = v.z / keep; v.w = v.w / keep;
-            }
-            dst[p] = v.x;
-            dst[P + p] = v.y;
-            dst[2 * P + p] = v.z;
-            dst[3 * P + p] = v.w;
-            if (n0 + p < N) *reinterpret_cast<float4 *>(sv + (size_t)p * npad) = v;
-        });
-        if (L.streamed) ++sched_i;
+        } else {
+            WideMap m;
+            m.set(npad);
+            const int col = 4 * m.cq;
+            float *dst = out + col * P;
+            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v) {
+                if (bias_s) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bias_s + col);
+                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad + col);
+                else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad + col));
+                v.x = (v.x < 0.f ? 0.f : v.x) * mk.x * inv_keep;
+                v.y = (v.y < 0.f ? 0.f : v.y) * mk.y * inv_keep;
+                v.z = (v.z < 0.f ? 0.f : v.z) * mk.z * inv_keep;
+                v.w = (v.w < 0.f ? 0.f : v.w) * mk.w * inv_keep;
+                dst[p] = v.x;
+                dst[P + p] = v.y;
+                dst[2 * P + p] = v.z;
+                dst[3 * P + p] = v.w;
+                if (n0 + p < N) *reinterpret_cast<float4 *>(sv + (size_t)p * npad + col) = v;
+            }, dbg_on ? prm.dbg + 64 + 12 * (mark0 + l) : nullptr);
+            ++sched_i;
+        }
         float *tmp = in; in = out; out = tmp;
+        PMB_MARK(mark0 + l);
     }
     const Lin &Lo = net.lin[net.nlin - 1];
-    narrow_layer<P>(Lo, smem, in, obuf, Lo.bias_soff >= 0 ? smem + Lo.bias_soff : nullptr);
+    narrow_layer<P>(Lo, nm, smem, in, obuf, Lo.bias_soff >= 0 ? smem + Lo.bias_soff : nullptr, red);
+    PMB_MARK(mark0 + net.nlin - 1);
 }
 
 template <int P>
 __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constant__ SweepParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[MAXS];
+    __shared__ __align__(16) ChunkDesc chunk_tab[MAXCHUNKS];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
-    const NetSweep &pol = prm.pol;
-    const NetSweep &dyn = prm.dyn;
     float *cst = smem + prm.off_cst;
     float *act0 = smem + prm.off_act0;
     float *act1 = smem + prm.off_act1;
     float *red = smem + prm.off_red;
-    float *misc = smem + prm.off_misc;
-    float *s_cur = misc, *s_nxt = misc + P * SD, *abuf = misc + 2 * P * SD, *obuf = misc + 3 * P * SD;
+    float *obuf = smem + prm.off_misc;
 
     // ---- thread roles for the per-particle stages (fixed for the whole horizon) ----
     const bool roleA = tid < P * U;                       // one (particle, action dim)
@@ -82,102 +102,113 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     const bool roleB = tid >= 128 && tid - 128 < P * D;   // one (particle, state dim)
     const int b_p = roleB ? (tid - 128) / D : 0, b_d = roleB ? (tid - 128) - b_p * D : 0;
     const int b_n = min(n0 + b_p, N - 1);
-    const bool roleOp = tid < P * pol.nout;               // raw policy outputs to keep for the reverse sweep
-    const int op_p = roleOp ? tid / pol.nout : 0, op_j = roleOp ? tid - op_p * pol.nout : 0;
-    const bool roleOd = tid < P * dyn.nout;
-    const int od_p = roleOd ? tid / dyn.nout : 0, od_j = roleOd ? tid - od_p * dyn.nout : 0;
+    // raw outputs kept for the reverse sweep: thread -> (particle, output) of the policy / dynamics net
+    const int op_p = tid / prm.pol.nout, op_j = tid - op_p * prm.pol.nout;
+    const int od_p = tid / prm.dyn.nout, od_j = tid - od_p * prm.dyn.nout;
 
+    for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
+    __syncthreads();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
+    float s_reg = 0.f;            // role B: this thread's element of the current state (never leaves registers)
     if (roleB) {
-        const float v = prm.x0[(size_t)b_n * D + b_d];
-        s_cur[b_p * SD + b_d] = v;
-        if (n0 + b_p < N) prm.states[(size_t)b_n * D + b_d] = v;
+        s_reg = prm.x0[(size_t)b_n * D + b_d];
+        act0[b_d * P + b_p] = s_reg;
+        if (n0 + b_p < N) prm.states[(size_t)b_n * D + b_d] = s_reg;
     }
     float zA = 0.f, zB = 0.f;
-    if (roleA && pol.has_density) zA = __ldg(pol.z + (size_t)a_n * U + a_u);
-    if (roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)b_n * D + b_d);
+    if (roleA && prm.pol.has_density) zA = __ldg(prm.pol.z + (size_t)a_n * U + a_u);
+    if (roleB && prm.dyn.has_density) zB = __ldg(prm.dyn.z + (size_t)b_n * D + b_d);
+    NarrowMap nm_pol, nm_dyn;
+    nm_pol.set<P>(prm.pol.lin[prm.pol.nlin - 1]);
+    nm_dyn.set<P>(prm.dyn.lin[prm.dyn.nlin - 1]);
     Stream S;
-    S.init(&prm, smem, bars);
+    S.init(&prm, smem, bars, chunk_tab);
     __syncthreads();
 
+#pragma unroll 1
     for (int t = 0; t < H; ++t) {
+        const bool dbg_on = prm.dbg != nullptr && blockIdx.x == 0 && tid == 0 && t == H / 2;
+        PMB_MARK(0);
+        S.dbgp = dbg_on ? prm.dbg + 256 : nullptr;
         int sched_i = 0;
         float *in = act0, *out = act1;
         // per-step noise (only when the caller pre-drew [H, N, .] tables): issue the loads early
-        if (pol.zstride != 0 && roleA && pol.has_density) zA = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)a_n * U + a_u);
-        if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
-        // ---- policy input tile ----
-        if (roleB) in[b_d * P + b_p] = s_cur[b_p * SD + b_d];
-        net_forward<P>(prm, pol, sched_i, in, out, obuf, smem, red, S, t, n0);
-        __syncthreads();
-        // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
-        //      dynamics input (core.py:269,177) ----
-        if (roleA) {
-            float uu;
-            if (pol.has_density) {
-                const float mu = obuf[a_p * pol.nout + a_u];
-                const float ls = clamp_logstd(obuf[a_p * pol.nout + U + a_u], pol.lmax);
-                uu = mu + zA * expf(ls);
+        if (prm.pol.zstride != 0 && roleA && prm.pol.has_density)
+            zA = __ldg(prm.pol.z + (size_t)t * prm.pol.zstride + (size_t)a_n * U + a_u);
+        if (prm.dyn.zstride != 0 && roleB && prm.dyn.has_density)
+            zB = __ldg(prm.dyn.z + (size_t)t * prm.dyn.zstride + (size_t)b_n * D + b_d);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const NetSweep &net = which ? prm.dyn : prm.pol;
+            net_forward<P>(prm, net, sched_i, in, out, obuf, smem, red, S, which ? nm_dyn : nm_pol, t, n0, dbg_on,
+                           1 + 8 * which);
+            __syncthreads();
+            PMB_MARK(7 + 8 * which);
+            if (which == 0) {
+                // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
+                //      dynamics input (core.py:269,177) ----
+                if (roleA) {
+                    float uu = obuf[a_p * net.nout + a_u];
+                    if (net.has_density) uu += zA * expf(clamp_logstd(obuf[a_p * net.nout + U + a_u], net.lmax));
+                    const float a = cst[C_SCALE + a_u] * tanhf(uu) + cst[C_BIAS + a_u];
+                    if (n0 + a_p < N) prm.actions[((size_t)t * N + a_n) * U + a_u] = a;
+                    out[(D + a_u) * P + a_p] = (a - cst[C_MX + D + a_u]) * cst[C_ISX + D + a_u];
+                }
+                if (roleB) out[b_d * P + b_p] = (s_reg - cst[C_MX + b_d]) * cst[C_ISX + b_d];
+                if (tid < P * net.nout && n0 + op_p < N)
+                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + op_p) * net.nout + op_j] = obuf[tid];
+                float *tmp = in; in = out; out = tmp;
             } else {
-                uu = obuf[a_p * pol.nout + a_u];
+                // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298);
+                //      it is also the next step's policy input ----
+                if (roleB) {
+                    const float sy = cst[C_SY + b_d], my = cst[C_MY + b_d];
+                    float delta;
+                    if (net.has_density) {
+                        const float mu = obuf[b_p * net.nout + b_d];
+                        const float ls = clamp_logstd(obuf[b_p * net.nout + D + b_d], net.lmax) + cst[C_LSY + b_d];
+                        delta = (mu * sy + my) + zB * expf(ls);
+                    } else {
+                        delta = obuf[b_p * net.nout + b_d] * sy + my;
+                    }
+                    s_reg += delta;
+                    act0[b_d * P + b_p] = s_reg;
+                    if (n0 + b_p < N) prm.states[((size_t)(t + 1) * N + b_n) * D + b_d] = s_reg;
+                }
+                if (tid < P * net.nout && n0 + od_p < N)
+                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + od_p) * net.nout + od_j] = obuf[tid];
             }
-            const float a = cst[C_SCALE + a_u] * tanhf(uu) + cst[C_BIAS + a_u];
-            abuf[a_p * SD + a_u] = a;
-            if (n0 + a_p < N) prm.actions[((size_t)t * N + a_n) * U + a_u] = a;
-            out[(D + a_u) * P + a_p] = (a - cst[C_MX + D + a_u]) * cst[C_ISX + D + a_u];
+            PMB_MARK(8 + 8 * which);
         }
-        if (roleB) out[b_d * P + b_p] = (s_cur[b_p * SD + b_d] - cst[C_MX + b_d]) * cst[C_ISX + b_d];
-        if (roleOp && n0 + op_p < N)
-            prm.ws[pol.outsaved_off + ((size_t)t * N + n0 + op_p) * pol.nout + op_j] = obuf[tid];
-        {
-            float *tmp = in; in = out; out = tmp;
+    }
+    // ---- rewards r_t = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset on (s_{t+1}, a_t) for every step
+    //      (envs/cartpole/env.py:62-86).  Nothing in the recurrence consumes them, so they are
+    //      evaluated here, off the serial chain, from the trajectory this CTA just wrote. ----
+    __syncthreads();
+    for (int i = tid; i < H * P; i += NT) {
+        const int tt = i / P, p = i - tt * P;
+        if (n0 + p >= N) continue;
+        const float *s1 = prm.states + ((size_t)(tt + 1) * N + n0 + p) * D;
+        const float *a = prm.actions + ((size_t)tt * N + n0 + p) * U;
+        float dl[PMB_MAX_REWARD_ROWS];
+        for (int r = 0; r < prm.KR; ++r) {
+            float acc = cst[C_C0 + r];
+            for (int d = 0; d < D; ++d) acc = fmaf(cst[C_C + r * SD + d], s1[d], acc);
+            dl[r] = acc;
         }
-        net_forward<P>(prm, dyn, sched_i, in, out, obuf, smem, red, S, t, n0);
-        __syncthreads();
-        // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
-        if (roleB) {
-            const float sy = cst[C_SY + b_d], my = cst[C_MY + b_d];
-            float delta;
-            if (dyn.has_density) {
-                const float mu = obuf[b_p * dyn.nout + b_d];
-                const float ls = clamp_logstd(obuf[b_p * dyn.nout + D + b_d], dyn.lmax) + cst[C_LSY + b_d];
-                delta = (mu * sy + my) + zB * expf(ls);
-            } else {
-                delta = obuf[b_p * dyn.nout + b_d] * sy + my;
-            }
-            const float s1 = s_cur[b_p * SD + b_d] + delta;
-            s_nxt[b_p * SD + b_d] = s1;
-            if (n0 + b_p < N) prm.states[((size_t)(t + 1) * N + b_n) * D + b_d] = s1;
+        float cost = 0.f;
+        for (int r = 0; r < prm.KR; ++r) {
+            float q = 0.f;
+            for (int j = 0; j < prm.KR; ++j) q = fmaf(dl[j], cst[C_Q + j * 4 + r], q);
+            cost = fmaf(q, dl[r], cost);
         }
-        if (roleOd && n0 + od_p < N)
-            prm.ws[dyn.outsaved_off + ((size_t)t * N + n0 + od_p) * dyn.nout + od_j] = obuf[tid];
-        __syncthreads();
-        // ---- reward on (s', a) (envs/cartpole/env.py:62-86) ----
-        if (tid < P && n0 + tid < N) {
-            const int p = tid;
-            float dl[PMB_MAX_REWARD_ROWS];
-            for (int i = 0; i < prm.KR; ++i) {
-                float s = cst[C_C0 + i];
-                for (int d = 0; d < D; ++d) s = fmaf(cst[C_C + i * SD + d], s_nxt[p * SD + d], s);
-                dl[i] = s;
-            }
-            float cost = 0.f;
-            for (int i = 0; i < prm.KR; ++i) {
-                float q = 0.f;
-                for (int j = 0; j < prm.KR; ++j) q = fmaf(dl[j], cst[C_Q + j * 4 + i], q);
-                cost = fmaf(q, dl[i], cost);
-            }
-            for (int u = 0; u < U; ++u) {
-                float q = 0.f;
-                for (int v = 0; v < U; ++v) q = fmaf(abuf[p * SD + v], cst[C_R + v * SD + u], q);
-                cost = fmaf(q, abuf[p * SD + u], cost);
-            }
-            prm.rewards[(size_t)t * N + n0 + p] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
+        for (int u = 0; u < U; ++u) {
+            float q = 0.f;
+            for (int v = 0; v < U; ++v) q = fmaf(a[v], cst[C_R + v * SD + u], q);
+            cost = fmaf(q, a[u], cost);
         }
-        {
-            float *tmp = s_cur; s_cur = s_nxt; s_nxt = tmp;
-        }
+        prm.rewards[(size_t)tt * N + n0 + p] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
     }
 }
 

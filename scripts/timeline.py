@@ -1,0 +1,44 @@
+"""Phase timeline (clock64 marks) of one forward and one backward step of the bench workload."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["PMB_CUDA_GRAPH"] = "0"; os.environ["PMB_NO_PBAR"] = "1"
+import torch, bench
+import prob_mbrl_b200 as pm
+from prob_mbrl_b200 import _lib
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+n = bench.CONFIGS[cfg][5]
+dyn, pol, x0, H = bench.build_workload(cfg, n, "cuda")
+opt = torch.optim.Adam(pol.parameters(), 1e-4)
+g_r = torch.full((H, n), -1.0 / (H * n), device="cuda")
+eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0)
+eng.step(x0.cuda()); eng.step(x0.cuda())
+dbg = torch.zeros(512, dtype=torch.int64, device="cuda")
+ptr = dbg.data_ptr()
+eng.tune.reserved[2] = ptr & 0xffffffff if (ptr & 0xffffffff) < 2**31 else (ptr & 0xffffffff) - 2**32
+eng.tune.reserved[3] = ptr >> 32
+eng.step(x0.cuda()); torch.cuda.synchronize()
+d = dbg.cpu().tolist()
+names_f = {0:"top",1:"pol L0",2:"pol L1",3:"pol out(narrow)",7:"sync",8:"squash stage",9:"dyn L0",10:"dyn L1",11:"dyn out(narrow)",15:"sync",16:"density"}
+prev = d[0]
+print("forward step (cycles):")
+for k in sorted(names_f):
+    if d[k]: print("  %-18s +%6d  (t=%6d)" % (names_f[k], d[k]-prev, d[k]-d[0])); prev = d[k]
+names_b = {32:"top",33:"density+wait sav",34:"dyn net bwd",35:"sync",36:"scaler+squash+preA",37:"pol net bwd",38:"sync",39:"gs+preB",40:"sync/end"}
+prev = d[32]
+print("backward step (cycles):")
+for k in sorted(names_b):
+    if d[k]: print("  %-18s +%6d  (t=%6d)" % (names_b[k], d[k]-prev, d[k]-d[32])); prev = d[k]
+
+print("wide-layer internals (fwd): marks = entry, [acquire/sync, accumulate]*, partial write, reduce sync, epilogue")
+for nm, base in (("pol L1", 2), ("dyn L1", 10)):
+    v = d[64 + 12 * base: 64 + 12 * base + 12]
+    v = [x for x in v if x]
+    print("  %-7s" % nm, [v[i + 1] - v[i] for i in range(len(v) - 1)])
+
+v = d[256:256+16]
+print("acquire internals (fwd, 4 chunks): [sync, issue, mbar wait] each:")
+for c in range(4):
+    q = v[4*c:4*c+4]
+    print("   chunk", c, [q[i+1]-q[i] for i in range(3)])
+
