@@ -379,3 +379,35 @@ def forward_with_saved(d, x0, H):
         rewards.append(r)
         s = s1
     return states, actions, rewards, saved
+
+
+# --------------------------------------------------------------------------- #
+# hand-derived adjoint of moment matching: the spec of the CUDA mm reverse step
+# --------------------------------------------------------------------------- #
+def mm_forward_parts(x, z, jitter=1e-12):
+    """mm_resample (reference utils/rollout.py:20-29) returning the pieces the reverse step needs."""
+    M = x.shape[0]
+    m = x.mean(0)
+    dx = x - m
+    S = dx.t() @ dx / (M - 1) + jitter * torch.eye(x.shape[1], dtype=x.dtype)
+    L = torch.linalg.cholesky(S)
+    zh = (z - z.mean(0)) / z.std(0)
+    return m + zh @ L.t(), m, L, zh
+
+
+def mm_backward(g_out, x, m, L, zh):
+    """Adjoint of x' = m + zh L^T w.r.t. the particles x (zh detached), with
+    S = (x-m)^T (x-m)/(M-1) + jitter, L = chol(S):
+        dm = sum_n g_n,  dL = tril(sum_n g_n zh_n^T),
+        Sbar = sym( L^-T Phi(L^T dL) L^-1 )   (Phi: lower triangle, diagonal halved),
+        dx_n = dm/M + 2/(M-1) * Sbar (x_n - m)."""
+    M = x.shape[0]
+    dm = g_out.sum(0)
+    dL = torch.tril(g_out.t() @ zh)
+    A = L.t() @ dL
+    Pm = torch.tril(A)
+    Pm = Pm - 0.5 * torch.diag(torch.diagonal(A))
+    X = torch.linalg.solve_triangular(L.t(), Pm, upper=True)            # L^-T P
+    Sb = torch.linalg.solve_triangular(L.t(), X.t(), upper=True).t()   # (L^-T P) L^-1 = (L^-T X^T)^T
+    Sb = 0.5 * (Sb + Sb.t())
+    return dm / M + (2.0 / (M - 1)) * (x - m) @ Sb

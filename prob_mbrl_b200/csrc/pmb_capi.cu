@@ -8,6 +8,7 @@
 
 #include "pmb_host.h"
 #include "pmb_internal.cuh"
+#include "pmb_mm.cuh"
 
 namespace pmb {
 
@@ -42,6 +43,8 @@ struct Plan {
     long long job_dst_off[MAX_PACK_JOBS];
     long long wpack_fwd_off, wpack_bwd_off;
     long long part_off;
+    long long s1pre_off, mmstat_off, mmrec_off, mmctr_off, rpre_off, rstat_off, geff_off;
+    int mm_G;
     long long nparam;
     long long ws_floats;
     int smem_fwd_bytes, smem_bwd_bytes;
@@ -153,7 +156,7 @@ static void plan_net(const pmb_net &net, int N, int H, bool is_policy, NetSweep 
 
 // shared-memory carve-up + stream schedule of one sweep
 static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, int P, int stream_mode,
-                      int nstages_req) {
+                      int nstages_req, bool mm_states) {
     int off = 0;
     S.nres = 0;
     S.nsched = 0;
@@ -191,6 +194,8 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
     S.off_act1 = off; off += ((tile_rows * P) + 31) & ~31;
     S.off_red = off;  off += 1024 * P;
     S.off_misc = off; off += 320 * P;
+    S.off_mm = off;
+    if (mm_states) off += (mm_smem_floats(P) + 31) & ~31;
     // backward: two buffers for the stored hidden activations of a step
     S.off_sav = off;
     S.sav_floats = 0;
@@ -276,12 +281,31 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     int rc;
     if ((rc = check_net(p->pol, p->D, p->pol.has_density ? 2 * p->U : p->U, "policy"))) return rc;
     if ((rc = check_net(p->dyn, p->D + p->U, p->dyn.has_density ? 2 * p->D : p->D, "dynamics"))) return rc;
-    if (p->mm_states || p->mm_rewards) return fail(PMB_E_UNSUPPORTED, "moment matching is not built into this library version");
+    const bool mm = p->mm_states || p->mm_rewards;
+    const int G = p->mm_groups > 1 ? p->mm_groups : 1;
+    if (mm) {
+        if (p->mm_states && !p->z_mm) return fail(PMB_E_INVALID, "mm_states needs z_mm");
+        if (p->mm_rewards && !p->z_rr) return fail(PMB_E_INVALID, "mm_rewards needs z_rr");
+        if (p->N % G != 0) return fail(PMB_E_INVALID, "N=%d is not divisible by mm_groups=%d", p->N, G);
+        if (p->N / G < 2) return fail(PMB_E_INVALID, "moment matching needs at least 2 particles per group");
+        if (p->n_global != p->N) return fail(PMB_E_UNSUPPORTED, "moment matching across devices is not supported");
+    }
 
     memset(&pl, 0, sizeof(pl));
+    pl.mm_G = G;
     int P = tune && tune->particles_per_cta ? tune->particles_per_cta : 0;
     if (P == 0) P = (p->N > 8 * 148) ? 8 : (p->N > 2 * 148) ? 4 : 2;   // few particles: spread over more SMs
     if (P != 1 && P != 2 && P != 4 && P != 8) return fail(PMB_E_INVALID, "particles_per_cta must be 1, 2, 4 or 8");
+    if (p->mm_states) {
+        // every CTA of the grid takes part in a per-step barrier: CTAs must not straddle groups and the
+        // whole grid must be co-resident (one CTA per SM)
+        if (G > 1) while (P > 1 && (p->N / G) % P != 0) P >>= 1;
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        while (P < 8 && (p->N + P - 1) / P > sms && (G == 1 || (p->N / G) % (2 * P) == 0)) P <<= 1;
+        if ((p->N + P - 1) / P > sms)
+            return fail(PMB_E_UNSUPPORTED, "mm_states with N=%d particles does not fit one co-resident grid", p->N);
+    }
     pl.P = P;
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
     if (pl.stream_mode != 1 && pl.stream_mode != 2) return fail(PMB_E_INVALID, "stream_mode must be 1 or 2");
@@ -315,6 +339,17 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     pl.nparam = np;
     pl.part_off = ws.take((long long)pl.nsplit * np);
+    if (mm) {
+        const long long HN = (long long)p->H * p->N;
+        const int grid = (p->N + P - 1) / P;
+        pl.s1pre_off = ws.take(HN * p->D);
+        pl.mmstat_off = ws.take((long long)p->H * G * (3 * SD + SD * SD));
+        pl.mmrec_off = ws.take(2LL * grid * MMREC * 2);      // doubles
+        pl.mmctr_off = ws.take(32);
+        pl.rpre_off = ws.take(HN);
+        pl.rstat_off = ws.take((long long)p->H * G * 4);
+        pl.geff_off = ws.take(HN);
+    }
     pl.ws_floats = ws.top;
 
     for (int pass = 0; pass < 2; ++pass) {
@@ -324,13 +359,15 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         S.mx = p->mx; S.iSx = p->iSx; S.my = p->my; S.Sy = p->Sy;
         S.KR = p->rew_rows; S.rew_C = p->rew_C; S.rew_c0 = p->rew_c0; S.rew_Q = p->rew_Q; S.rew_R = p->rew_R;
         S.rew_scale = p->rew_scale; S.rew_offset = p->rew_offset;
+        S.mm_states = p->mm_states; S.mm_rewards = p->mm_rewards; S.mm_G = G; S.mm_Ng = p->N / G;
+        S.z_mm = p->z_mm;
     }
     const NetSweep *fo[2] = {&F.pol, &F.dyn};
     const NetSweep *bo[2] = {&B.dyn, &B.pol};
     const int nst = tune ? tune->reserved[1] : 0;
-    if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode, nst)) < 0) return rc;
+    if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode, nst, p->mm_states != 0)) < 0) return rc;
     pl.smem_fwd_bytes = rc;
-    if ((rc = plan_sweep(B, bo, true, P, pl.stream_mode, nst)) < 0) return rc;
+    if ((rc = plan_sweep(B, bo, true, P, pl.stream_mode, nst, p->mm_states != 0)) < 0) return rc;
     pl.smem_bwd_bytes = rc;
     return PMB_OK;
 }
@@ -346,6 +383,15 @@ static void resolve(Plan &pl, float *ws) {
     pl.fwd.ws = pl.bwd.ws = ws;
     pl.fwd.wpack = ws + pl.wpack_fwd_off;
     pl.bwd.wpack = ws + pl.wpack_bwd_off;
+    if (pl.fwd.mm_states || pl.fwd.mm_rewards) {
+        for (int pass = 0; pass < 2; ++pass) {
+            SweepParams &S = pass ? pl.bwd : pl.fwd;
+            S.s1pre = ws + pl.s1pre_off;
+            S.mmstat = ws + pl.mmstat_off;
+            S.mmrec = reinterpret_cast<double *>(ws + pl.mmrec_off);
+            S.mmctr = reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + pass;   // one counter per sweep
+        }
+    }
 }
 
 }  // namespace pmb
@@ -400,9 +446,16 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     if (status_dev) PMB_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
     if (phases & 1) PMB_CUDA(launch_pack(pl.jobs, st));
     SweepParams &F = pl.fwd;
-    F.x0 = x0; F.states = states; F.actions = actions; F.rewards = rewards; F.status = status_dev;
+    float *wsf = (float *)workspace;
+    F.x0 = x0; F.states = states; F.actions = actions; F.status = status_dev;
+    // with mm_rewards the sweep writes the pre-matching rewards; a whole-horizon kernel matches them
+    F.rewards = p->mm_rewards ? wsf + pl.rpre_off : rewards;
+    if (p->mm_states) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
     F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     if (phases & 2) PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
+    if (p->mm_rewards)
+        PMB_CUDA(launch_reward_mm_fwd(wsf + pl.rpre_off, rewards, p->z_rr, wsf + pl.rstat_off, p->N, p->H, pl.mm_G,
+                                      status_dev, st));
     return PMB_OK;
 }
 
@@ -423,6 +476,17 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     B.states = const_cast<float *>(states); B.actions = const_cast<float *>(actions);
     B.rewards = const_cast<float *>(rewards);
     B.g_states = g_states; B.g_actions = g_actions; B.g_rewards = g_rewards; B.dx0 = dx0;
+    if (p->mm_rewards) {
+        // adjoint of the reward matching runs first, off the serial chain; the sweep then sees the
+        // pre-matching rewards and their cotangent
+        B.rewards = ws + pl.rpre_off;
+        if (g_rewards) {
+            PMB_CUDA(launch_reward_mm_bwd(g_rewards, ws + pl.rpre_off, p->z_rr, ws + pl.rstat_off, ws + pl.geff_off,
+                                          p->N, p->H, pl.mm_G, st));
+            B.g_rewards = ws + pl.geff_off;
+        }
+    }
+    if (p->mm_states) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
     if (phases & 2) PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));

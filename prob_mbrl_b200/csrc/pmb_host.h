@@ -24,6 +24,10 @@ cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cu
 cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb, int Nc, long long R, int nsplit,
                          float *part, long long part_stride, cudaStream_t stream);
 cudaError_t launch_reduce_partials(const float *part, long long n, int nsplit, float *out, cudaStream_t stream);
+cudaError_t launch_reward_mm_fwd(const float *rpre, float *rout, const float *z_rr, float *rstat, int N, int H, int G,
+                                 int *status, cudaStream_t stream);
+cudaError_t launch_reward_mm_bwd(const float *gout, const float *rpre, const float *z_rr, const float *rstat, float *gin,
+                                 int N, int H, int G, cudaStream_t stream);
 cudaError_t launch_clip_adam(const pmb_adam_tensor *tab, int nt, float max_norm, float lr, float beta1, float beta2,
                              float eps, long long step, long long *step_dev, float *scratch, cudaStream_t stream);
 

@@ -85,6 +85,14 @@ struct SweepParams {
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
     int *status;
+    // moment matching (pmb_mm.cuh)
+    int mm_states, mm_rewards, mm_G, mm_Ng;
+    const float *z_mm;
+    float *s1pre;               // [H][N][D] particles before moment matching
+    float *mmstat;              // [H][G][3*SD + SD*SD] mean, z mean, 1/z std, Cholesky factor of every step
+    double *mmrec;              // [2][grid][MMREC] per-CTA block statistics
+    unsigned *mmctr;            // grid-barrier arrival counter (zeroed before launch)
+    int off_mm;                 // shared-memory scratch of the mm step (floats)
     long long *dbg;             // profiling aid: clock64() marks of CTA 0 / thread 0 at step H/2 (nullable)
     // streaming schedule for one step, in consumption order
     int nsched;

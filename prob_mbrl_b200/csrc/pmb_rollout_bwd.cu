@@ -13,6 +13,7 @@
 // from global loads issued at the top of the previous step, and the stored hidden activations of the
 // step arrive by TMA bulk copies issued one step ahead: the serial chain only touches shared memory.
 #include "pmb_internal.cuh"
+#include "pmb_mm.cuh"
 
 namespace pmb {
 
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     float pf_r = 0.f, pf_gr = 0.f;                                            // role R
     auto prefetch = [&](int tt) {
         if (roleB) {
-            pf_s1 = __ldg(prm.states + ((size_t)(tt + 1) * N + b_n) * D + b_d);
+            // the reward (and the mm adjoint) act on the next state BEFORE moment matching
+            pf_s1 = prm.mm_states ? __ldg(prm.s1pre + ((size_t)tt * N + b_n) * D + b_d)
+                                  : __ldg(prm.states + ((size_t)(tt + 1) * N + b_n) * D + b_d);
             if (dyn.has_density) {
                 pf_ls = __ldg(prm.ws + dyn.outsaved_off + ((size_t)tt * N + b_n) * dyn.nout + D + b_d);
                 pf_zd = __ldg(dyn.z + (size_t)tt * dyn.zstride + (size_t)b_n * D + b_d);
@@ -253,6 +256,14 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
         }
     };
     const bool has_sav = (pol.nlin > 1) || (dyn.nlin > 1);
+    MMSmem mmS;
+    MMGroup grp;
+    unsigned epoch = 0;
+    if (prm.mm_states) {
+        mmS.carve<P>(smem + prm.off_mm);
+        mmS.xs = stg_s1;            // the staged pre-mm particles of the current step
+        grp.set<P>(prm, n0);
+    }
 
     // ---- prologue: everything step H-1 needs ----
     int cur = 0;
@@ -285,6 +296,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
                 copy_saved(t - 1, nxt);
             }
             prefetch(t - 1);
+        }
+        // ---- moment matching adjoint: cotangent of x' = m + zhat chol(S)^T  ->  cotangent of x ----
+        if (prm.mm_states) {
+            if (roleB) mmS.zs[b_p * SD + b_d] = __ldg(prm.z_mm + (size_t)((t + n0 + b_p) % N) * D + b_d);
+            mm_states_backward<P>(prm, mmS, grp, t, gs, roleB, b_p, b_d, epoch);
         }
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
@@ -357,7 +373,14 @@ cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cu
         e = cudaFuncSetAttribute(rollout_bwd_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                  smem_bytes);                                                                \
         if (e != cudaSuccess) return e;                                                                      \
-        rollout_bwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                       \
+        if (prm.mm_states) {                                                                                 \
+            void *args[] = {(void *)&prm};                                                                   \
+            e = cudaLaunchCooperativeKernel((void *)rollout_bwd_kernel<PP>, dim3(grid), dim3(NT), args,      \
+                                            smem_bytes, stream);                                             \
+            if (e != cudaSuccess) return e;                                                                  \
+        } else {                                                                                             \
+            rollout_bwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                   \
+        }                                                                                                    \
         break;
     switch (P) {
         PMB_LAUNCH_BWD(1)

@@ -7,6 +7,7 @@
 // B/CDropout masks (models/modules.py:61,160), DiagGaussianDensity (models/densities.py:87-121)
 // and the env reward (envs/cartpole/env.py:41-86 et al.).
 #include "pmb_internal.cuh"
+#include "pmb_mm.cuh"
 
 namespace pmb {
 
@@ -124,6 +125,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     nm_dyn.set<P>(prm.dyn.lin[prm.dyn.nlin - 1]);
     Stream S;
     S.init(&prm, smem, bars, chunk_tab);
+    MMSmem mmS;
+    MMGroup grp;
+    unsigned epoch = 0;
+    if (prm.mm_states) {
+        mmS.carve<P>(smem + prm.off_mm);
+        grp.set<P>(prm, n0);
+    }
     __syncthreads();
 
 #pragma unroll 1
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
             zA = __ldg(prm.pol.z + (size_t)t * prm.pol.zstride + (size_t)a_n * U + a_u);
         if (prm.dyn.zstride != 0 && roleB && prm.dyn.has_density)
             zB = __ldg(prm.dyn.z + (size_t)t * prm.dyn.zstride + (size_t)b_n * D + b_d);
+        float zrow = 0.f;      // moment matching: this particle's row of z_mm, rotated by the step index
+        if (prm.mm_states && roleB) zrow = __ldg(prm.z_mm + (size_t)((t + n0 + b_p) % N) * D + b_d);
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
             const NetSweep &net = which ? prm.dyn : prm.pol;
@@ -173,6 +183,10 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
                         delta = obuf[b_p * net.nout + b_d] * sy + my;
                     }
                     s_reg += delta;
+                }
+                if (prm.mm_states)      // rollout.py:121-132
+                    mm_states_forward<P>(prm, mmS, grp, t, n0, roleB, b_p, b_d, b_n, s_reg, zrow, epoch);
+                if (roleB) {
                     act0[b_d * P + b_p] = s_reg;
                     if (n0 + b_p < N) prm.states[((size_t)(t + 1) * N + b_n) * D + b_d] = s_reg;
                 }
@@ -189,7 +203,9 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     for (int i = tid; i < H * P; i += NT) {
         const int tt = i / P, p = i - tt * P;
         if (n0 + p >= N) continue;
-        const float *s1 = prm.states + ((size_t)(tt + 1) * N + n0 + p) * D;
+        // the reward sees the next state BEFORE moment matching (models/core.py:293 runs inside dynamics())
+        const float *s1 = prm.mm_states ? prm.s1pre + ((size_t)tt * N + n0 + p) * D
+                                        : prm.states + ((size_t)(tt + 1) * N + n0 + p) * D;
         const float *a = prm.actions + ((size_t)tt * N + n0 + p) * U;
         float dl[PMB_MAX_REWARD_ROWS];
         for (int r = 0; r < prm.KR; ++r) {
@@ -215,12 +231,20 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
 cudaError_t launch_rollout_fwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream) {
     const int grid = (prm.N + P - 1) / P;
     cudaError_t e;
+    // moment matching synchronises the whole grid every step: cooperative launch guarantees co-residency
 #define PMB_LAUNCH_FWD(PP)                                                                                   \
     case PP:                                                                                                 \
         e = cudaFuncSetAttribute(rollout_fwd_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                  smem_bytes);                                                                \
         if (e != cudaSuccess) return e;                                                                      \
-        rollout_fwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                       \
+        if (prm.mm_states) {                                                                                 \
+            void *args[] = {(void *)&prm};                                                                   \
+            e = cudaLaunchCooperativeKernel((void *)rollout_fwd_kernel<PP>, dim3(grid), dim3(NT), args,      \
+                                            smem_bytes, stream);                                             \
+            if (e != cudaSuccess) return e;                                                                  \
+        } else {                                                                                             \
+            rollout_fwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                   \
+        }                                                                                                    \
         break;
     switch (P) {
         PMB_LAUNCH_FWD(1)

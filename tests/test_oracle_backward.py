@@ -36,3 +36,19 @@ def test_manual_backward_equals_autograd(name, cots):
     for k, ga in zip(keys, auto[:-1]):
         assert torch.allclose(grads[k], ga, rtol=1e-9, atol=1e-12), k
     assert torch.allclose(dx0, auto[-1], rtol=1e-9, atol=1e-12)
+
+
+def test_mm_adjoint_equals_autograd():
+    """The hand-derived Cholesky/moment-matching adjoint (spec of the CUDA mm reverse step)."""
+    g = torch.Generator().manual_seed(5)
+    for M, D in ((25, 5), (12, 8), (9, 1)):
+        x = torch.randn(M, D, generator=g, dtype=torch.float64).requires_grad_(True)
+        z = torch.randn(M, D, generator=g, dtype=torch.float64)
+        go = torch.randn(M, D, generator=g, dtype=torch.float64)
+        y = orc.mm_resample(x, z)
+        (auto,) = torch.autograd.grad((y * go).sum(), x)
+        with torch.no_grad():
+            y2, m, L, zh = orc.mm_forward_parts(x, z)
+            man = orc.mm_backward(go, x, m, L, zh)
+        assert torch.allclose(y2, y, atol=1e-12)
+        assert torch.allclose(man, auto, rtol=1e-8, atol=1e-10)
