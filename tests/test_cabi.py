@@ -1,0 +1,152 @@
+"""The C-ABI shared library: loads on a GPU-less box, exports every symbol include/pmb_b200.h declares,
+its structs have the layout the ctypes binding assumes, and descriptor validation works without a device.
+No compute calls here (no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pmb_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from prob_mbrl_b200 import build
+    build.build()
+    from prob_mbrl_b200 import _lib
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_functions()
+    assert "pmb_rollout_forward" in names and "pmb_rollout_backward" in names and "pmb_clip_adam_step" in names
+    for n in names:
+        assert hasattr(lib, n), "libpmb_b200.so does not export %s" % n
+    from prob_mbrl_b200 import _lib
+    assert set(_lib.EXPORTS) == set(names)
+    assert lib.pmb_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_struct_layout_matches_the_c_header():
+    from prob_mbrl_b200 import _lib
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "pmb_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\n", sizeof(pmb_net), sizeof(pmb_problem), sizeof(pmb_tuning), sizeof(pmb_adam_tensor));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(pmb_net, W), offsetof(pmb_net, keep), offsetof(pmb_net, z),
+         offsetof(pmb_net, z_step_stride), offsetof(pmb_net, max_log_std));
+  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(pmb_problem, pol), offsetof(pmb_problem, dyn),
+         offsetof(pmb_problem, act_scale), offsetof(pmb_problem, rew_rows), offsetof(pmb_problem, z_mm),
+         offsetof(pmb_problem, n_global));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "layout.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "layout")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = subprocess.check_output([exe]).decode().split("\n")
+    sizes = [int(x) for x in out[0].split()]
+    assert sizes == [C.sizeof(_lib.PmbNet), C.sizeof(_lib.PmbProblem), C.sizeof(_lib.PmbTuning),
+                     C.sizeof(_lib.PmbAdamTensor)]
+    net = [int(x) for x in out[1].split()]
+    assert net == [getattr(_lib.PmbNet, f).offset for f in ("W", "keep", "z", "z_step_stride", "max_log_std")]
+    prob = [int(x) for x in out[2].split()]
+    assert prob == [getattr(_lib.PmbProblem, f).offset for f in ("pol", "dyn", "act_scale", "rew_rows", "z_mm",
+                                                                 "n_global")]
+
+
+def _fake_problem(N=100, H=400, D=5, U=1, hid=(200, 200), mm=False, groups=0):
+    """Descriptor with non-NULL fake pointers: enough for the host-side planner (never dereferenced)."""
+    from prob_mbrl_b200 import _lib
+    p = _lib.PmbProblem()
+    p.N, p.H, p.D, p.U = N, H, D, U
+    for net, nin, nout in ((p.pol, D, 2 * U), (p.dyn, D + U, 2 * D)):
+        dims = [nin] + list(hid) + [nout]
+        net.n_linear = len(dims) - 1
+        for i, d in enumerate(dims):
+            net.dims[i] = d
+        for i in range(net.n_linear):
+            net.W[i] = 0x1000
+            net.b[i] = 0x1000
+        for i in range(len(hid)):
+            net.mask[i] = 0x1000
+            net.keep[i] = 0.9
+        net.has_density, net.z, net.max_log_std = 1, 0x1000, 1.6
+    for f in ("act_scale", "act_bias", "mx", "iSx", "my", "Sy", "rew_C", "rew_c0", "rew_Q", "rew_R"):
+        setattr(p, f, 0x1000)
+    p.rew_rows, p.rew_scale, p.n_global = 2, 1.0, N
+    if mm:
+        p.mm_states = p.mm_rewards = 1
+        p.mm_groups = groups
+        p.z_mm = p.z_rr = 0x1000
+    return p
+
+
+def test_planner_accepts_the_baseline_configs(lib):
+    from prob_mbrl_b200 import _lib
+    tune = _lib.make_tuning()
+    cases = {"c1": dict(N=25, H=40), "c2": dict(N=100, H=400), "c3": dict(N=100, H=400, mm=True),
+             "c4": dict(N=125, H=600, D=8, hid=(400, 400, 400)), "c5": dict(N=250, H=1000, hid=(512, 512))}
+    for name, kw in cases.items():
+        p = _fake_problem(**kw)
+        assert lib.pmb_check_problem(C.byref(p), C.byref(tune)) == 0, (name, lib.pmb_last_error())
+        nbytes = lib.pmb_workspace_bytes(C.byref(p), C.byref(tune))
+        assert nbytes > 0
+        # activations kept for the reverse sweep dominate: H*N*(sum of hidden widths) floats, x3 (pol act, pol delta, dyn act)
+        hid = kw.get("hid", (200, 200))
+        lower = 4 * kw["H"] * kw["N"] * sum(hid) * 3
+        assert lower <= nbytes < 3 * lower + (96 << 20), (name, nbytes, lower)   # + split-K partials of the weight gradient
+    assert lib.pmb_policy_param_count(C.byref(_fake_problem())) == 200 * 5 + 200 + 200 * 200 + 200 + 2 * 200 + 2
+
+
+def test_planner_rejects_what_the_kernels_cannot_run(lib):
+    from prob_mbrl_b200 import _lib
+    from prob_mbrl_b200.operands import NotEligible
+    tune = _lib.make_tuning()
+    too_wide = _fake_problem(hid=(2048, 2048))
+    with pytest.raises(NotEligible):
+        _lib.check_problem(too_wide, tune)                      # PMB_E_UNSUPPORTED -> NotEligible
+    bad = _fake_problem()
+    bad.mx = None
+    with pytest.raises(RuntimeError):
+        _lib.check_problem(bad, tune)                           # PMB_E_INVALID -> RuntimeError
+    ragged_groups = _fake_problem(N=100, mm=True, groups=3)
+    with pytest.raises(RuntimeError):
+        _lib.check_problem(ragged_groups, tune)
+    huge_mm = _fake_problem(N=5000, mm=True)                    # grid barrier needs one co-resident grid
+    with pytest.raises(NotEligible):
+        _lib.check_problem(huge_mm, tune)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """CPU tensors / missing extension never fall back silently (fused is the default backend)."""
+    import prob_mbrl_b200 as pm
+    import golden_util as gu
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    dyn, pol = gu.modules_from_ops(ops)
+    os.environ.pop("PROB_MBRL_BACKEND", None)
+    with pytest.raises(pm.NotEligible):
+        pm.rollout(g["x0"], dyn, pol, 3, resample_state_noise=False, resample_action_noise=False)
+    from prob_mbrl_b200 import _lib
+    saved, _lib._lib = _lib._lib, None
+    real = _lib.LIB_PATH
+    try:
+        _lib.LIB_PATH = real + ".missing"
+        with pytest.raises(_lib.LibraryMissing):
+            _lib.load()
+    finally:
+        _lib.LIB_PATH, _lib._lib = real, saved
