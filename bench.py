@@ -245,11 +245,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: inputs resident in HBM ----------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    t_spin = time.perf_counter()
     for _ in range(args.warmup):
         eng.step(x0_dev)
-    clocks = ClockSampler(local_rank)
+    while time.perf_counter() - t_spin < 1.0:      # let nvidia-smi start streaming; keeps the GPU under load
+        eng.step(x0_dev)
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -369,7 +372,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rollout-steps/s",
                     "h2d_bytes_per_step": int(x0_glob_host.numel() * 4), "d2h_bytes_per_step": 4,
                     "api": "prob_mbrl_b200.mc_pilco(x0_host, dynamics, policy, H, opt, exp, K, pegasus=True)"},
-            "gpu_launches": args.steps * (3 + 2 * nlin + 3),
+            "gpu_launches": args.steps * (3 + nlin + 3),   # pack, fwd, bwd, wgrad/layer, reduce, norm, adam
             "kernels_ms": kern, "roofline": roof, "loss": loss_val,
         }
         if cb is not None:

@@ -4,7 +4,7 @@
 //   * wgrad_tile_kernel: batched policy weight gradient  dW[m][n] = sum_r delta[r][m] * inp[r][n]
 //                        over the r = (step, particle) axis, split-K across the grid -- the only piece of
 //                        the backward pass that is not on the sequential chain;
-//   * wgrad_thin_kernel: same contraction when one side has <= 16 columns (first/last layer, biases);
+//                        bias gradients ride along as an implicit column of ones;
 //   * reduce_partials_kernel: fixed-order sum of the split-K partials (deterministic, no atomics).
 // Replaces the weight-gradient part of loss.backward() (reference algorithms/mc_pilco.py:197).
 #include "pmb_internal.cuh"
@@ -34,16 +34,22 @@ cudaError_t launch_pack(const PackJobs &jobs, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// C[M][Nc] (row-major, ldc) partial over rows [r0, r1):  C = A^T B,  A:[R][lda] (cols m), B:[R][ldb] (cols n)
+// Partial over rows [r0, r1) of  C = A^T [B | 1]:  A:[R][lda] (M columns = layer output adjoints),
+// B:[R][ldb] (Nc columns = layer inputs), plus an implicit column of ones when bias_out != nullptr, so
+// the bias gradient (column sums of A) falls out of the same pass:
+//   w_out[m][n] = sum_r A[r][m] B[r][n]   (n < Nc, row stride Nc),   bias_out[m] = sum_r A[r][m].
+// 64x64 output tile per CTA, 4x4 per thread on the packed FP32 pipe (FFMA2), register-staged double
+// buffering of the 16-row k-slab.
 constexpr int BM = 64, BN = 64, BK = 16;
 
 __global__ void __launch_bounds__(256) wgrad_tile_kernel(const float *__restrict__ A, int lda, int M,
                                                          const float *__restrict__ B, int ldb, int Nc,
-                                                         long long R, int nsplit, float *__restrict__ part,
-                                                         long long part_stride, int ldc) {
+                                                         long long R, int nsplit, float *__restrict__ w_out,
+                                                         float *__restrict__ bias_out, long long part_stride) {
     __shared__ __align__(16) float As[2][BK][BM];
     __shared__ __align__(16) float Bs[2][BK][BN];
-    const int tiles_n = (Nc + BN - 1) / BN;
+    const int ncols = Nc + (bias_out ? 1 : 0);
+    const int tiles_n = (ncols + BN - 1) / BN;
     const int tm = blockIdx.x / tiles_n, tn = blockIdx.x - tm * tiles_n;
     const int m0 = tm * BM, n0 = tn * BN;
     const long long rows_per = (R + nsplit - 1) / nsplit;
@@ -51,22 +57,21 @@ __global__ void __launch_bounds__(256) wgrad_tile_kernel(const float *__restrict
     const long long r1 = min(R, r0 + rows_per);
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, 4x4 outputs each
-    // loader mapping: 4 elements per thread per operand tile
-    const int lc = tid & 63, lr = tid >> 6;      // column 0..63, row 0..3 (+4, +8, +12)
-    float acc[4][4];
+    const int lc = tid & 63, lr = tid >> 6;      // loader: column 0..63, rows lr, lr+4, lr+8, lr+12
+    float2 acc[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+    const bool a_ok = m0 + lc < M;
+    const int bcol = n0 + lc;
+    const int b_kind = bcol < Nc ? 0 : (bcol == Nc && bias_out) ? 1 : 2;   // data, ones, padding
     float ra[4], rb[4];
     auto gload = [&](long long rbase) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            long long r = rbase + lr + 4 * i;
-            bool okr = r < r1;
-            ra[i] = (okr && m0 + lc < M) ? __ldg(A + r * lda + m0 + lc) : 0.f;
-            rb[i] = (okr && n0 + lc < Nc) ? __ldg(B + r * ldb + n0 + lc) : 0.f;
+            const long long r = rbase + lr + 4 * i;
+            const bool okr = r < r1;
+            ra[i] = (okr && a_ok) ? __ldg(A + r * lda + m0 + lc) : 0.f;
+            rb[i] = !okr ? 0.f : b_kind == 0 ? __ldg(B + r * ldb + bcol) : b_kind == 1 ? 1.f : 0.f;
         }
     };
     auto sstore = [&](int buf) {
@@ -87,66 +92,34 @@ __global__ void __launch_bounds__(256) wgrad_tile_kernel(const float *__restrict
         if (more) gload(rb0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][4 * ty]);
-            float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tx]);
+            const float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tx]);
+            const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
             const float av[4] = {a.x, a.y, a.z, a.w};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i) {
+                const float2 a2 = make_float2(av[i], av[i]);
+                acc[i][0] = __ffma2_rn(a2, b01, acc[i][0]);
+                acc[i][1] = __ffma2_rn(a2, b23, acc[i][1]);
+            }
         }
         if (more) sstore(buf ^ 1);
         __syncthreads();
         buf ^= 1;
     }
-    float *out = part + (long long)blockIdx.y * part_stride;
+    float *wo = w_out + (long long)blockIdx.y * part_stride;
+    float *bo = bias_out ? bias_out + (long long)blockIdx.y * part_stride : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int m = m0 + 4 * ty + i;
+        const int m = m0 + 4 * ty + i;
         if (m >= M) continue;
+        const float v[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int n = n0 + 4 * tx + j;
-            if (n < Nc) out[(long long)m * ldc + n] = acc[i][j];
+            const int n = n0 + 4 * tx + j;
+            if (n < Nc) wo[(long long)m * Nc + n] = v[j];
+            else if (n == Nc && bo) bo[m] = v[j];
         }
-    }
-}
-
-// One side thin (T <= 16 columns).  Thread = one column w of the wide operand, T accumulators.
-//   thin_is_cols = 1 : C[w][i] = sum_r Wd[r][w] * Th[r][i]   (dW of the first layer: [h][D])
-//   thin_is_cols = 0 : C[i][w] = sum_r Th[r][i] * Wd[r][w]   (dW of the output layer: [nout][h])
-//   Th == nullptr    : Th[r][0] = 1 (bias gradient = column sums), T = 1
-template <int T>
-__global__ void __launch_bounds__(128) wgrad_thin_kernel(const float *__restrict__ Wd, int ldw, int Wn,
-                                                         const float *__restrict__ Th, int ldt, int Tn,
-                                                         long long R, int nsplit, float *__restrict__ part,
-                                                         long long part_stride, int ldc, int thin_is_cols) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long rows_per = (R + nsplit - 1) / nsplit;
-    const long long r0 = (long long)blockIdx.y * rows_per;
-    const long long r1 = min(R, r0 + rows_per);
-    if (w >= Wn) return;
-    float acc[T];
-#pragma unroll
-    for (int i = 0; i < T; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (long long r = r0; r < r1; ++r) {
-        float a = __ldg(Wd + r * ldw + w);
-        if (Th) {
-#pragma unroll
-            for (int i = 0; i < T; ++i)
-                if (i < Tn) acc[i] = fmaf(a, __ldg(Th + r * ldt + i), acc[i]);
-        } else {
-            acc[0] += a;
-        }
-    }
-    float *out = part + (long long)blockIdx.y * part_stride;
-#pragma unroll
-    for (int i = 0; i < T; ++i) {
-        if (i >= Tn) break;
-        if (thin_is_cols) out[(long long)w * ldc + i] = acc[i];
-        else out[(long long)i * ldc + w] = acc[i];
     }
 }
 
@@ -160,24 +133,12 @@ __global__ void reduce_partials_kernel(const float *__restrict__ part, long long
     }
 }
 
-// dC[M][Nc] partials for one linear layer; A = delta [R][lda] (M cols), B = layer input [R][ldb] (Nc cols)
+// partials of one linear layer: A = output adjoints [R][lda] (M columns), B = layer input [R][ldb] (Nc columns)
 cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb, int Nc, long long R,
-                         int nsplit, float *part, long long part_stride, cudaStream_t stream) {
-    if (M > 16 && Nc > 16) {
-        dim3 grid(((M + BM - 1) / BM) * ((Nc + BN - 1) / BN), nsplit);
-        wgrad_tile_kernel<<<grid, 256, 0, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, part, part_stride, Nc);
-    } else if (Nc <= 16) {
-        // thin side = layer input (first layer, or bias when B == nullptr); wide = delta columns
-        dim3 grid((M + 127) / 128, nsplit);
-        if (B == nullptr)
-            wgrad_thin_kernel<1><<<grid, 128, 0, stream>>>(A, lda, M, nullptr, 0, 1, R, nsplit, part, part_stride, 1, 1);
-        else
-            wgrad_thin_kernel<16><<<grid, 128, 0, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, part, part_stride, Nc, 1);
-    } else {
-        // thin side = delta (output layer): C[i][w] = sum_r delta[r][i] * inp[r][w]
-        dim3 grid((Nc + 127) / 128, nsplit);
-        wgrad_thin_kernel<16><<<grid, 128, 0, stream>>>(B, ldb, Nc, A, lda, M, R, nsplit, part, part_stride, Nc, 0);
-    }
+                         int nsplit, float *w_part, float *bias_part, long long part_stride, cudaStream_t stream) {
+    const int ncols = Nc + (bias_part ? 1 : 0);
+    dim3 grid(((M + BM - 1) / BM) * ((ncols + BN - 1) / BN), nsplit);
+    wgrad_tile_kernel<<<grid, 256, 0, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, w_part, bias_part, part_stride);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,44 @@
+"""2-rank NCCL check (torchrun): particle-sharded fused iteration == single-GPU iteration on the same
+global batch.  Rank 0 prints PASS/FAIL."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["PMB_NO_PBAR"] = "1"
+import torch, torch.distributed as dist
+import golden_util as gu
+import prob_mbrl_b200 as pm
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+ops, g = gu.load("dcartpole_48x3_n24_h30")
+
+def run(distributed):
+    dyn, pol = gu.modules_from_ops(ops, dev)
+    opt = torch.optim.Adam(pol.parameters(), 1e-3)
+    torch.manual_seed(17)
+    losses = []
+    if not distributed:
+        # hide the process group from mc_pilco: run the full batch locally
+        saved = pm.dist.world
+        pm.dist.world = lambda: (0, 1)
+        sys.modules["prob_mbrl_b200.mc_pilco"].dist.world = pm.dist.world
+    try:
+        pm.mc_pilco(g["x0"].to(dev), dyn, pol, 8, opt, None, 4, pegasus=True, maximize=True, clip_grad=1.0,
+                    resampling_period=3, init_state_noise=0.01,
+                    on_iteration=lambda i, loss, *a: losses.append(float(loss)))
+    finally:
+        if not distributed:
+            pm.dist.world = saved
+    return torch.cat([p.detach().flatten() for p in pol.parameters()]), losses
+
+dist.init_process_group("nccl", device_id=dev)
+p_single, l_single = run(False)
+p_shard, l_shard = run(True)
+err = float((p_single - p_shard).abs().max())
+moved = float((p_single - torch.cat([ops[k].flatten() for k in ("pol_W0", "pol_b0", "pol_W1", "pol_b1", "pol_W2", "pol_b2", "pol_W3", "pol_b3")]).to(dev)).abs().max())
+t = torch.tensor([err], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    ok = float(t) < 5e-7 and moved > 1e-4 and max(abs(a - b) for a, b in zip(l_single, l_shard)) < 1e-6
+    print("DIST", "PASS" if ok else "FAIL", "max|dparam| %.2e  moved %.2e" % (float(t), moved), l_single, l_shard)
+dist.destroy_process_group()
