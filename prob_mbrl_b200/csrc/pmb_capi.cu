@@ -26,7 +26,6 @@ static inline int round4(int x) { return (x + 3) & ~3; }
 static inline long long round32(long long x) { return (x + 31) & ~31LL; }
 
 constexpr int SMEM_LIMIT_FLOATS = 232448 / 4;   // 227 KB opt-in dynamic shared memory per CTA
-constexpr int STAGE_FLOATS_MAX = 8192;          // 32 KB per ring stage
 
 struct WGrad {
     long long delta_off;   // workspace floats

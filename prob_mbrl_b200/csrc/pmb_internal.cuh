@@ -16,8 +16,11 @@
 
 namespace pmb {
 
-constexpr int NT = 256;              // threads per CTA of the sweeps
+constexpr int NT = 256;              // COMPUTE threads per CTA of the sweeps (8 warps)
 constexpr int NWARP = NT / 32;
+constexpr int NT_LAUNCH = NT + 32;   // + one producer warp that only issues TMA copies
+// barrier among the compute warps only (the producer warp never joins it)
+#define CTA_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
 constexpr int MAXL = PMB_MAX_LINEAR; // linear layers per net
 constexpr int MAXS = 4;              // ring stages (max)
 constexpr int MAXSCHED = 2 * MAXL;   // streamed layers per step
@@ -129,6 +132,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -172,7 +178,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 
 // ----------------------------------------------------------------------------------------
 // The weight stream: a ring of `nstages` smem stages consumed in a fixed cyclic schedule.
-// All threads call acquire() in lockstep; thread 0 issues the copies `nstages-1` chunks ahead.
+// The 8 compute warps consume it in lockstep; a dedicated producer warp re-fills released stages.
 // ----------------------------------------------------------------------------------------
 struct ChunkDesc {
     const float *src;
@@ -181,91 +187,78 @@ struct ChunkDesc {
 };
 constexpr int MAXCHUNKS = 64;   // chunks per step (planner guarantees chunks_per_step <= MAXCHUNKS)
 
+// Barriers of the weight ring (static shared memory of the kernels).
+struct RingBars {
+    uint64_t full[MAXS];    // producer -> consumers: chunk landed (TMA complete_tx)
+    uint64_t empty[MAXS];   // consumers -> producer: all 8 compute warps are done with the stage
+};
+
+// Consumer view of the weight ring (compute warps, in lockstep).
 struct Stream {
     const SweepParams *prm;
     float *stage_base;
-    uint64_t *full;         // [nstages] mbarriers (mode 2)
-    ChunkDesc *tab;         // [chunks_per_step] in shared memory, the cyclic schedule of one step
-    int c_stage;            // consumer cursor (uniform)
+    RingBars *bars;
+    int c_stage;
     uint32_t c_parity;
-    int c_idx;              // consumer position inside the step's schedule (mode 1)
-    // producer cursor (thread 0 only)
-    int p_stage, p_idx;
-    unsigned p_left;
-    long long *dbgp;        // profiling aid: when non-null, acquire() appends clock64() marks
 
-    __device__ __forceinline__ void init(const SweepParams *p, float *smem, uint64_t *bars, ChunkDesc *table) {
+    __device__ __forceinline__ void init(const SweepParams *p, float *smem, RingBars *b) {
         prm = p;
         stage_base = smem + p->off_stage;
-        full = bars;
-        tab = table;
+        bars = b;
         c_stage = 0;
         c_parity = 0;
-        c_idx = 0;
-        dbgp = nullptr;
-        p_stage = p_idx = 0;
-        p_left = (unsigned)p->H * (unsigned)p->chunks_per_step;
-        if (threadIdx.x == 0) {
-            int k = 0;
-            for (int i = 0; i < p->nsched; ++i) {
-                const StreamItem &it = p->sched[i];
-                for (int c = 0; c < it.nchunks; ++c, ++k) {
-                    const int row0 = c * it.kc;
-                    const int rows = min(it.kc, it.K - row0);
-                    tab[k].src = p->wpack + it.goff + (long long)row0 * it.Npad;
-                    tab[k].bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
-                }
-            }
-            if (p->stream_mode == 2) {
-                for (int s = 0; s < p->nstages; ++s) mbar_init(&full[s], 1);
-                fence_mbar_init();
-                fence_proxy_async();
-            }
-        }
-        __syncthreads();
-        if (p->stream_mode == 2 && threadIdx.x == 0) {
-            for (int s = 0; s + 1 < p->nstages; ++s) issue_next();
-        }
     }
-
-    // thread 0: issue the next chunk of the cyclic schedule into its stage
-    __device__ __forceinline__ void issue_next() {
-        if (p_left == 0) return;
-        const ChunkDesc d = tab[p_idx];
-        mbar_expect_tx(&full[p_stage], d.bytes);
-        tma_bulk_g2s(stage_base + (size_t)p_stage * prm->stage_floats, d.src, d.bytes, &full[p_stage]);
-        --p_left;
-        if (++p_stage == prm->nstages) p_stage = 0;
-        if (++p_idx == prm->chunks_per_step) p_idx = 0;
-    }
-
-    // Make the next chunk of the schedule readable; returns its stage pointer.  Contains one
-    // __syncthreads() before any stage is overwritten, so callers may rely on it as the barrier that
-    // publishes the previous layer's shared-memory writes.
+    // wait for the next chunk of the schedule; returns its stage pointer
     __device__ __forceinline__ const float *acquire() {
-        if (dbgp) *dbgp++ = clock64();
-        __syncthreads();   // everyone is done with the previous chunk -> its stage may be refilled
-        if (dbgp) *dbgp++ = clock64();
-        const float *st = stage_base + (size_t)c_stage * prm->stage_floats;
-        if (prm->stream_mode == 2) {
-            if (threadIdx.x == 0) issue_next();
-            if (dbgp) *dbgp++ = clock64();
-            mbar_wait(&full[c_stage], c_parity);
-            if (dbgp) *dbgp++ = clock64();
-        } else {
-            const ChunkDesc d = tab[c_idx];
-            const int n4 = d.bytes / 16;
-            const float4 *src = reinterpret_cast<const float4 *>(d.src);
-            float4 *dst = reinterpret_cast<float4 *>(const_cast<float *>(st));
-            for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldg(src + i);
-            __syncthreads();
-            if (++c_idx == prm->chunks_per_step) c_idx = 0;
-        }
+        mbar_wait(&bars->full[c_stage], c_parity);
+        return stage_base + (size_t)c_stage * prm->stage_floats;
+    }
+    // every lane of the warp is done reading the current stage: hand it back to the producer
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->empty[c_stage]);
         if (++c_stage == prm->nstages) {
             c_stage = 0;
             c_parity ^= 1u;
         }
-        return st;
+    }
+};
+
+// Producer side: one elected thread of the extra warp walks the cyclic chunk schedule of all H steps,
+// re-filling a stage as soon as the 8 compute warps released it.
+__device__ __forceinline__ void ring_fill_table(const SweepParams &p, ChunkDesc *tab) {
+    int k = 0;
+    for (int i = 0; i < p.nsched; ++i) {
+        const StreamItem &it = p.sched[i];
+        for (int c = 0; c < it.nchunks; ++c, ++k) {
+            const int row0 = c * it.kc;
+            const int rows = min(it.kc, it.K - row0);
+            tab[k].src = p.wpack + it.goff + (long long)row0 * it.Npad;
+            tab[k].bytes = (uint32_t)rows * (uint32_t)it.Npad * 4u;
+        }
+    }
+}
+
+struct RingProducer {
+    int stage, idx;
+    uint32_t parity;      // parity of the NEXT wait on empty[stage]
+    unsigned issued;
+    __device__ __forceinline__ void init() { stage = idx = 0; parity = 0; issued = 0; }
+    // issue `n` chunks (blocking on stage availability)
+    __device__ __forceinline__ void issue(const SweepParams &p, float *stage_base, RingBars *bars,
+                                          const ChunkDesc *tab, int n) {
+        for (int i = 0; i < n; ++i) {
+            if (issued >= (unsigned)p.nstages) mbar_wait(&bars->empty[stage], parity);
+            const ChunkDesc d = tab[idx];
+            mbar_expect_tx(&bars->full[stage], d.bytes);
+            tma_bulk_g2s(stage_base + (size_t)stage * p.stage_floats, d.src, d.bytes, &bars->full[stage]);
+            ++issued;
+            if (++idx == p.chunks_per_step) idx = 0;
+            if (++stage == p.nstages) {
+                stage = 0;
+                if (issued > (unsigned)p.nstages) parity ^= 1u;
+            }
+        }
     }
 };
 
@@ -332,7 +325,7 @@ __device__ __forceinline__ void wide_accum(float2 (&acc)[P][2], const float *__r
 
 // Accumulate a whole wide layer (resident or streamed), combine the k-split partials and hand every
 // finished (particle p, 4 columns) tuple to `epi(p, float4 sums)`.  The k-split groups share the
-// epilogue work: group g finishes particles p = g, g+ks, ...  Starts with a __syncthreads(); contains a
+// epilogue work: group g finishes particles p = g, g+ks, ...  Starts with a CTA_SYNC(); contains a
 // second one when ks > 1.  `act` is the [K][P] input tile.
 template <int P, typename Epi>
 __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item, const float *res,
@@ -345,6 +338,7 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[p][0] = acc[p][1] = make_float2(0.f, 0.f);
     if (L.streamed) {
+        CTA_SYNC();        // publish the input tile written by the previous phase
 #pragma unroll 1
         for (int c = 0; c < L.nchunks; ++c) {
             const float *w = S.acquire();
@@ -352,10 +346,11 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
             const int row0 = c * L.kc;
             const int rows = min(L.kc, L.K - row0);
             if (m.active) wide_accum<P>(acc, w, rows, L.Npad, act + (size_t)row0 * P, m);
+            S.release();
             PMB_WMARK();
         }
     } else {
-        __syncthreads();
+        CTA_SYNC();
         PMB_WMARK();
         if (m.active) wide_accum<P>(acc, res + L.soff, L.K, L.Npad, act, m);
         PMB_WMARK();
@@ -375,7 +370,7 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
                 make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
     }
     PMB_WMARK();
-    __syncthreads();
+    CTA_SYNC();
     PMB_WMARK();
     if (m.active) {
 #pragma unroll 1
@@ -394,10 +389,10 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
 
 // thin-K wide layer (first layers, K = D / D+U; output-layer adjoints, K = 2D / 2U): one thread per
 // output column, all P particles, no k-split and no reduction.  epi(j, acc[P]) finishes column j.
-// Starts with a __syncthreads().
+// Starts with a CTA_SYNC().
 template <int P, typename Epi>
 __device__ __forceinline__ void thin_layer(const Lin &L, const float *res, const float *act, Epi epi) {
-    __syncthreads();
+    CTA_SYNC();
     const float *w = res + L.soff;
     const int K = L.K, npad = L.Npad;
 #pragma unroll 1
@@ -448,12 +443,12 @@ struct NarrowMap {
     }
 };
 
-// Starts with a __syncthreads() and contains a second one; results are visible after the caller's next
+// Starts with a CTA_SYNC() and contains a second one; results are visible after the caller's next
 // barrier.
 template <int P>
 __device__ __forceinline__ void narrow_layer(const Lin &L, const NarrowMap &nm, const float *res, const float *act,
                                              float *out, const float *bias, float *red) {
-    __syncthreads();
+    CTA_SYNC();
     if (nm.active) {
         const float *wj = res + L.soff + nm.woff;
         const float *ap = act + nm.aoff;
@@ -468,7 +463,7 @@ __device__ __forceinline__ void narrow_layer(const Lin &L, const NarrowMap &nm, 
         for (; k < nm.k1; ++k) s = fmaf(ap[k * P], wj[k], s);
         red[((threadIdx.x >> nm.ol2) << nm.ol2) + nm.o] = (s + s1) + (s2 + s3);
     }
-    __syncthreads();
+    CTA_SYNC();
     if (nm.final) {
         float v = red[nm.o];
         for (int rr = 1; rr < nm.R; ++rr) v += red[(rr << nm.ol2) + nm.o];
@@ -502,7 +497,7 @@ __device__ __forceinline__ void load_resident(const SweepParams &prm, float *sme
 __device__ __forceinline__ void load_constants(const SweepParams &prm, float *cst) {
     const int D = prm.D, U = prm.U, KR = prm.KR;
     for (int i = threadIdx.x; i < C_TOTAL; i += NT) cst[i] = 0.f;
-    __syncthreads();
+    CTA_SYNC();
     for (int i = threadIdx.x; i < D + U; i += NT) {
         cst[C_MX + i] = prm.mx[i];
         cst[C_ISX + i] = prm.iSx[i];

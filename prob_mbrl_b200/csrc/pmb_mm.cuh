@@ -43,7 +43,7 @@ constexpr int mm_smem_floats(int P) { return 2 * P * SD + 8 * SD + 3 * SD + 4 * 
 
 // All CTAs of the (cooperatively launched) grid meet here.  `epoch` counts arrivals expected so far.
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &epoch) {
-    __syncthreads();
+    CTA_SYNC();
     epoch += gridDim.x;
     if (threadIdx.x == 0) {
         __threadfence();
@@ -55,7 +55,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &epoch) {
         } while (v < epoch);
         __threadfence();
     }
-    __syncthreads();
+    CTA_SYNC();
 }
 
 struct MMGroup {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         M.zs[b_p * SD + b_d] = zrow;
         if (n0 + b_p < N) prm.s1pre[((size_t)t * N + b_n) * D + b_d] = s_reg;
     }
-    __syncthreads();
+    CTA_SYNC();
     if (tid < D) {
         double a = 0.0, b = 0.0;
         for (int p = 0; p < grp.Pv; ++p) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         lm[tid] = a / grp.Pv;
         lzm[tid] = b / grp.Pv;
     }
-    __syncthreads();
+    CTA_SYNC();
     double *rec = prm.mmrec + ((size_t)(t & 1) * gridDim.x + blockIdx.x) * MMREC;
     for (int idx = tid; idx < D * D; idx += NT) {
         const int i = idx / D, j = idx - i * D;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         gm[tid] = a / n;
         gzm[tid] = b / n;
     }
-    __syncthreads();
+    CTA_SYNC();
     for (int idx = tid; idx < D * D; idx += NT) {
         const int i = idx / D, j = idx - i * D;
         if (j <= i) {
@@ -160,7 +160,7 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         M.st[SD + tid] = (float)gzm[tid];
         M.st[2 * SD + tid] = 1.f / sqrtf((float)(a / (double)(grp.Ng - 1)));   // 1 / z.std(unbiased)
     }
-    __syncthreads();
+    CTA_SYNC();
     if (tid == 0) {
         bool ok = true;
         for (int i = 0; i < D; ++i) {
@@ -178,7 +178,7 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         }
         if (!ok && prm.status) atomicCAS(prm.status, 0, 1 + t);
     }
-    __syncthreads();
+    CTA_SYNC();
     // keep (m, L, z statistics) of this step for the reverse sweep
     if (blockIdx.x == grp.c0) {
         float *ms = prm.mmstat + ((size_t)t * max(prm.mm_G, 1) + grp.gid) * (3 * SD + SD * SD);
@@ -203,7 +203,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
     const float *ms = prm.mmstat + ((size_t)t * max(prm.mm_G, 1) + grp.gid) * (3 * SD + SD * SD);
     for (int i = tid; i < 3 * SD; i += NT) M.st[i] = __ldcg(ms + i);
     for (int i = tid; i < SD * SD; i += NT) M.L[i] = __ldcg(ms + 3 * SD + i);
-    __syncthreads();
+    CTA_SYNC();
     // block partials: dm = sum_n g_n,  dL = tril(sum_n g_n zhat_n^T)
     double *rec = prm.mmrec + ((size_t)(t & 1) * gridDim.x + blockIdx.x) * MMREC;
     for (int idx = tid; idx < D * D + D; idx += NT) {
@@ -227,7 +227,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
         if (idx < D * D) M.X[(idx / D) * SD + (idx % D)] = (float)a;     // dL (lower triangle), staged in X
         else M.dm[idx - D * D] = (float)a;
     }
-    __syncthreads();
+    CTA_SYNC();
     // A = Phi(L^T dL): lower triangle, diagonal halved
     for (int idx = tid; idx < D * D; idx += NT) {
         const int i = idx / D, j = idx - i * D;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
         }
         M.A[i * SD + j] = a;
     }
-    __syncthreads();
+    CTA_SYNC();
     // X = L^-T A  (back substitution, one column per thread)
     if (tid < D) {
         const int j = tid;
@@ -248,7 +248,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
             M.X[r * SD + j] = s / M.L[r * SD + r];
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     // Sb = X L^-1  (one row per thread)
     if (tid < D) {
         const int i = tid;
@@ -258,7 +258,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
             M.Sb[i * SD + c] = s / M.L[c * SD + c];
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     // dx_n = dm/M + 2/(M-1) * sym(Sb) (x_n - m)
     if (roleB) {
         float acc = 0.f;
@@ -266,7 +266,7 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
             acc = fmaf(0.5f * (M.Sb[b_d * SD + j] + M.Sb[j * SD + b_d]), M.xs[b_p * SD + j] - M.st[j], acc);
         gs[b_p * SD + b_d] = M.dm[b_d] / (float)grp.Ng + (2.f / (float)(grp.Ng - 1)) * acc;
     }
-    __syncthreads();
+    CTA_SYNC();
 }
 
 }  // namespace pmb

@@ -91,16 +91,63 @@ __device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSw
 }
 
 template <int P>
-__global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constant__ SweepParams prm) {
+__global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_constant__ SweepParams prm) {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t bars[MAXS];
-    __shared__ __align__(8) uint64_t sbar[2];
+    __shared__ __align__(8) RingBars ring;
+    __shared__ __align__(8) uint64_t sav_full[2], sav_empty[2];
     __shared__ __align__(16) ChunkDesc chunk_tab[MAXCHUNKS];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, KR = prm.KR;
     const NetSweep &pol = prm.pol;
     const NetSweep &dyn = prm.dyn;
+    const bool has_sav = (pol.nlin > 1) || (dyn.nlin > 1);
+    // ---- barriers, then the producer warp peels off: it feeds the weight ring and, one step ahead, the
+    //      stored hidden activations of each step (TMA bulk copies, one per hidden layer) ----
+    if (tid == 0) {
+        for (int s = 0; s < prm.nstages; ++s) {
+            mbar_init(&ring.full[s], 1);
+            mbar_init(&ring.empty[s], NWARP);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sav_full[b], 1);
+            mbar_init(&sav_empty[b], NWARP);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();                       // the only barrier all 288 threads take
+    if (tid >= NT) {
+        if (tid == NT) {
+            float *savb_p = smem + prm.off_sav;
+            ring_fill_table(prm, chunk_tab);
+            RingProducer rp;
+            rp.init();
+            uint32_t sav_bytes = 0;
+            for (int n = 0; n < 2; ++n) {
+                const NetSweep &net = n ? pol : dyn;
+                for (int h = 0; h + 1 < net.nlin; ++h) sav_bytes += (uint32_t)(P * net.lin[h + 1].Npad) * 4u;
+            }
+            for (int s = 0; s < H; ++s) {
+                const int tt = H - 1 - s, b = s & 1;
+                if (has_sav) {
+                    if (s >= 2) mbar_wait(&sav_empty[b], ((s >> 1) - 1) & 1);
+                    mbar_expect_tx(&sav_full[b], sav_bytes);
+                    for (int n = 0; n < 2; ++n) {
+                        const NetSweep &net = n ? pol : dyn;
+                        for (int h = 0; h + 1 < net.nlin; ++h) {
+                            const int npad = net.lin[h + 1].Npad;
+                            tma_bulk_g2s(savb_p + (size_t)b * prm.sav_floats + net.sav_soff[h],
+                                         prm.ws + net.saved_off[h] + ((size_t)tt * N + n0) * npad,
+                                         (uint32_t)(P * npad) * 4u, &sav_full[b]);
+                        }
+                    }
+                }
+                if (prm.chunks_per_step > 0) rp.issue(prm, smem + prm.off_stage, &ring, chunk_tab, prm.chunks_per_step);
+            }
+        }
+        return;
+    }
     float *cst = smem + prm.off_cst;
     float *act0 = smem + prm.off_act0;
     float *act1 = smem + prm.off_act1;
@@ -127,20 +174,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     const int r_n = min(n0 + r_p, N - 1);
 
     for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
-    __syncthreads();
+    CTA_SYNC();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
-    if (tid == 0 && prm.stream_mode == 2) {
-        mbar_init(&sbar[0], 1);
-        mbar_init(&sbar[1], 1);
-    }
     NarrowMap nm_pol, nm_dyn;
     nm_pol.set<P>(pol.lin[0]);
     nm_dyn.set<P>(dyn.lin[0]);
     Stream S;
-    S.init(&prm, smem, bars, chunk_tab);    // fences the mbarrier inits and synchronises the CTA (mode 2)
-    __syncthreads();
+    S.init(&prm, smem, &ring);
+    CTA_SYNC();
 
     // prefetch registers of the one-step-ahead precompute
     float pf_s1 = 0.f, pf_ls = 0.f, pf_zd = 0.f, pf_gs = 0.f;                 // role B
@@ -225,37 +268,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
             pre[PRE_RA * BL + a_p * SD + a_u] = pf_ga + stg_w[a_p] * s;
         }
     };
-    // stored hidden activations of step tt -> sav buffer `b` (TMA bulk copies, one per hidden layer)
-    auto issue_saved = [&](int tt, int b) {
-        uint32_t total = 0;
-        for (int n = 0; n < 2; ++n) {
-            const NetSweep &net = n ? pol : dyn;
-            for (int h = 0; h + 1 < net.nlin; ++h) total += (uint32_t)(P * net.lin[h + 1].Npad) * 4u;
-        }
-        if (total == 0) return;
-        mbar_expect_tx(&sbar[b], total);
-        for (int n = 0; n < 2; ++n) {
-            const NetSweep &net = n ? pol : dyn;
-            for (int h = 0; h + 1 < net.nlin; ++h) {
-                const int npad = net.lin[h + 1].Npad;
-                tma_bulk_g2s(savb + (size_t)b * prm.sav_floats + net.sav_soff[h],
-                             prm.ws + net.saved_off[h] + ((size_t)tt * N + n0) * npad, (uint32_t)(P * npad) * 4u,
-                             &sbar[b]);
-            }
-        }
-    };
-    auto copy_saved = [&](int tt, int b) {   // stream_mode 1: plain cooperative copy
-        for (int n = 0; n < 2; ++n) {
-            const NetSweep &net = n ? pol : dyn;
-            for (int h = 0; h + 1 < net.nlin; ++h) {
-                const int npad = net.lin[h + 1].Npad;
-                const float4 *src = reinterpret_cast<const float4 *>(prm.ws + net.saved_off[h] + ((size_t)tt * N + n0) * npad);
-                float4 *dst = reinterpret_cast<float4 *>(savb + (size_t)b * prm.sav_floats + net.sav_soff[h]);
-                for (int i = tid; i < P * npad / 4; i += NT) dst[i] = __ldg(src + i);
-            }
-        }
-    };
-    const bool has_sav = (pol.nlin > 1) || (dyn.nlin > 1);
     MMSmem mmS;
     MMGroup grp;
     unsigned epoch = 0;
@@ -268,16 +280,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
     // ---- prologue: everything step H-1 needs ----
     int cur = 0;
     uint32_t spar[2] = {0u, 0u};
-    if (prm.stream_mode == 2) {
-        if (tid == 0) issue_saved(H - 1, cur);
-    } else {
-        copy_saved(H - 1, cur);
-    }
     prefetch(H - 1);
     precompute_a(pre0 + cur * PRE_N * BL);
-    __syncthreads();
+    CTA_SYNC();
     precompute_b(pre0 + cur * PRE_N * BL);
-    __syncthreads();
+    CTA_SYNC();
 
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
@@ -289,14 +296,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
         int sched_i = 0;
         float *in = act0, *out = act1;
         // ---- one step ahead: stored activations + scalars of step t-1 ----
-        if (t > 0) {
-            if (prm.stream_mode == 2) {
-                if (tid == 0) issue_saved(t - 1, nxt);
-            } else {
-                copy_saved(t - 1, nxt);
-            }
-            prefetch(t - 1);
-        }
+        if (t > 0) prefetch(t - 1);
         // ---- moment matching adjoint: cotangent of x' = m + zhat chol(S)^T  ->  cotangent of x ----
         if (prm.mm_states) {
             if (roleB) mmS.zs[b_p * SD + b_d] = __ldg(prm.z_mm + (size_t)((t + n0 + b_p) % N) * D + b_d);
@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
             in[b_d * P + b_p] = g * cst[C_SY + b_d];
             if (dyn.has_density) in[(D + b_d) * P + b_p] = g * pre[PRE_FD * BL + b_p * SD + b_d];
         }
-        if (prm.stream_mode == 2 && has_sav) {
-            mbar_wait(&sbar[cur], spar[cur]);
+        if (has_sav) {
+            mbar_wait(&sav_full[cur], spar[cur]);
             spar[cur] ^= 1u;
         }
         const float *sav = savb + (size_t)cur * prm.sav_floats;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
             net_backward<P>(prm, net, which == 1, sched_i, in, out, obuf, smem, red, sav, S, which ? nm_pol : nm_dyn, t,
                             n0);
             PMB_MARK(34 + 3 * which);
-            __syncthreads();
+            CTA_SYNC();
             PMB_MARK(35 + 3 * which);
             if (which == 0) {
                 // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
@@ -358,7 +358,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_bwd_kernel(const __grid_constan
             }
             PMB_MARK(36 + 3 * which);
         }
-        __syncthreads();
+        if (has_sav) {      // this step's stored activations are consumed: the buffer may be refilled
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sav_empty[cur]);
+        }
+        CTA_SYNC();
         PMB_MARK(40);
         cur = nxt;
     }
@@ -375,11 +379,11 @@ cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cu
         if (e != cudaSuccess) return e;                                                                      \
         if (prm.mm_states) {                                                                                 \
             void *args[] = {(void *)&prm};                                                                   \
-            e = cudaLaunchCooperativeKernel((void *)rollout_bwd_kernel<PP>, dim3(grid), dim3(NT), args,      \
+            e = cudaLaunchCooperativeKernel((void *)rollout_bwd_kernel<PP>, dim3(grid), dim3(NT_LAUNCH), args,      \
                                             smem_bytes, stream);                                             \
             if (e != cudaSuccess) return e;                                                                  \
         } else {                                                                                             \
-            rollout_bwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                   \
+            rollout_bwd_kernel<PP><<<grid, NT_LAUNCH, smem_bytes, stream>>>(prm);                                   \
         }                                                                                                    \
         break;
     switch (P) {

@@ -83,13 +83,32 @@ __device__ __forceinline__ void net_forward(const SweepParams &prm, const NetSwe
 }
 
 template <int P>
-__global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constant__ SweepParams prm) {
+__global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_constant__ SweepParams prm) {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t bars[MAXS];
+    __shared__ __align__(8) RingBars ring;
     __shared__ __align__(16) ChunkDesc chunk_tab[MAXCHUNKS];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
+    // ---- barriers, then the producer warp peels off: it only feeds the weight ring ----
+    if (tid == 0) {
+        for (int s = 0; s < prm.nstages; ++s) {
+            mbar_init(&ring.full[s], 1);
+            mbar_init(&ring.empty[s], NWARP);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();                       // the only barrier all 288 threads take
+    if (tid >= NT) {
+        if (tid == NT && prm.chunks_per_step > 0) {
+            ring_fill_table(prm, chunk_tab);
+            RingProducer rp;
+            rp.init();
+            rp.issue(prm, smem + prm.off_stage, &ring, chunk_tab, H * prm.chunks_per_step);
+        }
+        return;
+    }
     float *cst = smem + prm.off_cst;
     float *act0 = smem + prm.off_act0;
     float *act1 = smem + prm.off_act1;
@@ -108,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     const int od_p = tid / prm.dyn.nout, od_j = tid - od_p * prm.dyn.nout;
 
     for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
-    __syncthreads();
+    CTA_SYNC();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
     float s_reg = 0.f;            // role B: this thread's element of the current state (never leaves registers)
@@ -124,7 +143,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     nm_pol.set<P>(prm.pol.lin[prm.pol.nlin - 1]);
     nm_dyn.set<P>(prm.dyn.lin[prm.dyn.nlin - 1]);
     Stream S;
-    S.init(&prm, smem, bars, chunk_tab);
+    S.init(&prm, smem, &ring);
     MMSmem mmS;
     MMGroup grp;
     unsigned epoch = 0;
@@ -132,13 +151,12 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
         mmS.carve<P>(smem + prm.off_mm);
         grp.set<P>(prm, n0);
     }
-    __syncthreads();
+    CTA_SYNC();
 
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const bool dbg_on = prm.dbg != nullptr && blockIdx.x == 0 && tid == 0 && t == H / 2;
         PMB_MARK(0);
-        S.dbgp = dbg_on ? prm.dbg + 256 : nullptr;
         int sched_i = 0;
         float *in = act0, *out = act1;
         // per-step noise (only when the caller pre-drew [H, N, .] tables): issue the loads early
@@ -153,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
             const NetSweep &net = which ? prm.dyn : prm.pol;
             net_forward<P>(prm, net, sched_i, in, out, obuf, smem, red, S, which ? nm_dyn : nm_pol, t, n0, dbg_on,
                            1 + 8 * which);
-            __syncthreads();
+            CTA_SYNC();
             PMB_MARK(7 + 8 * which);
             if (which == 0) {
                 // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
@@ -199,7 +217,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fwd_kernel(const __grid_constan
     // ---- rewards r_t = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset on (s_{t+1}, a_t) for every step
     //      (envs/cartpole/env.py:62-86).  Nothing in the recurrence consumes them, so they are
     //      evaluated here, off the serial chain, from the trajectory this CTA just wrote. ----
-    __syncthreads();
+    CTA_SYNC();
     for (int i = tid; i < H * P; i += NT) {
         const int tt = i / P, p = i - tt * P;
         if (n0 + p >= N) continue;
@@ -239,11 +257,11 @@ cudaError_t launch_rollout_fwd(const SweepParams &prm, int P, int smem_bytes, cu
         if (e != cudaSuccess) return e;                                                                      \
         if (prm.mm_states) {                                                                                 \
             void *args[] = {(void *)&prm};                                                                   \
-            e = cudaLaunchCooperativeKernel((void *)rollout_fwd_kernel<PP>, dim3(grid), dim3(NT), args,      \
+            e = cudaLaunchCooperativeKernel((void *)rollout_fwd_kernel<PP>, dim3(grid), dim3(NT_LAUNCH), args,      \
                                             smem_bytes, stream);                                             \
             if (e != cudaSuccess) return e;                                                                  \
         } else {                                                                                             \
-            rollout_fwd_kernel<PP><<<grid, NT, smem_bytes, stream>>>(prm);                                   \
+            rollout_fwd_kernel<PP><<<grid, NT_LAUNCH, smem_bytes, stream>>>(prm);                                   \
         }                                                                                                    \
         break;
     switch (P) {

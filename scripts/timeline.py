@@ -36,9 +36,3 @@ for nm, base in (("pol L1", 2), ("dyn L1", 10)):
     v = [x for x in v if x]
     print("  %-7s" % nm, [v[i + 1] - v[i] for i in range(len(v) - 1)])
 
-v = d[256:256+16]
-print("acquire internals (fwd, 4 chunks): [sync, issue, mbar wait] each:")
-for c in range(4):
-    q = v[4*c:4*c+4]
-    print("   chunk", c, [q[i+1]-q[i] for i in range(3)])
-

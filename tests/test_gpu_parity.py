@@ -107,14 +107,16 @@ def test_generic_cotangents_match_oracle_autograd(name):
     assert gu.rel_l2(r["dx0"], auto[-1]) < 2e-5
 
 
-def test_stream_modes_are_bitwise_identical():
-    """TMA bulk-copy ring (mode 2) and synchronous copies (mode 1) feed the same arithmetic."""
+def test_ring_depths_agree():
+    """The TMA weight ring with 2 or 4 stages (different k-chunk sizes, hence a different grouping of the
+    k-split partial sums) gives the same trajectory and gradient to fp32 rounding."""
     ops, g = gu.load("cartpole_200x2_n25_h40")
-    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_STREAM_MODE": 1})
-    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_STREAM_MODE": 2})
-    assert torch.equal(a["S"], b["S"]) and torch.equal(a["R"], b["R"])
-    for x, y in zip(a["grads"], b["grads"]):
-        assert torch.equal(x, y)
+    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 2})
+    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 4})
+    assert (a["S"] - b["S"]).abs().max() < 1e-6 and (a["R"] - b["R"]).abs().max() < 1e-6
+    assert gu.rel_l2(a["grads"], b["grads"]) < 2e-6
+    for r in (a, b):
+        assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
 
 
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
