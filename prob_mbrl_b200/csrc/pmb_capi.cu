@@ -192,7 +192,7 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
     S.off_act0 = off; off += ((tile_rows * P) + 31) & ~31;
     S.off_act1 = off; off += ((tile_rows * P) + 31) & ~31;
     S.off_red = off;  off += 1024 * P;
-    S.off_misc = off; off += 320 * P;
+    S.off_misc = off; off += 640 * P;   // per-particle scratch + partials of the fused projections
     S.off_mm = off;
     if (mm_states) off += (mm_smem_floats(P) + 31) & ~31;
     // backward: two buffers for the stored hidden activations of a step

@@ -324,7 +324,8 @@ __device__ __forceinline__ void wide_accum(float2 (&acc)[P][2], const float *__r
 }
 
 // Accumulate a whole wide layer (resident or streamed), combine the k-split partials and hand every
-// finished (particle p, 4 columns) tuple to `epi(p, float4 sums)`.  The k-split groups share the
+// finished (particle p, 4 columns) tuple to `epi(p, float4 sums, active)` (called by every lane of the
+// epilogue warps; `active` = the lane owns real columns).  The k-split groups share the
 // epilogue work: group g finishes particles p = g, g+ks, ...  Starts with a CTA_SYNC(); contains a
 // second one when ks > 1.  `act` is the [K][P] input tile.
 template <int P, typename Epi>
@@ -356,10 +357,9 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
         PMB_WMARK();
     }
     if (m.ks == 1) {
-        if (m.active) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) epi(p, make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y));
-        }
+        for (int p = 0; p < P; ++p)
+            epi(p, make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y), m.active != 0);
         return;
     }
     const int npad = L.Npad;
@@ -372,16 +372,18 @@ __device__ __forceinline__ void wide_layer(const Lin &L, const StreamItem *item,
     PMB_WMARK();
     CTA_SYNC();
     PMB_WMARK();
-    if (m.active) {
+    // whole warps walk this loop (g is warp-uniform), so the epilogue may use warp collectives
 #pragma unroll 1
-        for (int p = m.g; p < P; p += m.ks) {
-            float4 s = *reinterpret_cast<const float4 *>(red + ((size_t)p * npad) + 4 * m.cq);
+    for (int p = m.g; p < P; p += m.ks) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m.active) {
+            s = *reinterpret_cast<const float4 *>(red + ((size_t)p * npad) + 4 * m.cq);
             for (int gg = 1; gg < m.ks; ++gg) {
                 const float4 v = *reinterpret_cast<const float4 *>(red + ((size_t)(gg * P + p) * npad) + 4 * m.cq);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
-            epi(p, s);
         }
+        epi(p, s, m.active != 0);
     }
     PMB_WMARK();
 #undef PMB_WMARK
@@ -469,6 +471,42 @@ __device__ __forceinline__ void narrow_layer(const Lin &L, const NarrowMap &nm, 
         for (int rr = 1; rr < nm.R; ++rr) v += red[(rr << nm.ol2) + nm.o];
         out[nm.o] = v + (bias ? bias[nm.j] : 0.f);
     }
+}
+
+// Output projection fused into the epilogue of the last hidden layer: every lane holds 4 finished hidden
+// values v of particle p (zeros on idle lanes); the warp forms its share of out[p][j] = sum_k h[k] w[j][k]
+// for all j with 4 dot products in flight and a butterfly reduction, lane 0 publishes one partial per
+// (p, j, warp-of-the-group).  The consumers add the partials of the group's warps (read_out).
+__device__ __forceinline__ void narrow_fused(const float4 v, bool active, int p, int col, const float *wn, int K,
+                                             int nout, float *part, int wpg, int wig) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int j0 = 0; j0 < nout; j0 += 4) {
+        float s[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = min(j0 + q, nout - 1);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) w = *reinterpret_cast<const float4 *>(wn + (size_t)j * K + col);
+            s[q] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, v.w * w.w)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        }
+        if (lane < 4 && j0 + lane < nout) {
+            const float r = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
+            part[(p * nout + j0 + lane) * wpg + wig] = r;
+        }
+    }
+}
+// out[p][j] from the published partials (wpg = 1, bias = nullptr: plain buffer written by narrow_layer)
+__device__ __forceinline__ float read_out(const float *part, const float *bias, int p, int j, int nout, int wpg) {
+    const float *q = part + (p * nout + j) * wpg;
+    float v = bias ? bias[j] : 0.f;
+    for (int w = 0; w < wpg; ++w) v += q[w];
+    return v;
 }
 
 // cooperative copy of the resident blocks (weights, biases, this CTA's mask rows) into shared memory.

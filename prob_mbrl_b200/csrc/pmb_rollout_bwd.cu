@@ -29,8 +29,9 @@ template <int P>
 __device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSweep &net, bool kStoreDelta,
                                              int &sched_i, float *&in, float *&out, float *obuf, float *smem,
                                              float *red, const float *sav, Stream &S, const NarrowMap &nm, int t,
-                                             int n0) {
+                                             int n0, float *part, int &wpg) {
     const int N = prm.N;
+    const Lin &L0 = net.lin[0];
 #pragma unroll 1
     for (int l = net.nlin - 1; l >= 1; --l) {
         const Lin &L = net.lin[l];      // wide: K = outputs of linear l (padded), Npad = width of hidden l-1
@@ -68,7 +69,13 @@ __device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSw
             m.set(npad);
             const int col = 4 * m.cq;
             float *dst = out + col * P;
-            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v) {
+            // the adjoint of hidden layer 0 also forms its share of d(input) = delta_0 W_0 (narrow_fused)
+            const bool fuse = (l == 1);
+            const int cqn = npad >> 2;
+            wpg = fuse ? ((cqn <= 32 ? 32 : cqn <= 64 ? 64 : cqn <= 128 ? 128 : 256) >> 5) : 1;
+            const int wig = (threadIdx.x >> 5) & (wpg - 1);
+            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v, bool act) {
+              if (act) {
                 float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (mask_s) mk = *reinterpret_cast<const float4 *>(mask_s + p * npad + col);
                 else if (mask_g) mk = __ldg(reinterpret_cast<const float4 *>(mask_g + (size_t)min(n0 + p, N - 1) * npad + col));
@@ -82,12 +89,16 @@ __device__ __forceinline__ void net_backward(const SweepParams &prm, const NetSw
                 dst[2 * P + p] = v.z;
                 dst[3 * P + p] = v.w;
                 if (kStoreDelta && n0 + p < N) *reinterpret_cast<float4 *>(dl + (size_t)p * npad + col) = v;
+              }
+              if (fuse) narrow_fused(v, act, p, col, smem + L0.soff, L0.K, L0.Nout, part, wpg, wig);
             });
             ++sched_i;
+            if (fuse) return;               // d(input) sits in `part` as wpg partials per value
         }
         float *tmp = in; in = out; out = tmp;
     }
-    narrow_layer<P>(net.lin[0], nm, smem, in, obuf, nullptr, red);
+    wpg = 0;
+    narrow_layer<P>(L0, nm, smem, in, obuf, nullptr, red);
 }
 
 template <int P>
@@ -159,6 +170,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
     float *stg_s1 = misc + M_STG_S1 * BL, *stg_a = misc + M_STG_A * BL;
     float *pre0 = misc + M_PRE * BL;                    // two buffers of PRE_N blocks
     float *stg_w = pre0 + 2 * PRE_N * BL;               // [P]
+    float *part = misc + 320 * P;                       // partials of the fused input projection
 
     // ---- thread roles (fixed for the whole horizon) ----
     const bool roleA = tid < P * U;                       // (particle, action dim)
@@ -319,8 +331,11 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
             const NetSweep &net = which ? pol : dyn;
+            int wpg = 0;
             net_backward<P>(prm, net, which == 1, sched_i, in, out, obuf, smem, red, sav, S, which ? nm_pol : nm_dyn, t,
-                            n0);
+                            n0, part, wpg);
+            const float *ob = wpg ? part : obuf;
+            const int owpg = wpg ? wpg : 1;
             PMB_MARK(34 + 3 * which);
             CTA_SYNC();
             PMB_MARK(35 + 3 * which);
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
                 // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
                 //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
                 if (roleX) {
-                    const float v = obuf[x_p * dyn.nin + x_k] * cst[C_ISX + x_k];
+                    const float v = read_out(ob, nullptr, x_p, x_k, dyn.nin, owpg) * cst[C_ISX + x_k];
                     if (x_k < D) {
                         gsp[x_p * SD + x_k] += v;
                     } else {
@@ -353,7 +368,8 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
             } else {
                 // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
                 if (roleB)
-                    gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + obuf[b_p * pol.nin + b_d] + pre[PRE_GS0 * BL + b_p * SD + b_d];
+                    gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + read_out(ob, nullptr, b_p, b_d, pol.nin, owpg) +
+                                         pre[PRE_GS0 * BL + b_p * SD + b_d];
                 if (t > 0) precompute_b(pren);
             }
             PMB_MARK(36 + 3 * which);

@@ -17,8 +17,10 @@ namespace pmb {
 template <int P>
 __device__ __forceinline__ void net_forward(const SweepParams &prm, const NetSweep &net, int &sched_i,
                                             float *&in, float *&out, float *obuf, float *smem, float *red,
-                                            Stream &S, const NarrowMap &nm, int t, int n0, bool dbg_on, int mark0) {
+                                            Stream &S, const NarrowMap &nm, int t, int n0, bool dbg_on, int mark0,
+                                            float *part, int &wpg) {
     const int N = prm.N;
+    const Lin &Lo = net.lin[net.nlin - 1];
 #pragma unroll 1
     for (int l = 0; l + 1 < net.nlin; ++l) {
         const Lin &L = net.lin[l];
@@ -54,7 +56,13 @@ __device__ __forceinline__ void net_forward(const SweepParams &prm, const NetSwe
             m.set(npad);
             const int col = 4 * m.cq;
             float *dst = out + col * P;
-            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v) {
+            // the last hidden layer also forms its share of the output projection (narrow_fused)
+            const bool fuse = (l + 2 == net.nlin);
+            const int cqn = npad >> 2;
+            wpg = fuse ? ((cqn <= 32 ? 32 : cqn <= 64 ? 64 : cqn <= 128 ? 128 : 256) >> 5) : 1;
+            const int wig = (threadIdx.x >> 5) & (wpg - 1);
+            wide_layer<P>(L, &prm.sched[sched_i], smem, in, red, S, m, [&](int p, float4 v, bool act) {
+              if (act) {
                 if (bias_s) {
                     const float4 b = *reinterpret_cast<const float4 *>(bias_s + col);
                     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -71,13 +79,20 @@ __device__ __forceinline__ void net_forward(const SweepParams &prm, const NetSwe
                 dst[2 * P + p] = v.z;
                 dst[3 * P + p] = v.w;
                 if (n0 + p < N) *reinterpret_cast<float4 *>(sv + (size_t)p * npad + col) = v;
+              }
+              if (fuse) narrow_fused(v, act, p, col, smem + Lo.soff, Lo.K, Lo.Nout, part, wpg, wig);
             }, dbg_on ? prm.dbg + 64 + 12 * (mark0 + l) : nullptr);
             ++sched_i;
+            if (fuse) {
+                float *tmp = in; in = out; out = tmp;
+                PMB_MARK(mark0 + l);
+                return;                     // outputs are in `part` (wpg partials each), bias not yet added
+            }
         }
         float *tmp = in; in = out; out = tmp;
         PMB_MARK(mark0 + l);
     }
-    const Lin &Lo = net.lin[net.nlin - 1];
+    wpg = 0;                            // plain buffer: narrow_layer adds the bias itself
     narrow_layer<P>(Lo, nm, smem, in, obuf, Lo.bias_soff >= 0 ? smem + Lo.bias_soff : nullptr, red);
     PMB_MARK(mark0 + net.nlin - 1);
 }
@@ -114,6 +129,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
     float *act1 = smem + prm.off_act1;
     float *red = smem + prm.off_red;
     float *obuf = smem + prm.off_misc;
+    float *part = obuf + 320 * P;         // partials of the fused output projection
 
     // ---- thread roles for the per-particle stages (fixed for the whole horizon) ----
     const bool roleA = tid < P * U;                       // one (particle, action dim)
@@ -169,23 +185,31 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
             const NetSweep &net = which ? prm.dyn : prm.pol;
+            int wpg = 0;
             net_forward<P>(prm, net, sched_i, in, out, obuf, smem, red, S, which ? nm_dyn : nm_pol, t, n0, dbg_on,
-                           1 + 8 * which);
+                           1 + 8 * which, part, wpg);
             CTA_SYNC();
             PMB_MARK(7 + 8 * which);
+            // raw outputs of the net: fused path = partials + bias, fallback = finished values in obuf
+            const Lin &Lout = net.lin[net.nlin - 1];
+            const float *ob = wpg ? part : obuf;
+            const float *obias = (wpg && Lout.bias_soff >= 0) ? smem + Lout.bias_soff : nullptr;
+            const int owpg = wpg ? wpg : 1;
             if (which == 0) {
                 // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
                 //      dynamics input (core.py:269,177) ----
                 if (roleA) {
-                    float uu = obuf[a_p * net.nout + a_u];
-                    if (net.has_density) uu += zA * expf(clamp_logstd(obuf[a_p * net.nout + U + a_u], net.lmax));
+                    float uu = read_out(ob, obias, a_p, a_u, net.nout, owpg);
+                    if (net.has_density)
+                        uu += zA * expf(clamp_logstd(read_out(ob, obias, a_p, U + a_u, net.nout, owpg), net.lmax));
                     const float a = cst[C_SCALE + a_u] * tanhf(uu) + cst[C_BIAS + a_u];
                     if (n0 + a_p < N) prm.actions[((size_t)t * N + a_n) * U + a_u] = a;
                     out[(D + a_u) * P + a_p] = (a - cst[C_MX + D + a_u]) * cst[C_ISX + D + a_u];
                 }
                 if (roleB) out[b_d * P + b_p] = (s_reg - cst[C_MX + b_d]) * cst[C_ISX + b_d];
                 if (tid < P * net.nout && n0 + op_p < N)
-                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + op_p) * net.nout + op_j] = obuf[tid];
+                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + op_p) * net.nout + op_j] =
+                        read_out(ob, obias, op_p, op_j, net.nout, owpg);
                 float *tmp = in; in = out; out = tmp;
             } else {
                 // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298);
@@ -194,11 +218,12 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
                     const float sy = cst[C_SY + b_d], my = cst[C_MY + b_d];
                     float delta;
                     if (net.has_density) {
-                        const float mu = obuf[b_p * net.nout + b_d];
-                        const float ls = clamp_logstd(obuf[b_p * net.nout + D + b_d], net.lmax) + cst[C_LSY + b_d];
+                        const float mu = read_out(ob, obias, b_p, b_d, net.nout, owpg);
+                        const float ls = clamp_logstd(read_out(ob, obias, b_p, D + b_d, net.nout, owpg), net.lmax) +
+                                         cst[C_LSY + b_d];
                         delta = (mu * sy + my) + zB * expf(ls);
                     } else {
-                        delta = obuf[b_p * net.nout + b_d] * sy + my;
+                        delta = read_out(ob, obias, b_p, b_d, net.nout, owpg) * sy + my;
                     }
                     s_reg += delta;
                 }
@@ -209,7 +234,8 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
                     if (n0 + b_p < N) prm.states[((size_t)(t + 1) * N + b_n) * D + b_d] = s_reg;
                 }
                 if (tid < P * net.nout && n0 + od_p < N)
-                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + od_p) * net.nout + od_j] = obuf[tid];
+                    prm.ws[net.outsaved_off + ((size_t)t * N + n0 + od_p) * net.nout + od_j] =
+                        read_out(ob, obias, od_p, od_j, net.nout, owpg);
             }
             PMB_MARK(8 + 8 * which);
         }
