@@ -345,7 +345,7 @@ def main():
         flops = fm["bwd_data" if dom == "bwd_sweep_ms" else "fwd"] * work
         achieved = flops / (kern[dom] * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
-        P = eng.tune.particles_per_cta or (8 if n_per > 8 * 148 else 4 if n_per > 2 * 148 else 2)
+        P = eng.tune.particles_per_cta or (8 if n_per > 8 * 148 else 4 if n_per > 2 * 148 else 2 if n_per > 148 else 1)
         ctas = (n_per + P - 1) // P
         roof = {"bound": "tensor", "kernel": "rollout_bwd_kernel" if dom == "bwd_sweep_ms" else "rollout_fwd_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -293,7 +293,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     memset(&pl, 0, sizeof(pl));
     pl.mm_G = G;
     int P = tune && tune->particles_per_cta ? tune->particles_per_cta : 0;
-    if (P == 0) P = (p->N > 8 * 148) ? 8 : (p->N > 2 * 148) ? 4 : 2;   // few particles: spread over more SMs
+    if (P == 0) P = (p->N > 8 * 148) ? 8 : (p->N > 2 * 148) ? 4 : (p->N > 148) ? 2 : 1;   // few particles: spread over more SMs
     if (P != 1 && P != 2 && P != 4 && P != 8) return fail(PMB_E_INVALID, "particles_per_cta must be 1, 2, 4 or 8");
     if (p->mm_states) {
         // every CTA of the grid takes part in a per-step barrier: CTAs must not straddle groups and the
