@@ -1,0 +1,88 @@
+"""GPU tests at the other BASELINE.json shapes (no golden files: seeded inputs, CPU oracle as checker) and
+full-size property tests (particle independence, linearity of the reverse sweep, determinism)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import golden_util as gu  # noqa: E402
+from oracle import rollout_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _fused(dyn, pol, x0, H, cot=None):
+    from prob_mbrl_b200.rollout import fused_rollout_tensors
+    for p in pol.parameters():
+        p.grad = None
+    x = x0.cuda().clone().requires_grad_(True)
+    S, A, R, _ = fused_rollout_tensors(x, dyn, pol, H)
+    if cot is None:
+        obj = -(R.sum(0) / H).mean()
+    else:
+        obj = (R * cot).sum()
+    obj.backward()
+    return S.detach(), A.detach(), R.detach(), [p.grad.clone() for p in pol.parameters()], x.grad.clone(), obj.detach()
+
+
+@pytest.mark.parametrize("cfg,N,H", [("c4", 13, 12), ("c5", 10, 12), ("c1", 25, 40)])
+def test_other_baseline_shapes_match_oracle(cfg, N, H):
+    """3x[400] double-pole (D=8) and 2x[512] nets: wide layers with 2 / 1 k-split groups, three hidden
+    layers, larger rings -- against the fp32 and fp64 CPU oracle on the same seeded inputs."""
+    from prob_mbrl_b200 import operands
+    dyn, pol, x0, _ = bench.build_workload(cfg, N, "cpu")
+    flat = operands.extract(dyn, pol, N).to_flat()
+    ops32 = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in flat.items()}
+    ops64 = {k: (v.detach().double() if torch.is_tensor(v) else v) for k, v in flat.items()}
+    r32 = orc.loss_and_grads(ops32, x0, H)
+    r64 = orc.loss_and_grads(ops64, x0.double(), H)
+    S, A, R, grads, dx0, obj = _fused(dyn.cuda(), pol.cuda(), x0, H)
+    keys = orc.policy_param_keys(ops32)
+    assert (S.cpu() - torch.stack(r32["states"])).abs().max() < 2e-6
+    assert (A.cpu() - torch.stack(r32["actions"])).abs().max() < 4e-5          # actions are x maxU (10 / 20)
+    assert (R.cpu() - torch.stack(r32["rewards"]).squeeze(-1)).abs().max() < 2e-6
+    assert abs(float(obj) - float(r64["loss"])) < 1e-6 * abs(float(r64["loss"])) + 1e-8
+    g64 = [r64["grads"][k] for k in keys]
+    assert gu.rel_l2([g.cpu() for g in grads], g64) < max(1e-5, 3 * gu.rel_l2([r32["grads"][k] for k in keys], g64))
+    assert gu.rel_l2(dx0.cpu(), r64["dx0"]) < 1e-5
+
+
+def test_full_size_c5_shard_properties():
+    """BASELINE.json configs[4] per-GPU shard (Cartpole 2x[512], 250 particles, H=1000): size-independent
+    properties -- particles are independent (a sub-batch reproduces its rows), the reverse sweep is linear
+    in the cotangent, results are finite and deterministic."""
+    cfg, N, H = "c5", 250, 1000
+    dyn, pol, x0, _ = bench.build_workload(cfg, N, "cuda")
+    S, A, R, g1, dx1, _ = _fused(dyn, pol, x0, H)
+    assert torch.isfinite(S).all() and torch.isfinite(R).all() and all(torch.isfinite(g).all() for g in g1)
+    assert S.abs().max() < 50 and (R >= 0).all() and (R <= 1).all()
+    # determinism
+    S2, _, R2, g2, _, _ = _fused(dyn, pol, x0, H)
+    assert torch.equal(S, S2) and all(torch.equal(a, b) for a, b in zip(g1, g2))
+    # particle independence: the first 100 particles alone (another CTA shape: P=1 instead of P=2)
+    Ss, As, Rs, _, dxs, _ = _fused(dyn, pol, x0[:100], H)
+    assert (Ss - S[:, :100]).abs().max() < 1e-4 and (Rs - R[:, :100]).abs().max() < 1e-5
+    # dL/dx0 of the mean-return loss scales with 1/N: rows of the sub-batch gradient = rows of the full one x N/100
+    assert gu.rel_l2(dxs.cpu(), dx1[:100].cpu() * (N / 100.0)) < 1e-3
+    # linearity of the reverse sweep in the reward cotangent
+    gen = torch.Generator().manual_seed(1)
+    c1 = torch.randn(H, N, generator=gen).cuda() / (H * N)
+    c2 = torch.randn(H, N, generator=gen).cuda() / (H * N)
+    _, _, _, ga, _, _ = _fused(dyn, pol, x0, H, cot=c1)
+    _, _, _, gb, _, _ = _fused(dyn, pol, x0, H, cot=c2)
+    _, _, _, gc, _, _ = _fused(dyn, pol, x0, H, cot=2.0 * c1 - 3.0 * c2)
+    lin = [2.0 * a - 3.0 * b for a, b in zip(ga, gb)]
+    assert gu.rel_l2([g.cpu() for g in gc], [g.cpu() for g in lin]) < 1e-4
+
+
+def test_full_size_c4_shard_runs_and_is_finite():
+    """configs[3] per-GPU shard (DoubleCartpole 3x[400], 125 particles, H=600)."""
+    dyn, pol, x0, _ = bench.build_workload("c4", 125, "cuda")
+    S, A, R, g, dx, _ = _fused(dyn, pol, x0, 600)
+    assert torch.isfinite(S).all() and torch.isfinite(R).all() and all(torch.isfinite(t).all() for t in g)
+    assert A.abs().max() <= 20.0 + 1e-4 and (R >= 0).all() and (R <= 1).all()
+    assert sum(float(t.abs().sum()) for t in g) > 0
