@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
     const NetSweep &pol = prm.pol;
     const NetSweep &dyn = prm.dyn;
     const bool has_sav = (pol.nlin > 1) || (dyn.nlin > 1);
+    // tiles and scratch start finite; done by all threads BEFORE the producer may issue any TMA write
+    for (int i = tid; i < prm.off_stage; i += NT_LAUNCH) smem[i] = 0.f;
     // ---- barriers, then the producer warp peels off: it feeds the weight ring and, one step ahead, the
     //      stored hidden activations of each step (TMA bulk copies, one per hidden layer) ----
     if (tid == 0) {
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
     __syncthreads();                       // the only barrier all 288 threads take
     if (tid >= NT) {
         if (tid == NT) {
+            fence_proxy_async();
             float *savb_p = smem + prm.off_sav;
             ring_fill_table(prm, chunk_tab);
             RingProducer rp;
@@ -185,8 +188,6 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
     const int r_p = roleR ? tid - 224 : 0;
     const int r_n = min(n0 + r_p, N - 1);
 
-    for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
-    CTA_SYNC();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;

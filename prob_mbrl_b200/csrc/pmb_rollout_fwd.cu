@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * P;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
+    // tiles and scratch start finite; done by all threads BEFORE the producer may issue any TMA write
+    for (int i = tid; i < prm.off_stage; i += NT_LAUNCH) smem[i] = 0.f;
     // ---- barriers, then the producer warp peels off: it only feeds the weight ring ----
     if (tid == 0) {
         for (int s = 0; s < prm.nstages; ++s) {
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
     __syncthreads();                       // the only barrier all 288 threads take
     if (tid >= NT) {
         if (tid == NT && prm.chunks_per_step > 0) {
+            fence_proxy_async();
             ring_fill_table(prm, chunk_tab);
             RingProducer rp;
             rp.init();
@@ -142,8 +145,6 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
     const int op_p = tid / prm.pol.nout, op_j = tid - op_p * prm.pol.nout;
     const int od_p = tid / prm.dyn.nout, od_j = tid - od_p * prm.dyn.nout;
 
-    for (int i = tid; i < prm.off_stage; i += NT) smem[i] = 0.f;   // tiles and scratch start finite
-    CTA_SYNC();
     load_constants(prm, cst);
     load_resident(prm, smem, n0);
     float s_reg = 0.f;            // role B: this thread's element of the current state (never leaves registers)
