@@ -248,7 +248,10 @@ struct RingProducer {
     __device__ __forceinline__ void issue(const SweepParams &p, float *stage_base, RingBars *bars,
                                           const ChunkDesc *tab, int n) {
         for (int i = 0; i < n; ++i) {
-            if (issued >= (unsigned)p.nstages) mbar_wait(&bars->empty[stage], parity);
+            if (issued >= (unsigned)p.nstages) {
+                mbar_wait(&bars->empty[stage], parity);   // all 8 compute warps released the stage ...
+                fence_proxy_async();                      // ... order their generic reads before the TMA write
+            }
             const ChunkDesc d = tab[idx];
             mbar_expect_tx(&bars->full[stage], d.bytes);
             tma_bulk_g2s(stage_base + (size_t)stage * p.stage_floats, d.src, d.bytes, &bars->full[stage]);

@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
             for (int s = 0; s < H; ++s) {
                 const int tt = H - 1 - s, b = s & 1;
                 if (has_sav) {
-                    if (s >= 2) mbar_wait(&sav_empty[b], ((s >> 1) - 1) & 1);
+                    if (s >= 2) {
+                        mbar_wait(&sav_empty[b], ((s >> 1) - 1) & 1);
+                        fence_proxy_async();
+                    }
                     mbar_expect_tx(&sav_full[b], sav_bytes);
                     for (int n = 0; n < 2; ++n) {
                         const NetSweep &net = n ? pol : dyn;
