@@ -86,3 +86,47 @@ def test_full_size_c4_shard_runs_and_is_finite():
     assert torch.isfinite(S).all() and torch.isfinite(R).all() and all(torch.isfinite(t).all() for t in g)
     assert A.abs().max() <= 20.0 + 1e-4 and (R >= 0).all() and (R <= 1).all()
     assert sum(float(t.abs().sum()) for t in g) > 0
+
+
+def test_per_step_noise_tables_match_oracle():
+    """rollout() defaults (resample_state_noise / resample_action_noise = True, reference
+    utils/rollout.py:68-69): fresh output noise every step.  The fused path pre-draws [H, N, .] tables in
+    the reference's per-step order and the kernels read them with a step stride."""
+    from prob_mbrl_b200 import operands
+    from prob_mbrl_b200.rollout import FusedRolloutFunction
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    H, N = int(g["H"]), int(g["N"])
+    gen = torch.Generator().manual_seed(3)
+    zp = torch.randn(H, N, 1, generator=gen)
+    zd = torch.randn(H, N, 5, generator=gen)
+    o = operands.RolloutOperands.from_flat(ops, device="cuda")
+    o.pol.z, o.dyn.z = zp.cuda(), zd.cuda()
+    params = [p.requires_grad_(True) for p in o.policy_parameters()]
+    x0 = g["x0"].cuda().requires_grad_(True)
+    mm = dict(mm_states=False, mm_rewards=False, mm_groups=None, z_mm=None, z_rr=None)
+    S, A, R, _ = FusedRolloutFunction.apply(x0, (o, N, H, mm), *params)
+    loss = -(R.sum(0) / H).mean()
+    grads = torch.autograd.grad(loss, params + [x0])
+    d = dict(ops)
+    d["pol_z"], d["dyn_z"] = zp, zd
+    ref = orc.loss_and_grads(d, g["x0"], H)
+    keys = orc.policy_param_keys(ops)
+    assert (S.detach().cpu() - torch.stack(ref["states"])).abs().max() < 2e-6
+    assert abs(float(loss) - float(ref["loss"])) < 1e-7
+    assert gu.rel_l2([x.cpu() for x in grads[:-1]], [ref["grads"][k] for k in keys]) < 1e-5
+    assert gu.rel_l2(grads[-1].cpu(), ref["dx0"]) < 1e-5
+
+
+def test_rollout_default_flags_draw_fresh_noise_and_leave_buffers_like_the_reference():
+    import prob_mbrl_b200 as pm
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    dyn, pol = gu.modules_from_ops(ops, "cuda")
+    torch.manual_seed(0)
+    S1, A1, R1 = pm.rollout(g["x0"].cuda(), dyn, pol, 6)           # defaults: resample_*_noise=True
+    z_after = dyn.output_density.z.clone()
+    S2, A2, R2 = pm.rollout(g["x0"].cuda(), dyn, pol, 6)
+    assert len(S1) == 7 and not torch.equal(torch.stack(S1), torch.stack(S2))     # fresh noise each call
+    assert not torch.equal(z_after, dyn.output_density.z) and dyn.output_density.z.shape == (7, 5)
+    Sp1 = torch.stack(pm.rollout(g["x0"].cuda(), dyn, pol, 6, resample_state_noise=False, resample_action_noise=False)[0])
+    Sp2 = torch.stack(pm.rollout(g["x0"].cuda(), dyn, pol, 6, resample_state_noise=False, resample_action_noise=False)[0])
+    assert torch.equal(Sp1, Sp2)                                                  # PEGASUS: frozen noise
