@@ -130,3 +130,50 @@ def test_rollout_default_flags_draw_fresh_noise_and_leave_buffers_like_the_refer
     Sp1 = torch.stack(pm.rollout(g["x0"].cuda(), dyn, pol, 6, resample_state_noise=False, resample_action_noise=False)[0])
     Sp2 = torch.stack(pm.rollout(g["x0"].cuda(), dyn, pol, 6, resample_state_noise=False, resample_action_noise=False)[0])
     assert torch.equal(Sp1, Sp2)                                                  # PEGASUS: frozen noise
+
+
+@pytest.mark.parametrize("variant", ["cvar", "sgd_discount", "value_func"])
+def test_mc_pilco_generic_path_matches_eager_loop(variant, monkeypatch):
+    """Loss variants that go through autograd on the fused rollout's outputs (reference
+    algorithms/mc_pilco.py:136-188,193-194): CVaR subset, callable optimiser other than Adam + discount,
+    value-function tail on states[-1].  Checked against the same mc_pilco on the eager module loop (CPU)."""
+    import prob_mbrl_b200 as pm
+    monkeypatch.setenv("PMB_NO_PBAR", "1")
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    results = []
+    for dev, backend in (("cpu", "eager"), ("cuda", "fused")):
+        monkeypatch.setenv("PROB_MBRL_BACKEND", backend)
+        dyn, pol = gu.modules_from_ops(ops, dev)
+        kw = dict(pegasus=True, maximize=True, clip_grad=1.0, resampling_period=10 ** 6, init_state_noise=0.0)
+        vf = None
+        if variant == "cvar":
+            opt = torch.optim.Adam(pol.parameters(), 1e-3)
+            kw.update(cvar_eps=0.5)
+        elif variant == "sgd_discount":
+            opt = torch.optim.SGD(pol.parameters(), 1e-2, momentum=0.9)
+            kw.update(discount=0.97)
+        else:
+            opt = torch.optim.Adam(pol.parameters(), 1e-3)
+            torch.manual_seed(1)
+            lin = torch.nn.Linear(5, 1).to(dev)
+
+            class V(torch.nn.Module):
+                def forward(self, x, **kwargs):
+                    return lin(x)
+
+                def resample(self, **kwargs):
+                    pass
+            vf = V()
+            kw.update(value_func=vf)
+        sys.modules["prob_mbrl_b200.mc_pilco"].policy_update_counter[pol] = 1     # keep the fixture's noise
+        # the initial resample() inside mc_pilco redraws masks: neutralise it so both runs use the fixture's
+        dyn.resample = lambda *a, **k: None
+        pol.resample = lambda *a, **k: None
+        losses = []
+        pm.mc_pilco(g["x0"].to(dev), dyn, pol, int(g["H"]), opt, None, 3,
+                    on_iteration=lambda i, loss, *a: losses.append(float(loss)), **kw)
+        results.append((torch.cat([p.detach().cpu().flatten() for p in pol.parameters()]), losses))
+    (pa, la), (pb, lb) = results
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-6
+    assert (pa - pb).abs().max() < 5e-6
+    assert (pa - torch.cat([ops[k].flatten() for k in orc.policy_param_keys(ops)])).abs().max() > 1e-4
