@@ -347,9 +347,14 @@ def main():
         peak = peaks["bf16_tflops"]
         P = eng.tune.particles_per_cta or (8 if n_per > 8 * 148 else 4 if n_per > 2 * 148 else 2 if n_per > 148 else 1)
         ctas = (n_per + P - 1) // P
-        roof = {"bound": "tensor", "kernel": "rollout_bwd_kernel" if dom == "bwd_sweep_ms" else "rollout_fwd_kernel",
+        kname = "rollout_bwd_kernel" if dom == "bwd_sweep_ms" else "rollout_fwd_kernel"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # dram__bytes_read+write per launch, from
+        if cfg == "c2" and os.path.exists(tpath):                             # the committed `ncu --set full` capture
+            traffic = json.load(open(tpath)).get("pmb::" + kname)
+        roof = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "%s bf16 burst (kernel timed alone)" % peaks["source"], "traffic": None,
+                "peak_source": "%s bf16 burst (kernel timed alone)" % peaks["source"], "traffic": traffic,
                 "algorithmic_flops_per_launch": flops, "launch_ms": kern[dom],
                 "sms_occupied": min(ctas, 148),
                 "frac_of_occupied_sm_peak": achieved / (peak * min(ctas, 148) / 148.0),
