@@ -351,7 +351,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # dram__bytes_read+write per launch, from
         if cfg == "c2" and os.path.exists(tpath):                             # the committed `ncu --set full` capture
-            traffic = json.load(open(tpath)).get("pmb::" + kname)
+            traffic = json.load(open(tpath)).get(kname)
         roof = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16 burst (kernel timed alone)" % peaks["source"], "traffic": traffic,
