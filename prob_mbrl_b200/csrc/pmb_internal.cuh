@@ -175,6 +175,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float clamp_logstd(float l, float lmax) { return lmax - softplus_f(lmax - l); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// exp(clamp_logstd(l, lmax)) = exp(lmax - log(1 + exp(lmax - l))) = exp(lmax) / (1 + exp(lmax - l)):
+// one expf and one division on the serial chain instead of expf + log1pf + expf (same value to ~2 ulp;
+// for lmax - l > 88 it underflows to 0 exactly like exp(l) does).  `elmax` = exp(lmax), precomputed.
+__device__ __forceinline__ float exp_clamped_logstd(float l, float lmax, float elmax) {
+    return elmax / (1.f + expf(lmax - l));
+}
 
 // ----------------------------------------------------------------------------------------
 // The weight stream: a ring of `nstages` smem stages consumed in a fixed cyclic schedule.
@@ -480,28 +486,41 @@ __device__ __forceinline__ void narrow_layer(const Lin &L, const NarrowMap &nm, 
 // values v of particle p (zeros on idle lanes); the warp forms its share of out[p][j] = sum_k h[k] w[j][k]
 // for all j with 4 dot products in flight and a butterfly reduction, lane 0 publishes one partial per
 // (p, j, warp-of-the-group).  The consumers add the partials of the group's warps (read_out).
+template <int B>
+__device__ __forceinline__ void narrow_fused_batch(const float4 v, bool active, int p, int col, const float *wn, int K,
+                                                   int nout, int j0, float *part, int wpg, int wig) {
+    const int lane = threadIdx.x & 31;
+    float s[B];
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+        const int j = min(j0 + q, nout - 1);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) w = *reinterpret_cast<const float4 *>(wn + (size_t)j * K + col);
+        s[q] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, v.w * w.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < B; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    }
+    if (lane < B && j0 + lane < nout) {
+        float r = s[0];
+#pragma unroll
+        for (int q = 1; q < B; ++q) r = lane == q ? s[q] : r;
+        part[(p * nout + j0 + lane) * wpg + wig] = r;
+    }
+}
+// B dot products in flight: 4 for the 2-output policy head, 12 for the 10/16-output heads (B = 12 covers
+// the 10 outputs of a 5-dim state in one batch).
 __device__ __forceinline__ void narrow_fused(const float4 v, bool active, int p, int col, const float *wn, int K,
                                              int nout, float *part, int wpg, int wig) {
-    const int lane = threadIdx.x & 31;
+    if (nout <= 4) {
+        narrow_fused_batch<4>(v, active, p, col, wn, K, nout, 0, part, wpg, wig);
+    } else if (nout <= 8) {
+        narrow_fused_batch<8>(v, active, p, col, wn, K, nout, 0, part, wpg, wig);
+    } else {
 #pragma unroll 1
-    for (int j0 = 0; j0 < nout; j0 += 4) {
-        float s[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = min(j0 + q, nout - 1);
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) w = *reinterpret_cast<const float4 *>(wn + (size_t)j * K + col);
-            s[q] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, v.w * w.w)));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-        }
-        if (lane < 4 && j0 + lane < nout) {
-            const float r = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
-            part[(p * nout + j0 + lane) * wpg + wig] = r;
-        }
+        for (int j0 = 0; j0 < nout; j0 += 12) narrow_fused_batch<12>(v, active, p, col, wn, K, nout, j0, part, wpg, wig);
     }
 }
 // out[p][j] from the published partials (wpg = 1, bias = nullptr: plain buffer written by narrow_layer)

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
         act0[b_d * P + b_p] = s_reg;
         if (n0 + b_p < N) prm.states[(size_t)b_n * D + b_d] = s_reg;
     }
+    const float elmax_pol = expf(prm.pol.lmax), elmax_dyn = expf(prm.dyn.lmax);
     float zA = 0.f, zB = 0.f;
     if (roleA && prm.pol.has_density) zA = __ldg(prm.pol.z + (size_t)a_n * U + a_u);
     if (roleB && prm.dyn.has_density) zB = __ldg(prm.dyn.z + (size_t)b_n * D + b_d);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
                 if (roleA) {
                     float uu = read_out(ob, obias, a_p, a_u, net.nout, owpg);
                     if (net.has_density)
-                        uu += zA * expf(clamp_logstd(read_out(ob, obias, a_p, U + a_u, net.nout, owpg), net.lmax));
+                        uu += zA * exp_clamped_logstd(read_out(ob, obias, a_p, U + a_u, net.nout, owpg), net.lmax, elmax_pol);
                     const float a = cst[C_SCALE + a_u] * tanhf(uu) + cst[C_BIAS + a_u];
                     if (n0 + a_p < N) prm.actions[((size_t)t * N + a_n) * U + a_u] = a;
                     out[(D + a_u) * P + a_p] = (a - cst[C_MX + D + a_u]) * cst[C_ISX + D + a_u];
@@ -220,9 +221,10 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_fwd_kernel(const __grid_
                     float delta;
                     if (net.has_density) {
                         const float mu = read_out(ob, obias, b_p, b_d, net.nout, owpg);
-                        const float ls = clamp_logstd(read_out(ob, obias, b_p, D + b_d, net.nout, owpg), net.lmax) +
-                                         cst[C_LSY + b_d];
-                        delta = (mu * sy + my) + zB * expf(ls);
+                        // exp(clamped log-std + log Sy) = Sy * exp(clamped log-std)   (densities.py:105)
+                        const float sd = sy * exp_clamped_logstd(read_out(ob, obias, b_p, D + b_d, net.nout, owpg),
+                                                                 net.lmax, elmax_dyn);
+                        delta = (mu * sy + my) + zB * sd;
                     } else {
                         delta = read_out(ob, obias, b_p, b_d, net.nout, owpg) * sy + my;
                     }
