@@ -91,7 +91,9 @@ typedef struct pmb_tuning {
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
                                 4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default.
                                 reserved[2..3]: low/high half of a device pointer to >= 64 int64 that receives
-                                clock64() timeline marks of one step (profiling aid), 0 = off */
+                                clock64() timeline marks of one step (profiling aid), 0 = off.
+                                reserved[4]: hidden x hidden weight gradient on tcgen05 (TF32 x3 split): 0 = auto (when a split-K
+                                slice is <= 1024 rows), 1 = always, 2 = never (FFMA2 kernel) */
 } pmb_tuning;
 
 int pmb_abi_version(void);

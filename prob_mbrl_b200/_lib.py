@@ -221,6 +221,7 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t = PmbTuning()
     t.reserved[0] = int(phases)
     t.reserved[1] = int(os.environ.get("PMB_STAGES", "0"))
+    t.reserved[4] = int(os.environ.get("PMB_WGRAD_UMMA", "0"))
     t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))

@@ -498,7 +498,8 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
         const float *A = ws + g.delta_off;
         const float *Bm = g.inp_off < 0 ? states : ws + g.inp_off;
         PMB_CUDA(launch_wgrad(A, g.lda, g.M, Bm, g.ldb, g.Nc, R, pl.nsplit, part + g.w_off,
-                              g.b_off >= 0 ? part + g.b_off : nullptr, pl.nparam, st));
+                              g.b_off >= 0 ? part + g.b_off : nullptr, pl.nparam, st,
+                              tune ? tune->reserved[4] : 0));
     }
     PMB_CUDA(launch_reduce_partials(part, pl.nparam, pl.nsplit, grad_flat, st));
     return PMB_OK;

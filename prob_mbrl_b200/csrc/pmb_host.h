@@ -22,7 +22,7 @@ cudaError_t launch_pack(const PackJobs &jobs, cudaStream_t stream);
 cudaError_t launch_rollout_fwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream);
 cudaError_t launch_rollout_bwd(const SweepParams &prm, int P, int smem_bytes, cudaStream_t stream);
 cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb, int Nc, long long R, int nsplit,
-                         float *w_part, float *bias_part, long long part_stride, cudaStream_t stream);
+                         float *w_part, float *bias_part, long long part_stride, cudaStream_t stream, int use_umma);
 cudaError_t launch_reduce_partials(const float *part, long long n, int nsplit, float *out, cudaStream_t stream);
 cudaError_t launch_reward_mm_fwd(const float *rpre, float *rout, const float *z_rr, float *rstat, int N, int H, int G,
                                  int *status, cudaStream_t stream);

@@ -123,6 +123,184 @@ __global__ void __launch_bounds__(256) wgrad_tile_kernel(const float *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM version of the same contraction for the hidden x hidden layers (the one genuinely dense
+// GEMM of the path: [M x R] . [R x N] with R = H*N rows).  fp32 parity on the tensor pipe needs a split:
+// x = hi + lo with hi = tf32(x); C += A_hi B_hi + A_hi B_lo + A_lo B_hi (3 x kind::tf32, fp32 accumulate in
+// TMEM; the dropped lo*lo term is ~2^-22 relative).  In global memory the reduction index r is the slow axis
+// of both delta[r][m] and x[r][n] (MN-major), but kind::tf32 reads MN-major no-swizzle operands as zeros on
+// this part (tests/csrc/umma_probe.cu, profiles/r01_umma_layout_probe.txt), so the loader transposes while
+// staging into the K-major no-swizzle canonical layout the probe confirmed: core matrix = 8 MN rows x 16 B
+// (4 k), the two k halves of a K=8 MMA 128 B apart (LBO), groups of 8 MN rows 256 B apart (SBO).
+// One CTA = one 128-row M tile x all N (<= 256) columns x one split-K slice; 256 threads load, split and
+// store; one elected thread issues the MMAs; 4 warps drain TMEM with tcgen05.ld.
+// ---------------------------------------------------------------------------------------------
+constexpr int UM = 128;        // UMMA M
+constexpr int UKB = 4;         // k-blocks (of 8 rows) per stage
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // version 1 (sm_100), SWIZZLE_NONE
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restrict__ A, int lda, int M,
+                                                            const float *__restrict__ B, int ldb, int Nc,
+                                                            long long R, int nsplit, float *__restrict__ w_out,
+                                                            float *__restrict__ bias_out, long long part_stride,
+                                                            int n16) {
+    extern __shared__ __align__(128) float usm[];
+    __shared__ __align__(8) uint64_t stage_free[2], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * UM;
+    const long long rows_per = (((R + nsplit - 1) / nsplit) + 7) & ~7LL;
+    const long long r0 = (long long)blockIdx.y * rows_per;
+    const long long r1 = min(R, r0 + rows_per);
+    const int a_kb = UM * 8;                 // floats per k-block of A
+    const int b_kb = n16 * 8;                // floats per k-block of B
+    const int stage_floats = UKB * 2 * (a_kb + b_kb);
+    const int ncols = Nc + (bias_out ? 1 : 0);
+
+    if (tid == 0) {
+        mbar_init(&stage_free[0], 1);
+        mbar_init(&stage_free[1], 1);
+        mbar_init(&done_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    // fp32 accumulate, tf32 x tf32, both operands K-major
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+
+    constexpr int A_ITEMS = UKB * 2 * UM / 256, B_ITEMS = UKB * 2 * 256 / 256;
+    int b_n[B_ITEMS], b_rq[B_ITEMS];          // this thread's (column, row quad) items of a B stage
+#pragma unroll
+    for (int j = 0; j < B_ITEMS; ++j) {
+        const int i = tid + 256 * j;
+        b_n[j] = i % n16;
+        b_rq[j] = i / n16;                    // >= 2*UKB: past the stage (n16 < 256)
+    }
+
+    int s = 0;
+    for (long long rs = r0; rs < r1; rs += 8 * UKB, ++s) {
+        const int b = s & 1;
+        float *st = usm + (size_t)b * stage_floats;
+        float *Ahi = st, *Alo = st + UKB * a_kb, *Bhi = st + 2 * UKB * a_kb, *Blo = Bhi + UKB * b_kb;
+        // Lanes run over the MN index (coalesced 128 B row segments), each thread gathers 4 consecutive k rows of
+        // one column and stores them as one 16 B K-major core-matrix row (conflict-free per quarter warp).
+        // All of a stage's loads are issued before the first conversion so ~44 requests per thread are in flight.
+        float va[A_ITEMS][4], vb[B_ITEMS][4];
+#pragma unroll
+        for (int j = 0; j < A_ITEMS; ++j) {
+            const int i = tid + 256 * j, ml = i % UM, rq = i / UM;
+            const long long r = rs + 4 * rq;
+            const int m = m0 + ml;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) va[j][e] = (m < M && r + e < r1) ? __ldg(A + (r + e) * lda + m) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < B_ITEMS; ++j) {
+            const long long r = rs + 4 * b_rq[j];
+            const int n = b_n[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                vb[j][e] = (b_rq[j] < 2 * UKB && r + e < r1) ? (n < Nc ? __ldg(B + (r + e) * ldb + n) : ((n == Nc && bias_out) ? 1.f : 0.f)) : 0.f;
+        }
+        if (s >= 2) mbar_wait(&stage_free[b], ((s >> 1) - 1) & 1);   // the MMAs that read this buffer retired
+#pragma unroll
+        for (int j = 0; j < A_ITEMS; ++j) {
+            const int i = tid + 256 * j, ml = i % UM, rq = i / UM;
+            const float4 h = make_float4(tf32_hi(va[j][0]), tf32_hi(va[j][1]), tf32_hi(va[j][2]), tf32_hi(va[j][3]));
+            const int off = (rq >> 1) * a_kb + (ml >> 3) * 64 + (rq & 1) * 32 + (ml & 7) * 4;
+            *reinterpret_cast<float4 *>(Ahi + off) = h;
+            *reinterpret_cast<float4 *>(Alo + off) = make_float4(va[j][0] - h.x, va[j][1] - h.y, va[j][2] - h.z, va[j][3] - h.w);
+        }
+#pragma unroll
+        for (int j = 0; j < B_ITEMS; ++j) {
+            if (b_rq[j] < 2 * UKB) {
+                const int n = b_n[j], rq = b_rq[j];
+                const float4 h = make_float4(tf32_hi(vb[j][0]), tf32_hi(vb[j][1]), tf32_hi(vb[j][2]), tf32_hi(vb[j][3]));
+                const int off = (rq >> 1) * b_kb + (n >> 3) * 64 + (rq & 1) * 32 + (n & 7) * 4;
+                *reinterpret_cast<float4 *>(Bhi + off) = h;
+                *reinterpret_cast<float4 *>(Blo + off) = make_float4(vb[j][0] - h.x, vb[j][1] - h.y, vb[j][2] - h.z, vb[j][3] - h.w);
+            }
+        }
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long left = (r1 - rs + 7) / 8;
+            const int nkb = left < UKB ? (int)left : UKB;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint64_t dAh = umma_desc(smem_u32(Ahi + kb * a_kb), 128, 256);
+                const uint64_t dAl = umma_desc(smem_u32(Alo + kb * a_kb), 128, 256);
+                const uint64_t dBh = umma_desc(smem_u32(Bhi + kb * b_kb), 128, 256);
+                const uint64_t dBl = umma_desc(smem_u32(Blo + kb * b_kb), 128, 256);
+                umma_tf32(tmem_d, dAh, dBh, idesc, (s | kb) ? 1u : 0u);
+                umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+                umma_tf32(tmem_d, dAl, dBh, idesc, 1u);
+            }
+            umma_commit(&stage_free[b]);
+        }
+    }
+    if (tid == 0) umma_commit(&done_bar);
+    float *wo = w_out + (long long)blockIdx.y * part_stride;
+    float *bo = bias_out ? bias_out + (long long)blockIdx.y * part_stride : nullptr;
+    if (s == 0) {           // empty slice: contribute zeros
+        for (int i = tid; i < UM * ncols; i += 256) {
+            const int m = m0 + i / ncols, n = i % ncols;
+            if (m < M) { if (n < Nc) wo[(long long)m * Nc + n] = 0.f; else bo[m] = 0.f; }
+        }
+    } else {
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp < 4) {         // warp w drains TMEM lanes 32w .. 32w+31 = rows m0 + 32w + lane
+            const int m = m0 + 32 * warp + lane;
+            for (int c = 0; c < n16; c += 8) {
+                uint32_t v[8];
+                const uint32_t taddr = tmem_d + ((uint32_t)(32 * warp) << 16) + (uint32_t)c;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int n = c + e;
+                        if (n < Nc) wo[(long long)m * Nc + n] = __uint_as_float(v[e]);
+                        else if (n == Nc && bo) bo[m] = __uint_as_float(v[e]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
+}
+
 __global__ void reduce_partials_kernel(const float *__restrict__ part, long long n, int nsplit,
                                        float *__restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -135,8 +313,22 @@ __global__ void reduce_partials_kernel(const float *__restrict__ part, long long
 
 // partials of one linear layer: A = output adjoints [R][lda] (M columns), B = layer input [R][ldb] (Nc columns)
 cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb, int Nc, long long R,
-                         int nsplit, float *w_part, float *bias_part, long long part_stride, cudaStream_t stream) {
+                         int nsplit, float *w_part, float *bias_part, long long part_stride, cudaStream_t stream,
+                         int use_umma) {
     const int ncols = Nc + (bias_part ? 1 : 0);
+    const int n16 = (ncols + 15) & ~15;
+    // mode 0 (auto): tensor cores while one split-K slice accumulates <= 1024 rows in TMEM -- the tensor core's
+    // fp32 accumulation rounds coarser than FFMA (measured 2.1e-6 vs 3.7e-7 gradient error at 625 rows per
+    // slice against a 1e-5 budget); 1: always; 2: never.
+    const bool umma = use_umma == 1 || (use_umma == 0 && (R + nsplit - 1) / nsplit <= 1024);
+    if (umma && M > 16 && Nc > 16 && n16 <= 256) {
+        const int smem = 2 * UKB * 2 * (UM * 8 + n16 * 8) * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid((M + UM - 1) / UM, nsplit);
+        wgrad_umma_kernel<<<grid, 256, smem, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, w_part, bias_part, part_stride, n16);
+        return cudaGetLastError();
+    }
     dim3 grid(((M + BM - 1) / BM) * ((ncols + BN - 1) / BN), nsplit);
     wgrad_tile_kernel<<<grid, 256, 0, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, w_part, bias_part, part_stride);
     return cudaGetLastError();

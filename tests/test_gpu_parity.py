@@ -119,6 +119,22 @@ def test_ring_depths_agree():
         assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
 
 
+@pytest.mark.parametrize("fixture", ["cartpole_200x2_n25_h40", "cartpole_200x2_n100_h400", "cartpole_37x2_n7_h12"])
+def test_tensor_core_weight_gradient_matches_fp32_kernel(fixture):
+    """PMB_WGRAD_UMMA=1 (0 = auto, 2 = off) routes the hidden x hidden weight gradient through the tcgen05 kernel (TF32 hi/lo split,
+    3 MMAs, fp32 accumulation in TMEM).  It must agree with the FFMA2 split-K kernel to fp32 rounding and
+    meet the same 1e-5 budget against the reference's gradient."""
+    ops, g = gu.load(fixture)
+    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_WGRAD_UMMA": 2})
+    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_WGRAD_UMMA": 1})
+    ref = gu.policy_grad_list(g, "nomm", ops)
+    ea, eb = gu.rel_l2(a["grads"], ref), gu.rel_l2(b["grads"], ref)
+    print(f"{fixture}: FFMA2 vs reference {ea:.2e}, tcgen05 vs reference {eb:.2e}, "
+          f"mutual {gu.rel_l2(a['grads'], b['grads']):.2e}")
+    assert gu.rel_l2(a["grads"], b["grads"]) < 5e-6      # two fp32 summation orders over H*N rows
+    assert ea < 1e-5 and eb < 1e-5
+
+
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
 def test_particles_per_cta_variants(P):
     ops, g = gu.load("cartpole_37x2_n7_h12")   # N=7: ragged last CTA for every P > 1
