@@ -86,10 +86,15 @@ typedef struct pmb_problem {
 /* Tunables (0 = library default). */
 typedef struct pmb_tuning {
     int particles_per_cta;   /* 1, 2, 4 or 8 */
-    int stream_mode;         /* 0 default (=2), 1 = synchronous copies, 2 = TMA bulk copies + mbarrier ring */
+    int stream_mode;         /* sweep variant: 0 = auto (cluster-resident sweeps when the nets fit, else 2),
+                                1/2 = streaming sweeps (hidden x hidden weights through a TMA + mbarrier ring),
+                                3 = cluster-resident sweeps required (all weights in the shared memory of a
+                                thread-block cluster; PMB_E_UNSUPPORTED when the problem is outside them) */
     int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
-                                4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default.
+                                4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default; with
+                                stream_mode 3: bits 0-3 particles per cluster (1..8, 0 = auto), bits 4-7 CTAs per
+                                cluster (4 or 8, 0 = 8).
                                 reserved[2..3]: low/high half of a device pointer to >= 64 int64 that receives
                                 clock64() timeline marks of one step (profiling aid), 0 = off.
                                 reserved[4]: hidden x hidden weight gradient on tcgen05 (TF32 x3 split): 0 = auto (when a split-K

@@ -223,7 +223,11 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t.reserved[1] = int(os.environ.get("PMB_STAGES", "0"))
     t.reserved[4] = int(os.environ.get("PMB_WGRAD_UMMA", "0"))
     t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))
+    # 0 = auto (cluster-resident sweeps when eligible), 1/2 = streaming sweeps, 3 = cluster-resident (required)
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
+    if t.stream_mode == 3:
+        # particles per cluster (1..8, 0 = auto) and CTAs per cluster (4 or 8, 0 = 8)
+        t.reserved[1] = int(os.environ.get("PMB_CLUSTER_PG", "0")) | (int(os.environ.get("PMB_CLUSTER_C", "0")) << 4)
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
 

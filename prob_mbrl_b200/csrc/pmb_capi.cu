@@ -9,6 +9,7 @@
 #include "pmb_host.h"
 #include "pmb_internal.cuh"
 #include "pmb_mm.cuh"
+#include "pmb_cluster.cuh"
 
 namespace pmb {
 
@@ -49,6 +50,10 @@ struct Plan {
     int smem_fwd_bytes, smem_bwd_bytes;
     int n_wg;
     WGrad wg[MAXL];
+    // cluster-resident sweeps (pmb_cluster.cuh): used instead of the streaming sweeps when eligible
+    int cluster;              // 0 = streaming sweeps, otherwise CTAs per cluster
+    int cl_nclusters;
+    ClusterParams cfwd, cbwd;
 };
 
 struct Alloc {
@@ -269,6 +274,137 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
     return off * 4;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster-resident sweeps: eligibility, operand tables and shared-memory carve-up (pmb_cluster.cuh).
+// Eligible: two hidden layers per net (models.mlp as used by every example of the reference), hidden
+// widths <= 256, D+U <= 16, outputs <= 16, no moment matching of the states.
+// ---------------------------------------------------------------------------------------------
+static bool cluster_eligible(const pmb_problem *p, int C) {
+    if (p->mm_states) return false;
+    const pmb_net *nets[2] = {&p->pol, &p->dyn};
+    for (int i = 0; i < 2; ++i) {
+        const pmb_net &n = *nets[i];
+        if (n.n_linear != 3) return false;
+        const int w0 = round4(n.dims[1]), w1 = round4(n.dims[2]);
+        if (w0 > CL_TW || w1 > CL_TW) return false;
+        if (n.dims[0] > CL_NO || n.dims[3] > CL_NO) return false;
+        if (round4((w0 + C - 1) / C) > CL_HS || round4((w1 + C - 1) / C) > CL_HS) return false;
+    }
+    return true;
+}
+
+static void cluster_net(const NetSweep &S, bool reverse, bool is_policy, int C, CNet &n) {
+    memset(&n, 0, sizeof(n));
+    const Lin &thin = reverse ? S.lin[2] : S.lin[0];
+    const Lin &wide = S.lin[1];
+    const Lin &narrow = reverse ? S.lin[0] : S.lin[2];
+    const int ht = reverse ? 1 : 0, hw = reverse ? 0 : 1;     // hidden layer produced by the thin / wide op
+    n.tK = thin.K;
+    n.tW = thin.Npad;
+    n.tsl = round4((n.tW + C - 1) / C);
+    n.wN = wide.Npad;
+    n.hs = round4((n.wN + C - 1) / C);
+    n.nN = narrow.Nout;
+    n.nNp = round4(n.nN);
+    n.t_goff = thin.goff;
+    n.w_goff = wide.goff;
+    n.n_goff = narrow.goff;
+    n.tb_off = reverse ? -1 : thin.boff;
+    n.wb_off = reverse ? -1 : wide.boff;
+    n.nb_off = reverse ? -1 : narrow.boff;
+    n.tm_off = S.mask_off[ht];
+    n.wm_off = S.mask_off[hw];
+    n.tkeep_inv = 1.f / S.keep[ht];
+    n.wkeep_inv = 1.f / S.keep[hw];
+    n.tsav_off = S.saved_off[ht];
+    n.wsav_off = S.saved_off[hw];
+    n.tdel_off = (reverse && is_policy) ? S.delta_off[ht] : -1;
+    n.wdel_off = (reverse && is_policy) ? S.delta_off[hw] : -1;
+    n.odel_off = (reverse && is_policy) ? S.delta_off[2] : -1;
+    n.raw_off = S.outsaved_off;
+    n.nraw = S.nout;
+    n.has_density = S.has_density;
+    n.lmax = S.lmax;
+    n.z = S.z;
+    n.zstride = S.zstride;
+}
+
+static int cluster_carve(ClusterParams &P, bool reverse) {
+    int off = 0;
+    auto take = [&](int nfl) { int o = off; off += (nfl + 31) & ~31; return o; };
+    P.off_cst = take(C_TOTAL);
+    CNet *nets[2] = {&P.pol, &P.dyn};
+    int tw_max = 4;
+    for (int i = 0; i < 2; ++i) {
+        CNet &n = *nets[i];
+        n.s_tw = take(n.tK * n.tW);
+        n.s_ww = take(n.tW * n.hs);
+        n.s_nw = take(n.nN * n.hs);
+        n.s_nwt = take(CL_NO * CL_HS);
+        n.s_tb = take(n.tW);
+        n.s_wb = take(n.hs);
+        n.s_nb = take(CL_NO);
+        n.s_tm = take(CL_PS * n.tW);
+        n.s_wm = take(CL_PS * n.hs);
+        tw_max = max(tw_max, n.tW);
+    }
+    P.off_xa = take(2 * CL_NO * CL_PS);
+    P.off_xb = take(2 * CL_NO * CL_PS);
+    P.off_act = take(tw_max * CL_PS);
+    P.off_red = take(8 * CL_PS * 32);
+    P.off_h2s = take(CL_PS * 32);
+    P.off_part = take(CL_INBOX);
+    P.off_inbox = take(2 * P.C * CL_INBOX);
+    P.off_misc = take(reverse ? (4 + 2 * 6) * CL_PS * SD + 32 : CL_PS * SD);
+    P.smem_floats = off;
+    return off;
+}
+
+// fills pl.cluster / pl.cfwd / pl.cbwd from the streaming plan's layer tables (same workspace layout)
+static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
+    pl.cluster = 0;
+    const int mode = tune ? tune->stream_mode : 0;
+    if (mode == 1 || mode == 2) return PMB_OK;
+    int C = (tune && mode == 3) ? (tune->reserved[1] >> 4) & 15 : 0;
+    if (C == 0) C = 8;
+    if (C != 4 && C != 8) return fail(PMB_E_INVALID, "cluster size must be 4 or 8");
+    if (!cluster_eligible(p, C)) {
+        if (mode == 3) return fail(PMB_E_UNSUPPORTED, "problem is outside the cluster-resident sweeps");
+        return PMB_OK;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const SweepParams &S = pass ? pl.bwd : pl.fwd;
+        ClusterParams &P = pass ? pl.cbwd : pl.cfwd;
+        memset(&P, 0, sizeof(P));
+        P.N = S.N; P.H = S.H; P.D = S.D; P.U = S.U; P.C = C;
+        cluster_net(S.pol, pass == 1, true, C, P.pol);
+        cluster_net(S.dyn, pass == 1, false, C, P.dyn);
+        P.act_scale = S.act_scale; P.act_bias = S.act_bias; P.mx = S.mx; P.iSx = S.iSx; P.my = S.my; P.Sy = S.Sy;
+        P.KR = S.KR; P.rew_C = S.rew_C; P.rew_c0 = S.rew_c0; P.rew_Q = S.rew_Q; P.rew_R = S.rew_R;
+        P.rew_scale = S.rew_scale; P.rew_offset = S.rew_offset;
+        if (cluster_carve(P, pass == 1) > SMEM_LIMIT_FLOATS) {
+            if (mode == 3) return fail(PMB_E_UNSUPPORTED, "cluster-resident plan does not fit in shared memory");
+            return PMB_OK;
+        }
+    }
+    // particles per cluster: spread the particles over every cluster the device can hold at once
+    int PG = (tune && mode == 3) ? tune->reserved[1] & 15 : 0;
+    if (PG < 0 || PG > CL_PS) return fail(PMB_E_INVALID, "particles per cluster must be 1..%d", CL_PS);
+    if (PG == 0) {
+        static int cached[2] = {-1, -1};
+        int &mc = cached[C == 8];
+        if (mc < 0) mc = cluster_max_active(C, max(pl.cfwd.smem_floats, pl.cbwd.smem_floats) * 4, true);
+        const int maxc = mc > 0 ? mc : (C == 8 ? 16 : 32);
+        PG = (p->N + maxc - 1) / maxc;
+        if (PG > CL_PS) PG = CL_PS;
+        if (PG < 1) PG = 1;
+    }
+    pl.cfwd.PG = pl.cbwd.PG = PG;
+    pl.cl_nclusters = (p->N + PG - 1) / PG;
+    pl.cluster = C;
+    return PMB_OK;
+}
+
 static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     if (!p) return fail(PMB_E_INVALID, "problem is NULL");
     if (p->N < 1 || p->H < 1 || p->D < 1 || p->U < 1) return fail(PMB_E_INVALID, "N, H, D, U must be >= 1");
@@ -307,7 +443,8 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     pl.P = P;
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
-    if (pl.stream_mode != 1 && pl.stream_mode != 2) return fail(PMB_E_INVALID, "stream_mode must be 1 or 2");
+    if (pl.stream_mode < 1 || pl.stream_mode > 3) return fail(PMB_E_INVALID, "stream_mode must be 0..3");
+    if (pl.stream_mode == 3) pl.stream_mode = 2;
     pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : 64;
     if (pl.nsplit < 1 || pl.nsplit > 1024) return fail(PMB_E_INVALID, "wgrad_splits outside [1,1024]");
 
@@ -363,6 +500,8 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     const NetSweep *fo[2] = {&F.pol, &F.dyn};
     const NetSweep *bo[2] = {&B.dyn, &B.pol};
+    if ((rc = plan_cluster(p, tune, pl)) != PMB_OK) return rc;
+    if (pl.cluster) return PMB_OK;
     const int nst = tune ? tune->reserved[1] : 0;
     if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode, nst, p->mm_states != 0)) < 0) return rc;
     pl.smem_fwd_bytes = rc;
@@ -382,6 +521,9 @@ static void resolve(Plan &pl, float *ws) {
     pl.fwd.ws = pl.bwd.ws = ws;
     pl.fwd.wpack = ws + pl.wpack_fwd_off;
     pl.bwd.wpack = ws + pl.wpack_bwd_off;
+    pl.cfwd.ws = pl.cbwd.ws = ws;
+    pl.cfwd.wpack = ws + pl.wpack_fwd_off;
+    pl.cbwd.wpack = ws + pl.wpack_bwd_off;
     if (pl.fwd.mm_states || pl.fwd.mm_rewards) {
         for (int pass = 0; pass < 2; ++pass) {
             SweepParams &S = pass ? pl.bwd : pl.fwd;
@@ -451,7 +593,13 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     F.rewards = p->mm_rewards ? wsf + pl.rpre_off : rewards;
     if (p->mm_states) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
     F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
-    if (phases & 2) PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
+    if (pl.cluster) {
+        ClusterParams &CF = pl.cfwd;
+        CF.x0 = x0; CF.states = states; CF.actions = actions; CF.rewards = F.rewards; CF.dbg = F.dbg;
+        if (phases & 2) PMB_CUDA(launch_cluster_fwd(CF, pl.cl_nclusters, st));
+    } else if (phases & 2) {
+        PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
+    }
     if (p->mm_rewards)
         PMB_CUDA(launch_reward_mm_fwd(wsf + pl.rpre_off, rewards, p->z_rr, wsf + pl.rstat_off, p->N, p->H, pl.mm_G,
                                       status_dev, st));
@@ -488,7 +636,14 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     if (p->mm_states) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
-    if (phases & 2) PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));
+    if (pl.cluster) {
+        ClusterParams &CB = pl.cbwd;
+        CB.states = B.states; CB.actions = B.actions; CB.rewards = B.rewards;
+        CB.g_states = B.g_states; CB.g_actions = B.g_actions; CB.g_rewards = B.g_rewards; CB.dx0 = B.dx0; CB.dbg = B.dbg;
+        if (phases & 2) PMB_CUDA(launch_cluster_bwd(CB, pl.cl_nclusters, st));
+    } else if (phases & 2) {
+        PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));
+    }
     if (!(phases & 4)) return PMB_OK;
     // batched policy weight gradient over the (H*N) axis
     const long long R = (long long)p->H * p->N;

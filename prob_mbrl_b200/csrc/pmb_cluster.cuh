@@ -1,0 +1,408 @@
+// Cluster-resident sweeps (sm_100a): the imagined rollout with ALL weights resident in the shared memory of a
+// thread-block cluster, no per-step weight traffic at all.
+//
+// A cluster of C CTAs owns PG <= 8 particles for the whole horizon.  For the reference's two-hidden-layer
+// nets (Policy / DynamicsModel built by models.mlp, reference models/core.py:39-73) one net pass is
+//   thin   : K <= 16 inputs  -> hidden a (full width)      computed redundantly by every CTA of the cluster
+//   wide   : hidden a (K <= 256) -> hidden b                COLUMN-SPLIT: CTA r owns `hs` columns of hidden b;
+//                                                            its [K][hs] slice of the matrix lives in its smem
+//   narrow : hidden b -> <= 16 outputs                      every CTA forms the partial sums over ITS columns
+//   exchange                                                the partials (PG x outputs floats) go to every CTA of
+//                                                            the cluster with st.async (DSMEM store + mbarrier
+//                                                            complete_tx in one instruction); every CTA adds the C
+//                                                            partials in rank order (deterministic, identical)
+// so the only inter-CTA traffic per net pass is C x PG x outputs floats, and each CTA keeps a full copy of
+// the (tiny) per-particle state.  The reverse sweep has the same shape with the transposed matrices
+// (thin = output-projection adjoint, wide = hidden x hidden adjoint split over the columns of hidden 0,
+// narrow = input-projection adjoint).  Inner products run on the packed FP32 pipe (FFMA2).
+#pragma once
+#include "pmb_internal.cuh"
+
+namespace pmb {
+
+constexpr int CL_NT = 256;     // threads per CTA (8 warps, all compute)
+constexpr int CL_PS = 8;       // particle slots of a cluster tile
+constexpr int CL_HS = 32;      // widest column slice per CTA
+constexpr int CL_TW = 256;     // widest thin layer (= K of the wide layer)
+constexpr int CL_NO = 16;      // narrow outputs / thin inputs (max)
+constexpr int CL_INBOX = CL_PS * CL_NO;   // floats one CTA sends per exchange (max)
+
+// One net in one direction.
+struct CNet {
+    int tK, tW;               // thin layer: rows (inputs), padded width (= K of the wide layer)
+    int tsl;                  // columns of the thin output this CTA stores to global (multiple of 4)
+    int wN;                   // padded full width of the wide layer's output
+    int hs;                   // columns of the wide layer per CTA (multiple of 4, <= CL_HS)
+    int nN, nNp;              // narrow layer: outputs, padded to a multiple of 4
+    long long t_goff, w_goff, n_goff;        // packed matrices (float offsets inside this sweep's packed area)
+    long long tb_off, wb_off, nb_off;        // padded biases in the workspace, -1 = none (forward only)
+    long long tm_off, wm_off;                // dropout masks [N][tW] / [N][wN] in the workspace, -1 = none
+    float tkeep_inv, wkeep_inv;              // 1/keep of the thin-output / wide-output hidden layer
+    long long tsav_off, wsav_off;            // stored activations [H][N][tW] / [H][N][wN]
+    long long tdel_off, wdel_off, odel_off;  // backward, policy: adjoints kept for the weight gradient, -1 = none
+    long long raw_off;                       // raw outputs of the net [H][N][nraw]
+    int nraw;
+    int has_density;
+    float lmax;
+    const float *z;
+    long long zstride;
+    int s_tw, s_ww, s_nw, s_tb, s_wb, s_nb, s_tm, s_wm;   // shared-memory offsets (floats)
+    int s_nwt;                // narrow matrix of this CTA's columns as [4][CL_HS][4]: (o >> 2, column, o & 3)
+};
+
+struct ClusterParams {
+    int N, H, D, U;
+    int PG;                     // particles per cluster
+    int C;                      // CTAs per cluster
+    CNet pol, dyn;
+    const float *wpack;         // packed weights of THIS sweep
+    float *ws;                  // workspace base
+    const float *act_scale, *act_bias, *mx, *iSx, *my, *Sy;
+    int KR;
+    const float *rew_C, *rew_c0, *rew_Q, *rew_R;
+    float rew_scale, rew_offset;
+    const float *x0;
+    float *states, *actions, *rewards;
+    const float *g_states, *g_actions, *g_rewards;
+    float *dx0;
+    long long *dbg;             // clock64() marks of cluster 0 / rank 0 / thread 0 at step H/2 (nullable)
+    int off_cst, off_xa, off_xb, off_act, off_red, off_h2s, off_part, off_inbox, off_misc;
+    int smem_floats;
+};
+
+// ----------------------------------------------------------------------------------------
+// cluster PTX helpers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cl_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// 16-byte store into a peer CTA's shared memory that also signals 16 bytes on the peer's mbarrier
+__device__ __forceinline__ void cl_st_async_v4(uint32_t daddr, float4 v, uint32_t dbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(daddr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(dbar)
+                 : "memory");
+}
+__device__ __forceinline__ float2 cl_fma2(float a, float2 w, float2 c) {
+    return __ffma2_rn(make_float2(a, a), w, c);
+}
+
+#define CL_MARK(i) do { if (dbg_on) prm.dbg[(i)] = clock64(); } while (0)
+// per-warp arrival marks (lane 0 of every warp), placed BEFORE barriers: dbg[i * 8 + warp]
+#define CL_TMARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0) prm.dbg[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+
+// ----------------------------------------------------------------------------------------
+// resident operands of one net: thin matrix, this CTA's column slice of the wide and narrow matrices,
+// biases (forward), the cluster's rows of the dropout masks (1.0 where the layer has no mask)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet &n, float *smem, int rank, int n0,
+                                            bool fwd) {
+    const int tid = threadIdx.x;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(prm.wpack + n.t_goff);
+        float4 *dst = reinterpret_cast<float4 *>(smem + n.s_tw);
+        for (int i = tid; i < (n.tK * n.tW) / 4; i += CL_NT) dst[i] = __ldg(src + i);
+    }
+    const int hs4 = n.hs >> 2;
+    for (int i = tid; i < n.tW * hs4; i += CL_NT) {
+        const int k = i / hs4, c4 = i - k * hs4;
+        const int gc = rank * n.hs + 4 * c4;
+        float4 v = z4;
+        if (gc < n.wN) v = __ldg(reinterpret_cast<const float4 *>(prm.wpack + n.w_goff + (long long)k * n.wN + gc));
+        *reinterpret_cast<float4 *>(smem + n.s_ww + k * n.hs + 4 * c4) = v;
+    }
+    for (int i = tid; i < n.nN * hs4; i += CL_NT) {
+        const int o = i / hs4, c4 = i - o * hs4;
+        const int gc = rank * n.hs + 4 * c4;
+        float4 v = z4;
+        if (gc < n.wN) v = __ldg(reinterpret_cast<const float4 *>(prm.wpack + n.n_goff + (long long)o * n.wN + gc));
+        *reinterpret_cast<float4 *>(smem + n.s_nw + o * n.hs + 4 * c4) = v;
+    }
+    for (int i = tid; i < CL_NO * CL_HS; i += CL_NT) {
+        const int o = i / CL_HS, c = i - o * CL_HS;
+        const int gc = rank * n.hs + c;
+        float v = 0.f;
+        if (o < n.nN && c < n.hs && gc < n.wN) v = __ldg(prm.wpack + n.n_goff + (long long)o * n.wN + gc);
+        smem[n.s_nwt + (o >> 2) * (CL_HS * 4) + c * 4 + (o & 3)] = v;
+    }
+    if (fwd) {
+        for (int j = tid; j < n.tW; j += CL_NT) smem[n.s_tb + j] = n.tb_off >= 0 ? __ldg(prm.ws + n.tb_off + j) : 0.f;
+        for (int c = tid; c < n.hs; c += CL_NT) {
+            const int gc = rank * n.hs + c;
+            smem[n.s_wb + c] = (n.wb_off >= 0 && gc < n.wN) ? __ldg(prm.ws + n.wb_off + gc) : 0.f;
+        }
+        for (int o = tid; o < CL_NO; o += CL_NT) smem[n.s_nb + o] = (n.nb_off >= 0 && o < n.nN) ? __ldg(prm.ws + n.nb_off + o) : 0.f;
+    }
+    for (int i = tid; i < CL_PS * n.tW; i += CL_NT) {
+        const int p = i / n.tW, j = i - p * n.tW;
+        const int nn = min(n0 + p, prm.N - 1);
+        smem[n.s_tm + i] = n.tm_off >= 0 ? __ldg(prm.ws + n.tm_off + (long long)nn * n.tW + j) : 1.f;
+    }
+    for (int i = tid; i < CL_PS * n.hs; i += CL_NT) {
+        const int p = i / n.hs, c = i - p * n.hs;
+        const int nn = min(n0 + p, prm.N - 1);
+        const int gc = rank * n.hs + c;
+        float v = 0.f;
+        if (gc < n.wN) v = n.wm_off >= 0 ? __ldg(prm.ws + n.wm_off + (long long)nn * n.wN + gc) : 1.f;
+        smem[n.s_wm + i] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// thin layer: thread = output column j, all 8 particle slots; x is the [tK][8] input tile.
+// acc[h] holds the particle pairs (2h, 2h+1).  epi(j, acc) finishes column j.
+// ----------------------------------------------------------------------------------------
+template <typename Epi>
+__device__ __forceinline__ void cl_thin(const float *__restrict__ tw, int tK, int tW, const float *__restrict__ x, Epi epi) {
+#pragma unroll 1
+    for (int j = threadIdx.x; j < tW; j += CL_NT) {
+        float2 acc[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < tK; ++k) {
+            const float w = tw[k * tW + j];
+            const float4 x0 = *reinterpret_cast<const float4 *>(x + k * CL_PS);
+            const float4 x1 = *reinterpret_cast<const float4 *>(x + k * CL_PS + 4);
+            acc[0] = cl_fma2(w, make_float2(x0.x, x0.y), acc[0]);
+            acc[1] = cl_fma2(w, make_float2(x0.z, x0.w), acc[1]);
+            acc[2] = cl_fma2(w, make_float2(x1.x, x1.y), acc[2]);
+            acc[3] = cl_fma2(w, make_float2(x1.z, x1.w), acc[3]);
+        }
+        epi(j, acc);
+    }
+}
+// the thin output is the wide layer's input tile act[k][8]; the two 4-particle halves of a row are swapped
+// on rows with bit 2 set so that a warp's 16-byte stores of consecutive rows hit distinct banks
+__device__ __forceinline__ void cl_store_act(float *act, int j, const float (&v)[CL_PS]) {
+    const int sw = (j >> 2) & 1;
+    *reinterpret_cast<float4 *>(act + j * CL_PS + (sw << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(act + j * CL_PS + ((sw ^ 1) << 2)) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ----------------------------------------------------------------------------------------
+// wide layer, this CTA's column slice: warp w takes the rows k = w, w+8, ... (8-way k-split); lane = (column
+// quad q, particle pair pp).  Per row one LDS.128 of weights + one LDS.64 of activations feed 4 FFMA2.
+// The partial sums go to red[w][p][32]; cl_wide_reduce (after a barrier) returns the finished value of
+// (particle = warp, column = lane).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void cl_wide_accum(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
+                                              float *__restrict__ red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane >> 2, pp = lane & 3;
+    if (4 * q >= hs) return;
+    float2 a00 = make_float2(0.f, 0.f), a01 = a00, a10 = a00, a11 = a00;
+    const int sw = (warp >> 2) & 1;           // swizzle bit of every row this warp visits
+    const float *wp = ww + warp * hs + 4 * q;
+    const float *ap = act + warp * CL_PS + ((((pp >> 1) ^ sw)) << 2) + ((pp & 1) << 1);
+    const int n = (K - warp + 7) >> 3;
+    const int wstride = 8 * hs;
+#pragma unroll 5
+    for (int i = 0; i < n; ++i) {
+        const float4 w = *reinterpret_cast<const float4 *>(wp);
+        const float2 a = *reinterpret_cast<const float2 *>(ap);
+        wp += wstride;
+        ap += 8 * CL_PS;
+        a00 = cl_fma2(a.x, make_float2(w.x, w.y), a00);
+        a01 = cl_fma2(a.x, make_float2(w.z, w.w), a01);
+        a10 = cl_fma2(a.y, make_float2(w.x, w.y), a10);
+        a11 = cl_fma2(a.y, make_float2(w.z, w.w), a11);
+    }
+    float *r = red + ((warp * CL_PS + 2 * pp) << 5) + 4 * q;
+    *reinterpret_cast<float4 *>(r) = make_float4(a00.x, a00.y, a01.x, a01.y);
+    *reinterpret_cast<float4 *>(r + 32) = make_float4(a10.x, a10.y, a11.x, a11.y);
+}
+__device__ __forceinline__ float cl_wide_reduce(const float *__restrict__ red) {
+    const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+    const float *r = red + (p << 5) + lane;
+    float s0 = r[0], s1 = r[1 * CL_PS * 32], s2 = r[2 * CL_PS * 32], s3 = r[3 * CL_PS * 32];
+    s0 += r[4 * CL_PS * 32];
+    s1 += r[5 * CL_PS * 32];
+    s2 += r[6 * CL_PS * 32];
+    s3 += r[7 * CL_PS * 32];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// narrow layer over this CTA's columns: thread (p = tid >> 4, o = tid & 15) forms
+// part[p * nNp + o] = sum_c h2s[p][c] * nw[o][c]   (c < hs)
+__device__ __forceinline__ void cl_narrow_partial(const float *__restrict__ nw, int hs, int nN, int nNp,
+                                                  const float *__restrict__ h2s, float *__restrict__ part) {
+    const int tid = threadIdx.x;
+    if (tid >= CL_PS * CL_NO) return;
+    const int p = tid >> 4, o = tid & 15;
+    if (o >= nNp) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (o < nN) {
+        const float *hp = h2s + (p << 5);
+        const float *wp = nw + o * hs;
+        for (int c = 0; c < hs; c += 4) {
+            const float4 h = *reinterpret_cast<const float4 *>(hp + c);
+            const float4 w = *reinterpret_cast<const float4 *>(wp + c);
+            s0 = fmaf(h.x, w.x, s0);
+            s1 = fmaf(h.y, w.y, s1);
+            s2 = fmaf(h.z, w.z, s2);
+            s3 = fmaf(h.w, w.w, s3);
+        }
+    }
+    part[p * nNp + o] = (s0 + s1) + (s2 + s3);
+}
+
+// send this CTA's partials to every CTA of the cluster (its own included): warp w serves the destination
+// ranks w, w+8, ...; 16 bytes per st.async, inbox slot = sender's rank.
+template <int C>
+__device__ __forceinline__ void cl_send(const float *part, int nchunks, uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int dst = warp; dst < C; dst += CL_NT / 32) {
+        const uint32_t dbar = cl_mapa(bar_saddr, dst);
+        const uint32_t dbase = cl_mapa(inbox_saddr + (uint32_t)(rank * CL_INBOX) * 4u, dst);
+        for (int ch = lane; ch < nchunks; ch += 32)
+            cl_st_async_v4(dbase + (uint32_t)ch * 16u, *reinterpret_cast<const float4 *>(part + 4 * ch), dbar);
+    }
+}
+// sum of the C partials of value `idx` in rank order
+template <int C>
+__device__ __forceinline__ float cl_gather(const float *inbox, int idx) {
+    float s = inbox[idx];
+#pragma unroll
+    for (int r = 1; r < C; ++r) s += inbox[r * CL_INBOX + idx];
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------
+// v2 building blocks
+// ----------------------------------------------------------------------------------------
+// wide layer with two independent accumulator sets per thread (rows i and i+1 of the warp's k-slice)
+__device__ __forceinline__ void cl_wide_accum2(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
+                                               float *__restrict__ red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane >> 2, pp = lane & 3;
+    if (4 * q >= hs) return;
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 a00 = z2, a01 = z2, a10 = z2, a11 = z2, b00 = z2, b01 = z2, b10 = z2, b11 = z2;
+    const int sw = (warp >> 2) & 1;           // swizzle bit of every row this warp visits
+    const float *wp = ww + warp * hs + 4 * q;
+    const float *ap = act + warp * CL_PS + ((((pp >> 1) ^ sw)) << 2) + ((pp & 1) << 1);
+    const int n = (K - warp + 7) >> 3;
+    const int wstride = 8 * hs;
+    int i = 0;
+#pragma unroll 3
+    for (; i + 2 <= n; i += 2) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(wp);
+        const float2 x0 = *reinterpret_cast<const float2 *>(ap);
+        const float4 w1 = *reinterpret_cast<const float4 *>(wp + wstride);
+        const float2 x1 = *reinterpret_cast<const float2 *>(ap + 8 * CL_PS);
+        wp += 2 * wstride;
+        ap += 16 * CL_PS;
+        a00 = cl_fma2(x0.x, make_float2(w0.x, w0.y), a00);
+        a01 = cl_fma2(x0.x, make_float2(w0.z, w0.w), a01);
+        a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
+        a11 = cl_fma2(x0.y, make_float2(w0.z, w0.w), a11);
+        b00 = cl_fma2(x1.x, make_float2(w1.x, w1.y), b00);
+        b01 = cl_fma2(x1.x, make_float2(w1.z, w1.w), b01);
+        b10 = cl_fma2(x1.y, make_float2(w1.x, w1.y), b10);
+        b11 = cl_fma2(x1.y, make_float2(w1.z, w1.w), b11);
+    }
+    if (i < n) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(wp);
+        const float2 x0 = *reinterpret_cast<const float2 *>(ap);
+        a00 = cl_fma2(x0.x, make_float2(w0.x, w0.y), a00);
+        a01 = cl_fma2(x0.x, make_float2(w0.z, w0.w), a01);
+        a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
+        a11 = cl_fma2(x0.y, make_float2(w0.z, w0.w), a11);
+    }
+    float *r = red + ((warp * CL_PS + 2 * pp) << 5) + 4 * q;
+    *reinterpret_cast<float4 *>(r) = make_float4(a00.x + b00.x, a00.y + b00.y, a01.x + b01.x, a01.y + b01.y);
+    *reinterpret_cast<float4 *>(r + 32) = make_float4(a10.x + b10.x, a10.y + b10.y, a11.x + b11.x, a11.y + b11.y);
+}
+
+// 16-byte / 4-byte remote stores used by the exchange
+__device__ __forceinline__ void cl_st_async_b32(uint32_t daddr, float v, uint32_t dbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(daddr),
+                 "r"(__float_as_uint(v)), "r"(dbar)
+                 : "memory");
+}
+
+// Narrow layer + exchange fused into the wide layer's epilogue.  Warp = particle slot p, lane = column of this
+// CTA's slice; `v` is the lane's finished hidden value (0 on idle lanes).  The warp forms
+//   out[o] = sum_lanes v * nw[o][lane]   for o < NV
+// with a reduce-scatter butterfly (NV values per lane -> 1), four neighbouring holders are gathered into one
+// lane and that lane sends the 16-byte chunk (p, 4 outputs) to every CTA of the cluster.  NV = 4, 8 or 16.
+template <int C, int NV>
+__device__ __forceinline__ void cl_narrow_send(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
+                                               uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
+    const int lane = threadIdx.x & 31;
+    float pr[NV];
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+        const float4 w = *reinterpret_cast<const float4 *>(nwt + i * (CL_HS * 4) + lane * 4);
+        pr[4 * i] = v * w.x;
+        pr[4 * i + 1] = v * w.y;
+        pr[4 * i + 2] = v * w.z;
+        pr[4 * i + 3] = v * w.w;
+    }
+    int m = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? pr[n / 2 + i] : pr[i];
+            const float give = up ? pr[i] : pr[n / 2 + i];
+            pr[i] = keep + __shfl_xor_sync(0xffffffffu, give, m);
+        }
+    }
+#pragma unroll
+    for (; m >= 1; m >>= 1) pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], m);
+    // output o = lane / s sits in every lane of its group of s = 32 / NV lanes
+    constexpr int s = 32 / NV;
+    const float q1 = __shfl_sync(0xffffffffu, pr[0], (lane + s) & 31);
+    const float q2 = __shfl_sync(0xffffffffu, pr[0], (lane + 2 * s) & 31);
+    const float q3 = __shfl_sync(0xffffffffu, pr[0], (lane + 3 * s) & 31);
+    if (send_ok && (lane & (4 * s - 1)) == 0) {
+        const int chunk = lane / (4 * s);
+        if (4 * chunk < nN) {
+            const float4 out = make_float4(pr[0], q1, q2, q3);
+            const uint32_t off = (uint32_t)(rank * CL_INBOX + p * CL_NO + 4 * chunk) * 4u;
+#pragma unroll
+            for (int dst = 0; dst < C; ++dst) cl_st_async_v4(cl_mapa(inbox_saddr + off, dst), out, cl_mapa(bar_saddr, dst));
+        }
+    }
+}
+template <int C>
+__device__ __forceinline__ void cl_narrow_send_any(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
+                                                   uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
+    if (nN <= 4) cl_narrow_send<C, 4>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
+    else if (nN <= 8) cl_narrow_send<C, 8>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
+    else cl_narrow_send<C, 16>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
+}
+// value (p, o) from the inbox written by cl_narrow_send: C partials added in rank order
+template <int C>
+__device__ __forceinline__ float cl_gather2(const float *inbox, int p, int o) {
+    const float *q = inbox + p * CL_NO + o;
+    float s = q[0];
+#pragma unroll
+    for (int r = 1; r < C; ++r) s += q[r * CL_INBOX];
+    return s;
+}
+
+cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
+cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
+int cluster_max_active(int C, int smem_bytes, bool fwd);
+
+}  // namespace pmb

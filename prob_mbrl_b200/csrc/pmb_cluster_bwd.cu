@@ -1,0 +1,367 @@
+// Reverse sweep, cluster-resident variant (see pmb_cluster.cuh): back-propagation through time without
+// recompute for PG particles per cluster of C CTAs, all (transposed) weights resident in the cluster's shared
+// memory.  Consumes what either forward variant stored, walks t = H-1 .. 0 and produces dL/dx0 plus the
+// per-layer output adjoints of the POLICY net for every (t, particle), which pmb_wgrad.cu contracts over the
+// (H*N) axis afterwards.  Replaces loss.backward() through utils.rollout (reference
+// algorithms/mc_pilco.py:197); the adjoint formulas are those of oracle/rollout_oracle.py::manual_backward.
+//
+// Everything that depends only on forward values (reward adjoint, density / tanh derivative factors, direct
+// cotangents, the ReLU/dropout gates) is fetched ONE STEP AHEAD into registers and turned into a
+// double-buffered "pre" block in shared memory, so the serial chain never waits on global memory.
+#include "pmb_cluster.cuh"
+#include "pmb_host.h"
+
+namespace pmb {
+
+// float offsets inside the per-particle scratch block (`misc`), in units of one [8][SD] block
+constexpr int CM_GS = 0, CM_GSP = 1, CM_STG_S1 = 2, CM_STG_A = 3, CM_PRE = 4;
+constexpr int CPRE_RS = 0, CPRE_RA = 1, CPRE_FD = 2, CPRE_TP = 3, CPRE_FP = 4, CPRE_GS0 = 5, CPRE_N = 6;
+constexpr int CBL = CL_PS * SD;
+
+// Adjoint pass through one net up to and including the send of the input-adjoint partials.
+//   x     : [tK][8] adjoint of the net's raw outputs
+//   gt    : gate bits of the thin output (bit p: stored activation of hidden 1, particle slot p, column tid)
+//   gw    : stored activation of hidden 0 for (particle slot = warp, column = rank*hs + lane)
+template <int C, bool kStore>
+__device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const CNet &n, float *smem, const float *x,
+                                                unsigned gt, float gw, int t, int n0, int nval, int rank,
+                                                uint32_t inbox_saddr, uint32_t bar_saddr, bool dbg_on, int mark0) {
+    float *act = smem + prm.off_act, *red = smem + prm.off_red, *h2s = smem + prm.off_h2s, *part = smem + prm.off_part;
+    const int N = prm.N;
+    // ---- thin: adjoint of hidden 1 = (dout W2) gated by the stored activation, * mask1 / keep1 ----
+    {
+        const float *tm = smem + n.s_tm;
+        const int tW = n.tW;
+        const float kinv = n.tkeep_inv;
+        const int j0 = rank * n.tsl, j1 = j0 + n.tsl;
+        float *dl = kStore ? prm.ws + n.tdel_off + ((size_t)t * N + n0) * tW : nullptr;
+        cl_thin(smem + n.s_tw, n.tK, tW, x, [&](int j, float2 (&acc)[4]) {
+            float v[CL_PS];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                v[2 * h] = acc[h].x;
+                v[2 * h + 1] = acc[h].y;
+            }
+            // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
+#pragma unroll
+            for (int p = 0; p < CL_PS; ++p) v[p] = ((gt >> p) & 1u) ? v[p] * kinv * tm[p * tW + j] : 0.f;
+            cl_store_act(act, j, v);
+            if (kStore && j >= j0 && j < j1) {
+#pragma unroll
+                for (int p = 0; p < CL_PS; ++p)
+                    if (p < nval) dl[(size_t)p * tW + j] = v[p];
+            }
+        });
+    }
+    __syncthreads();
+    CL_MARK(mark0);
+    // ---- wide: this CTA's columns of the adjoint of hidden 0 ----
+    cl_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red);
+    __syncthreads();
+    CL_MARK(mark0 + 1);
+    {
+        const int p = threadIdx.x >> 5, c = threadIdx.x & 31;
+        float v = cl_wide_reduce(red);
+        if (c < n.hs) {
+            v = gw != 0.f ? v * n.wkeep_inv * smem[n.s_wm + p * n.hs + c] : 0.f;
+            const int gc = rank * n.hs + c;
+            if (kStore && p < nval && gc < n.wN) prm.ws[n.wdel_off + ((size_t)t * N + n0 + p) * n.wN + gc] = v;
+        } else {
+            v = 0.f;
+        }
+        h2s[(p << 5) + c] = v;
+    }
+    __syncthreads();
+    // ---- narrow: partial sums of d(input) = delta_0 W_0 over this CTA's columns; exchange ----
+    cl_narrow_partial(smem + n.s_nw, n.hs, n.nN, n.nNp, h2s, part);
+    __syncthreads();
+    CL_MARK(mark0 + 2);
+    cl_send<C>(part, (prm.PG * n.nNp) >> 2, inbox_saddr, bar_saddr, rank);
+}
+
+template <int C>
+__global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_constant__ ClusterParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t xbar[2];          // [0] dynamics exchange, [1] policy exchange
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cl_rank();
+    const int PG = prm.PG;
+    const int n0 = (int)cl_id_x() * PG;
+    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, KR = prm.KR;
+    const int nval = min(PG, N - n0);
+    const CNet &pol = prm.pol;
+    const CNet &dyn = prm.dyn;
+
+    for (int i = tid; i < prm.smem_floats; i += CL_NT) smem[i] = 0.f;
+    __syncthreads();
+    float *cst = smem + prm.off_cst;
+    float *xd = smem + prm.off_xa;         // [2D][8]  adjoint of the dynamics net's raw outputs
+    float *xp = smem + prm.off_xb;         // [2U][8]  adjoint of the policy net's raw outputs
+    float *misc = smem + prm.off_misc;
+    float *gs = misc + CM_GS * CBL, *gsp = misc + CM_GSP * CBL;
+    float *stg_s1 = misc + CM_STG_S1 * CBL, *stg_a = misc + CM_STG_A * CBL;
+    float *pre0 = misc + CM_PRE * CBL;                 // two buffers of CPRE_N blocks
+    float *stg_w = pre0 + 2 * CPRE_N * CBL;            // [8]
+    const float *inbox_dyn = smem + prm.off_inbox;
+    const float *inbox_pol = inbox_dyn + C * CL_INBOX;
+    const uint32_t bytes_dyn = (uint32_t)(C * PG * dyn.nNp) * 4u, bytes_pol = (uint32_t)(C * PG * pol.nNp) * 4u;
+    if (tid == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&xbar[0], bytes_dyn);
+        mbar_expect_tx(&xbar[1], bytes_pol);
+    }
+    load_constants(prm, cst);
+    cl_load_net(prm, dyn, smem, rank, n0, false);
+    cl_load_net(prm, pol, smem, rank, n0, false);
+
+    // ---- thread roles (fixed for the whole horizon) ----
+    const bool roleA = tid < CL_PS * U;                       // (particle slot, action dim)
+    const int a_p = roleA ? tid / U : 0, a_u = roleA ? tid - a_p * U : 0;
+    const int a_n = min(n0 + a_p, N - 1);
+    const bool roleB = tid >= 128 && tid - 128 < CL_PS * D;   // (particle slot, state dim)
+    const int b_p = roleB ? (tid - 128) / D : 0, b_d = roleB ? (tid - 128) - b_p * D : 0;
+    const int b_n = min(n0 + b_p, N - 1);
+    const bool roleX = tid < CL_PS * (D + U);                 // (particle slot, dynamics-input dim)
+    const int x_p = roleX ? tid / (D + U) : 0, x_k = roleX ? tid - x_p * (D + U) : 0;
+    const bool x_own = roleX && x_p < nval && (x_p % C) == rank;
+    const bool roleR = tid >= 224 && tid - 224 < CL_PS;       // particle slot (reward weight)
+    const int r_p = roleR ? tid - 224 : 0;
+    const int r_n = min(n0 + r_p, N - 1);
+    // gates: thin epilogue thread = column tid of hidden 1; wide epilogue thread = (slot warp, column lane) of hidden 0
+    const bool gt_dyn_on = tid < dyn.tW, gt_pol_on = tid < pol.tW;
+    const int gw_n = min(n0 + warp, N - 1);
+    const int gwc_dyn = rank * dyn.hs + lane, gwc_pol = rank * pol.hs + lane;
+    const bool gw_dyn_on = lane < dyn.hs && gwc_dyn < dyn.wN, gw_pol_on = lane < pol.hs && gwc_pol < pol.wN;
+
+    if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
+
+    // prefetch registers of the one-step-ahead precompute
+    float pf_s1 = 0.f, pf_ls = 0.f, pf_zd = 0.f, pf_gs = 0.f;                 // role B
+    float pf_a = 0.f, pf_mu = 0.f, pf_lsp = 0.f, pf_zp = 0.f, pf_ga = 0.f;    // role A
+    float pf_r = 0.f, pf_gr = 0.f;                                            // role R
+    float pg_td[CL_PS], pg_tp[CL_PS];                                         // raw gate values of the next step
+    float pg_wd = 0.f, pg_wp = 0.f;
+#pragma unroll
+    for (int p = 0; p < CL_PS; ++p) pg_td[p] = pg_tp[p] = 0.f;
+    auto prefetch = [&](int tt) {
+        if (roleB) {
+            pf_s1 = __ldg(prm.states + ((size_t)(tt + 1) * N + b_n) * D + b_d);
+            if (dyn.has_density) {
+                pf_ls = __ldg(prm.ws + dyn.raw_off + ((size_t)tt * N + b_n) * dyn.nraw + D + b_d);
+                pf_zd = __ldg(dyn.z + (size_t)tt * dyn.zstride + (size_t)b_n * D + b_d);
+            }
+            pf_gs = prm.g_states ? __ldg(prm.g_states + ((size_t)tt * N + b_n) * D + b_d) : 0.f;
+        }
+        if (roleA) {
+            const float *op = prm.ws + pol.raw_off + ((size_t)tt * N + a_n) * pol.nraw;
+            pf_a = __ldg(prm.actions + ((size_t)tt * N + a_n) * U + a_u);
+            pf_mu = __ldg(op + a_u);
+            if (pol.has_density) {
+                pf_lsp = __ldg(op + U + a_u);
+                pf_zp = __ldg(pol.z + (size_t)tt * pol.zstride + (size_t)a_n * U + a_u);
+            }
+            pf_ga = prm.g_actions ? __ldg(prm.g_actions + ((size_t)tt * N + a_n) * U + a_u) : 0.f;
+        }
+        if (roleR) {
+            pf_r = __ldg(prm.rewards + (size_t)tt * N + r_n);
+            pf_gr = prm.g_rewards ? __ldg(prm.g_rewards + (size_t)tt * N + r_n) : 0.f;
+        }
+        // stored activations that gate the adjoints (plain loads: written by the forward kernel, read-only here)
+#pragma unroll
+        for (int p = 0; p < CL_PS; ++p) {
+            const size_t row = (size_t)tt * N + min(n0 + p, N - 1);
+            if (gt_dyn_on) pg_td[p] = __ldg(prm.ws + dyn.tsav_off + row * dyn.tW + tid);
+            if (gt_pol_on) pg_tp[p] = __ldg(prm.ws + pol.tsav_off + row * pol.tW + tid);
+        }
+        if (gw_dyn_on) pg_wd = __ldg(prm.ws + dyn.wsav_off + ((size_t)tt * N + gw_n) * dyn.wN + gwc_dyn);
+        if (gw_pol_on) pg_wp = __ldg(prm.ws + pol.wsav_off + ((size_t)tt * N + gw_n) * pol.wN + gwc_pol);
+    };
+    unsigned gt_dyn = 0u, gt_pol = 0u;
+    float gw_dyn = 0.f, gw_pol = 0.f;
+    auto latch_gates = [&]() {
+        gt_dyn = gt_pol = 0u;
+#pragma unroll
+        for (int p = 0; p < CL_PS; ++p) {
+            gt_dyn |= (pg_td[p] != 0.f ? 1u : 0u) << p;
+            gt_pol |= (pg_tp[p] != 0.f ? 1u : 0u) << p;
+        }
+        gw_dyn = pg_wd;
+        gw_pol = pg_wp;
+    };
+    // first half of the precompute: factors that need no cross-thread data (+ staging of s', a, w)
+    auto precompute_a = [&](float *pre) {
+        if (roleB) {
+            stg_s1[b_p * SD + b_d] = pf_s1;
+            float fd = 0.f;
+            if (dyn.has_density) {
+                const float lst = clamp_logstd(pf_ls, dyn.lmax) + cst[C_LSY + b_d];
+                fd = pf_zd * expf(lst) * sigmoid_f(dyn.lmax - pf_ls);     // d s' / d log_std (raw)
+            }
+            pre[CPRE_FD * CBL + b_p * SD + b_d] = fd;
+            pre[CPRE_GS0 * CBL + b_p * SD + b_d] = pf_gs;
+        }
+        if (roleA) {
+            stg_a[a_p * SD + a_u] = pf_a;
+            const float sc = cst[C_SCALE + a_u];
+            float tp, fp = 0.f;
+            if (pol.has_density) {
+                const float el = expf(clamp_logstd(pf_lsp, pol.lmax));
+                const float th = tanhf(pf_mu + pf_zp * el);
+                tp = sc * (1.f - th * th);                                  // d a / d u
+                fp = pf_zp * el * sigmoid_f(pol.lmax - pf_lsp);             // d u / d log_std (raw)
+            } else {
+                const float th = tanhf(pf_mu);
+                tp = sc * (1.f - th * th);
+            }
+            pre[CPRE_TP * CBL + a_p * SD + a_u] = tp;
+            pre[CPRE_FP * CBL + a_p * SD + a_u] = fp;
+        }
+        if (roleR) stg_w[r_p] = -0.5f * pf_gr * (pf_r - prm.rew_offset);   // g_r * d r / d cost, r - off = scale*exp(-cost)
+    };
+    // second half: reward adjoint on (s', a):  w * C^T (Q+Q^T) delta  and  g_a + w * (R+R^T) a
+    auto precompute_b = [&](float *pre) {
+        if (roleB) {
+            float dl[PMB_MAX_REWARD_ROWS];
+            for (int i = 0; i < KR; ++i) {
+                float s = cst[C_C0 + i];
+                for (int d = 0; d < D; ++d) s = fmaf(cst[C_C + i * SD + d], stg_s1[b_p * SD + d], s);
+                dl[i] = s;
+            }
+            float acc = 0.f;
+            for (int i = 0; i < KR; ++i) {
+                float qd = 0.f;
+                for (int j = 0; j < KR; ++j) qd = fmaf(cst[C_QS + i * 4 + j], dl[j], qd);
+                acc = fmaf(qd, cst[C_C + i * SD + b_d], acc);
+            }
+            pre[CPRE_RS * CBL + b_p * SD + b_d] = stg_w[b_p] * acc;
+        }
+        if (roleA) {
+            float s = 0.f;
+            for (int v = 0; v < U; ++v) s = fmaf(cst[C_RS + a_u * SD + v], stg_a[a_p * SD + v], s);
+            pre[CPRE_RA * CBL + a_p * SD + a_u] = pf_ga + stg_w[a_p] * s;
+        }
+    };
+
+    const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
+    const uint32_t bar_dyn = smem_u32(&xbar[0]), bar_pol = smem_u32(&xbar[1]);
+
+    // ---- prologue: everything step H-1 needs ----
+    int cur = 0;
+    prefetch(H - 1);
+    __syncthreads();            // constants are in place
+    precompute_a(pre0);
+    __syncthreads();
+    precompute_b(pre0);
+    latch_gates();
+    __syncthreads();
+    cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
+
+#pragma unroll 1
+    for (int t = H - 1, it = 0; t >= 0; --t, ++it) {
+        const bool dbg_on = prm.dbg != nullptr && blockIdx.x == 0 && tid == 0 && t == H / 2;
+        const uint32_t par = (uint32_t)(it & 1);
+        CL_MARK(256);
+        const int nxt = cur ^ 1;
+        float *pre = pre0 + cur * CPRE_N * CBL;
+        float *pren = pre0 + nxt * CPRE_N * CBL;
+        // ---- one step ahead: scalars and gates of step t-1 ----
+        if (t > 0) prefetch(t - 1);
+        // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
+        //      s' = s + mu*Sy + my + z*exp(lstd) ----
+        if (roleB) {
+            const float g = gs[b_p * SD + b_d] + pre[CPRE_RS * CBL + b_p * SD + b_d];
+            gsp[b_p * SD + b_d] = g;
+            xd[b_d * CL_PS + b_p] = g * cst[C_SY + b_d];
+            if (dyn.has_density) xd[(D + b_d) * CL_PS + b_p] = g * pre[CPRE_FD * CBL + b_p * SD + b_d];
+        }
+        __syncthreads();
+        CL_MARK(257);
+        // ================= dynamics net =================
+        cl_net_backward<C, false>(prm, dyn, smem, xd, gt_dyn, gw_dyn, t, n0, nval, rank, inbox_saddr, bar_dyn, dbg_on, 258);
+        if (roleX) {
+            // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
+            //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
+            mbar_wait(&xbar[0], par);
+            if (tid == 0) mbar_expect_tx(&xbar[0], bytes_dyn);
+            const float v = cl_gather<C>(inbox_dyn, x_p * dyn.nNp + x_k) * cst[C_ISX + x_k];
+            if (x_k < D) {
+                gsp[x_p * SD + x_k] += v;
+            } else {
+                const int u = x_k - D;
+                const float ga = pre[CPRE_RA * CBL + x_p * SD + u] + v;
+                const float du = ga * pre[CPRE_TP * CBL + x_p * SD + u];
+                xp[u * CL_PS + x_p] = du;
+                float dls = 0.f;
+                if (pol.has_density) {
+                    dls = du * pre[CPRE_FP * CBL + x_p * SD + u];
+                    xp[(U + u) * CL_PS + x_p] = dls;
+                }
+                if (x_own) {
+                    float *dd = prm.ws + pol.odel_off + ((size_t)t * N + n0 + x_p) * pol.nraw;
+                    dd[u] = du;
+                    if (pol.has_density) dd[U + u] = dls;
+                }
+            }
+        }
+        if (t > 0) precompute_a(pren);
+        __syncthreads();
+        CL_MARK(262);
+        // ================= policy net =================
+        cl_net_backward<C, true>(prm, pol, smem, xp, gt_pol, gw_pol, t, n0, nval, rank,
+                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, dbg_on, 263);
+        if (roleB) {
+            // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
+            mbar_wait(&xbar[1], par);
+            if (tid == 128) mbar_expect_tx(&xbar[1], bytes_pol);
+            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather<C>(inbox_pol, b_p * pol.nNp + b_d) +
+                                 pre[CPRE_GS0 * CBL + b_p * SD + b_d];
+        }
+        if (t > 0) {
+            precompute_b(pren);
+            latch_gates();
+        }
+        __syncthreads();
+        CL_MARK(267);
+        cur = nxt;
+    }
+    if (prm.dx0 && roleB && b_p < nval && (b_p % C) == rank) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];
+    cl_sync();          // no CTA leaves while a peer could still address its shared memory
+}
+
+static cudaError_t cluster_launch_cfg_b(const void *fn, int C, int smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (C > 8) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+}
+
+cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream) {
+    const int smem_bytes = prm.smem_floats * 4;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = prm.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(nclusters * prm.C);
+    cfg.blockDim = dim3(CL_NT);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    switch (prm.C) {
+        case 8:
+            if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<8>, 8, smem_bytes)) != cudaSuccess) return e;
+            return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<8>, prm);
+        case 4:
+            if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<4>, 4, smem_bytes)) != cudaSuccess) return e;
+            return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<4>, prm);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace pmb

@@ -554,7 +554,8 @@ __device__ __forceinline__ void load_resident(const SweepParams &prm, float *sme
 }
 
 // constants block: scalers, squashing, reward matrices (+ symmetrised copies for the adjoint)
-__device__ __forceinline__ void load_constants(const SweepParams &prm, float *cst) {
+template <typename PRM>
+__device__ __forceinline__ void load_constants(const PRM &prm, float *cst) {
     const int D = prm.D, U = prm.U, KR = prm.KR;
     for (int i = threadIdx.x; i < C_TOTAL; i += NT) cst[i] = 0.f;
     CTA_SYNC();

@@ -36,3 +36,22 @@ for nm, base in (("pol L1", 2), ("dyn L1", 10)):
     v = [x for x in v if x]
     print("  %-7s" % nm, [v[i + 1] - v[i] for i in range(len(v) - 1)])
 
+
+if os.environ.get("PMB_STREAM_MODE", "0") in ("0", "3"):
+    print("cluster-resident forward sweep: per-warp arrival (cycles after the first warp entered the step), cluster 0 / rank 0")
+    names = {0: "step top", 1: "pol thin done", 2: "pol wide accum done", 3: "pol epilogue+narrow+send done",
+             4: "squash role done", 5: "dyn thin done", 6: "dyn wide accum done", 7: "dyn epilogue+narrow+send done",
+             8: "density role done"}
+    t0 = min(x for x in d[0:8] if x)
+    for k in sorted(names):
+        v = [x - t0 for x in d[8 * k: 8 * k + 8]]
+        print("    %-30s min %6d max %6d  | %s" % (names[k], min(v), max(v), " ".join("%6d" % x for x in v)))
+    print("cluster-resident backward sweep (thread 0 marks, cycles):")
+    names = {256: "top", 257: "density adj", 258: "dyn thin", 259: "dyn wide accum", 260: "dyn reduce+narrow",
+             262: "exchange+scaler/squash", 263: "pol thin", 264: "pol wide accum", 265: "pol reduce+narrow", 267: "exchange+gs"}
+    ks = sorted(names)
+    prev = d[ks[0]]
+    for k in ks:
+        if d[k]:
+            print("    %-24s +%6d  (t=%6d)" % (names[k], d[k] - prev, d[k] - d[ks[0]]))
+            prev = d[k]

@@ -59,11 +59,19 @@ def _run(ops, x0, H, cot="loss", env=None, gen_seed=0, mm=None):
                 os.environ[k] = v
 
 
+# sweep variants behind the same C ABI: "ring" = streaming sweeps (hidden x hidden weights through a TMA ring),
+# "cluster" = cluster-resident sweeps (weights in the shared memory of a thread-block cluster; two hidden layers)
+SWEEPS = {"ring": {"PMB_STREAM_MODE": 2}, "cluster": {"PMB_STREAM_MODE": 3}}
+
+
+@pytest.mark.parametrize("sweeps", ["ring", "cluster"])
 @pytest.mark.parametrize("name", ["cartpole_200x2_n25_h40", "dcartpole_48x3_n24_h30", "cartpole_37x2_n7_h12"])
-def test_rollout_and_gradient_match_reference_golden(name):
+def test_rollout_and_gradient_match_reference_golden(name, sweeps):
+    if sweeps == "cluster" and "x3" in name:
+        pytest.skip("three hidden layers: streaming sweeps only")
     ops, g = gu.load(name)
     H = int(g["H"])
-    r = _run(ops, g["x0"], H)
+    r = _run(ops, g["x0"], H, env=SWEEPS[sweeps])
     assert (r["S"] - g["nomm_states"]).abs().max() < 2e-6
     assert (r["A"] - g["nomm_actions"]).abs().max() < 2e-5
     assert (r["R"] - g["nomm_rewards"]).abs().max() < 2e-6
@@ -72,11 +80,12 @@ def test_rollout_and_gradient_match_reference_golden(name):
     assert gu.rel_l2(r["dx0"], g["nomm_dx0"]) < 1e-5
 
 
-def test_c2_full_size_matches_reference_golden():
+@pytest.mark.parametrize("sweeps", ["ring", "cluster"])
+def test_c2_full_size_matches_reference_golden(sweeps):
     """BASELINE.json configs[1]: Cartpole 2x[200], 100 particles, H=400."""
     ops, g = gu.load("cartpole_200x2_n100_h400")
     H, thin = int(g["H"]), int(g["thin"])
-    r = _run(ops, g["x0"], H)
+    r = _run(ops, g["x0"], H, env=SWEEPS[sweeps])
     assert (r["S"][::thin] - g["nomm_states"]).abs().max() < 5e-5
     assert abs(float(r["obj"]) - float(g["nomm_loss"])) <= 1e-6 * abs(float(g["nomm_loss"]))
     assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-4
@@ -87,12 +96,13 @@ def test_c2_full_size_matches_reference_golden():
     assert gu.rel_l2(r["grads"], [r64["grads"][k] for k in keys]) < 2e-5
 
 
-@pytest.mark.parametrize("name", ["cartpole_37x2_n7_h12", "dcartpole_48x3_n24_h30"])
-def test_generic_cotangents_match_oracle_autograd(name):
+@pytest.mark.parametrize("name,sweeps", [("cartpole_37x2_n7_h12", "ring"), ("cartpole_37x2_n7_h12", "cluster"),
+                                         ("cartpole_200x2_n25_h40", "cluster"), ("dcartpole_48x3_n24_h30", "ring")])
+def test_generic_cotangents_match_oracle_autograd(name, sweeps):
     """Arbitrary cotangents on states/actions/rewards (value-function tails, CVaR, callbacks)."""
     ops, g = gu.load(name)
     H = int(g["H"])
-    r = _run(ops, g["x0"], H, cot="generic")
+    r = _run(ops, g["x0"], H, cot="generic", env=SWEEPS[sweeps])
     ops64, g64 = gu.load(name, torch.float64)
     keys = orc.policy_param_keys(ops64)
     d = dict(ops64)
@@ -111,8 +121,8 @@ def test_ring_depths_agree():
     """The TMA weight ring with 2 or 4 stages (different k-chunk sizes, hence a different grouping of the
     k-split partial sums) gives the same trajectory and gradient to fp32 rounding."""
     ops, g = gu.load("cartpole_200x2_n25_h40")
-    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 2})
-    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 4})
+    a = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 2, "PMB_STREAM_MODE": 2})
+    b = _run(ops, g["x0"], int(g["H"]), env={"PMB_STAGES": 4, "PMB_STREAM_MODE": 2})
     assert (a["S"] - b["S"]).abs().max() < 1e-6 and (a["R"] - b["R"]).abs().max() < 1e-6
     assert gu.rel_l2(a["grads"], b["grads"]) < 2e-6
     for r in (a, b):
@@ -138,9 +148,34 @@ def test_tensor_core_weight_gradient_matches_fp32_kernel(fixture):
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
 def test_particles_per_cta_variants(P):
     ops, g = gu.load("cartpole_37x2_n7_h12")   # N=7: ragged last CTA for every P > 1
-    r = _run(ops, g["x0"], int(g["H"]), env={"PMB_PARTICLES_PER_CTA": P})
+    r = _run(ops, g["x0"], int(g["H"]), env={"PMB_PARTICLES_PER_CTA": P, "PMB_STREAM_MODE": 2})
     assert (r["S"] - g["nomm_states"]).abs().max() < 2e-6
     assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
+
+
+@pytest.mark.parametrize("C", [4, 8])
+@pytest.mark.parametrize("PG", [1, 2, 3, 5, 8])
+def test_particles_per_cluster_variants(PG, C):
+    """Cluster-resident sweeps with every tiling of N=7 particles (ragged last cluster, partly filled tiles) and
+    both cluster sizes (different column slices, hence a different grouping of the partial sums)."""
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    r = _run(ops, g["x0"], int(g["H"]), env={"PMB_STREAM_MODE": 3, "PMB_CLUSTER_PG": PG, "PMB_CLUSTER_C": C})
+    assert (r["S"] - g["nomm_states"]).abs().max() < 2e-6
+    assert (r["A"] - g["nomm_actions"]).abs().max() < 2e-5
+    assert (r["R"] - g["nomm_rewards"]).abs().max() < 2e-6
+    assert gu.rel_l2(r["grads"], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
+    assert gu.rel_l2(r["dx0"], g["nomm_dx0"]) < 1e-5
+
+
+def test_sweep_variants_agree():
+    """The streaming and the cluster-resident sweeps give the same trajectory and gradient to fp32 rounding."""
+    ops, g = gu.load("cartpole_200x2_n25_h40")
+    ref = gu.policy_grad_list(g, "nomm", ops)
+    a = _run(ops, g["x0"], int(g["H"]), env=SWEEPS["ring"])
+    b = _run(ops, g["x0"], int(g["H"]), env=SWEEPS["cluster"])
+    assert (a["S"] - b["S"]).abs().max() < 1e-6 and (a["R"] - b["R"]).abs().max() < 1e-6
+    assert gu.rel_l2(a["grads"], b["grads"]) < 5e-6
+    assert gu.rel_l2(a["grads"], ref) < 1e-5 and gu.rel_l2(b["grads"], ref) < 1e-5
 
 
 def test_determinism():
