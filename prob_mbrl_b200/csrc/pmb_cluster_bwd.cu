@@ -18,72 +18,110 @@ constexpr int CM_GS = 0, CM_GSP = 1, CM_STG_S1 = 2, CM_STG_A = 3, CM_PRE = 4;
 constexpr int CPRE_RS = 0, CPRE_RA = 1, CPRE_FD = 2, CPRE_TP = 3, CPRE_FP = 4, CPRE_GS0 = 5, CPRE_N = 6;
 constexpr int CBL = CL_PS * SD;
 
+// Per-thread constants and running pointers of one net's adjoint pass.
+//   thin layer : thread = column tid of hidden 1;  epilogue of the wide layer: thread = (slot = warp, column = lane)
+struct BwdNetRegs {
+    bool thin_on, thin_store, wide_on, wide_store, send_ok;
+    float wmk;                       // mask / keep of (slot, column) of hidden 0
+    const float *tw;                 // smem: thin matrix, column of this thread
+    const float *tmk;                // smem: mask rows of hidden 1, column of this thread
+    float tkinv;
+    const float *gt_ptr, *gw_ptr;    // global: stored activations that gate the adjoints (next step to fetch)
+    float *dl_thin, *dl_wide;        // global: policy adjoints kept for the weight gradient (current step)
+    size_t thin_step, wide_step;
+    int tW, tK;
+    __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int n0,
+                                         int nval, bool store) {
+        const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
+        const int H = prm.H, N = prm.N;
+        tW = n.tW;
+        tK = n.tK;
+        thin_on = tid < n.tW;
+        tw = smem + n.s_tw + tid;
+        tmk = smem + n.s_tm + tid;
+        tkinv = n.tkeep_inv;
+        thin_store = store && thin_on && tid >= rank * n.tsl && tid < (rank + 1) * n.tsl;
+        thin_step = (size_t)N * n.tW;
+        gt_ptr = prm.ws + n.tsav_off + ((size_t)(H - 1) * N + n0) * n.tW + tid;
+        dl_thin = store ? prm.ws + n.tdel_off + ((size_t)(H - 1) * N + n0) * n.tW + tid : nullptr;
+        const int gc = rank * n.hs + lane;
+        wide_on = lane < n.hs && gc < n.wN;
+        wmk = wide_on ? smem[n.s_wm + p * n.hs + lane] * n.wkeep_inv : 0.f;
+        wide_store = store && wide_on && p < nval;
+        wide_step = (size_t)N * n.wN;
+        const int np = min(n0 + p, N - 1);
+        gw_ptr = prm.ws + n.wsav_off + ((size_t)(H - 1) * N + np) * n.wN + gc;
+        dl_wide = store ? prm.ws + n.wdel_off + ((size_t)(H - 1) * N + n0 + p) * n.wN + gc : nullptr;
+        send_ok = p < prm.PG;
+    }
+};
+
 // Adjoint pass through one net up to and including the send of the input-adjoint partials.
-//   x     : [tK][8] adjoint of the net's raw outputs
-//   gt    : gate bits of the thin output (bit p: stored activation of hidden 1, particle slot p, column tid)
-//   gw    : stored activation of hidden 0 for (particle slot = warp, column = rank*hs + lane)
+//   x   : [tK][8] adjoint of the net's raw outputs
+//   gtf : per particle slot, (stored activation of hidden 1 != 0) ? mask / keep : 0   for column tid
+//   gwf : same for hidden 0 at (slot = warp, column = lane of this CTA's slice)
+// y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
 template <int C, bool kStore>
-__device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const CNet &n, float *smem, const float *x,
-                                                unsigned gt, float gw, int t, int n0, int nval, int rank,
-                                                uint32_t inbox_saddr, uint32_t bar_saddr, bool dbg_on, int mark0) {
-    float *act = smem + prm.off_act, *red = smem + prm.off_red, *h2s = smem + prm.off_h2s, *part = smem + prm.off_part;
-    const int N = prm.N;
-    // ---- thin: adjoint of hidden 1 = (dout W2) gated by the stored activation, * mask1 / keep1 ----
-    {
-        const float *tm = smem + n.s_tm;
-        const int tW = n.tW;
-        const float kinv = n.tkeep_inv;
-        const int j0 = rank * n.tsl, j1 = j0 + n.tsl;
-        float *dl = kStore ? prm.ws + n.tdel_off + ((size_t)t * N + n0) * tW : nullptr;
-        cl_thin(smem + n.s_tw, n.tK, tW, x, [&](int j, float2 (&acc)[4]) {
-            float v[CL_PS];
+__device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const CNet &n, BwdNetRegs &R, float *smem,
+                                                const float *x, const float (&gtf)[CL_PS], float gwf, int nval, int rank,
+                                                uint32_t inbox_saddr, uint32_t bar_saddr, bool dbg_step, int mark0) {
+    float *act = smem + prm.off_act, *red = smem + prm.off_red;
+    // ---- thin: adjoint of hidden 1 = (dout W2) * gate ----
+    if (R.thin_on) {
+        float2 acc[4];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                v[2 * h] = acc[h].x;
-                v[2 * h + 1] = acc[h].y;
-            }
-            // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
-#pragma unroll
-            for (int p = 0; p < CL_PS; ++p) v[p] = ((gt >> p) & 1u) ? v[p] * kinv * tm[p * tW + j] : 0.f;
-            cl_store_act(act, j, v);
-            if (kStore && j >= j0 && j < j1) {
-#pragma unroll
-                for (int p = 0; p < CL_PS; ++p)
-                    if (p < nval) dl[(size_t)p * tW + j] = v[p];
-            }
-        });
-    }
-    __syncthreads();
-    CL_MARK(mark0);
-    // ---- wide: this CTA's columns of the adjoint of hidden 0 ----
-    cl_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red);
-    __syncthreads();
-    CL_MARK(mark0 + 1);
-    {
-        const int p = threadIdx.x >> 5, c = threadIdx.x & 31;
-        float v = cl_wide_reduce(red);
-        if (c < n.hs) {
-            v = gw != 0.f ? v * n.wkeep_inv * smem[n.s_wm + p * n.hs + c] : 0.f;
-            const int gc = rank * n.hs + c;
-            if (kStore && p < nval && gc < n.wN) prm.ws[n.wdel_off + ((size_t)t * N + n0 + p) * n.wN + gc] = v;
-        } else {
-            v = 0.f;
+        for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
+        const float *wp = R.tw;
+        const float *xp = x;
+#pragma unroll 2
+        for (int k = 0; k < R.tK; ++k) {
+            const float w = *wp;
+            const float4 x0 = *reinterpret_cast<const float4 *>(xp);
+            const float4 x1 = *reinterpret_cast<const float4 *>(xp + 4);
+            wp += R.tW;
+            xp += CL_PS;
+            acc[0] = cl_fma2(w, make_float2(x0.x, x0.y), acc[0]);
+            acc[1] = cl_fma2(w, make_float2(x0.z, x0.w), acc[1]);
+            acc[2] = cl_fma2(w, make_float2(x1.x, x1.y), acc[2]);
+            acc[3] = cl_fma2(w, make_float2(x1.z, x1.w), acc[3]);
         }
-        h2s[(p << 5) + c] = v;
+        float v[CL_PS];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            v[2 * h] = acc[h].x * gtf[2 * h];
+            v[2 * h + 1] = acc[h].y * gtf[2 * h + 1];
+        }
+        cl_store_act(act, threadIdx.x, v);
+        if (kStore && R.thin_store) {
+#pragma unroll
+            for (int p = 0; p < CL_PS; ++p)
+                if (p < nval) R.dl_thin[(size_t)p * R.tW] = v[p];
+        }
     }
+    if (kStore) R.dl_thin -= R.thin_step;
+    CL_TMARK(mark0);
     __syncthreads();
-    // ---- narrow: partial sums of d(input) = delta_0 W_0 over this CTA's columns; exchange ----
-    cl_narrow_partial(smem + n.s_nw, n.hs, n.nN, n.nNp, h2s, part);
+    // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the warps ----
+    cl_wide_accum2(smem + n.s_ww, n.tW, n.hs, act, red);
+    CL_TMARK(mark0 + 1);
     __syncthreads();
-    CL_MARK(mark0 + 2);
-    cl_send<C>(part, (prm.PG * n.nNp) >> 2, inbox_saddr, bar_saddr, rank);
+    // ---- epilogue (warp = particle slot, lane = column) + partial sums of d(input) = delta_0 W_0 + exchange ----
+    {
+        const float v = cl_wide_reduce(red) * gwf;      // idle lanes: gwf = 0 and red holds zeros
+        if (kStore) {
+            if (R.wide_store) *R.dl_wide = v;
+            R.dl_wide -= R.wide_step;
+        }
+        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank);
+    }
+    CL_TMARK(mark0 + 2);
 }
 
 template <int C>
 __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_constant__ ClusterParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t xbar[2];          // [0] dynamics exchange, [1] policy exchange
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int rank = (int)cl_rank();
     const int PG = prm.PG;
     const int n0 = (int)cl_id_x() * PG;
@@ -115,6 +153,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     load_constants(prm, cst);
     cl_load_net(prm, dyn, smem, rank, n0, false);
     cl_load_net(prm, pol, smem, rank, n0, false);
+    __syncthreads();
+    BwdNetRegs Rd, Rp;
+    Rd.init(prm, dyn, smem, rank, n0, nval, false);
+    Rp.init(prm, pol, smem, rank, n0, nval, true);
 
     // ---- thread roles (fixed for the whole horizon) ----
     const bool roleA = tid < CL_PS * U;                       // (particle slot, action dim)
@@ -129,11 +171,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     const bool roleR = tid >= 224 && tid - 224 < CL_PS;       // particle slot (reward weight)
     const int r_p = roleR ? tid - 224 : 0;
     const int r_n = min(n0 + r_p, N - 1);
-    // gates: thin epilogue thread = column tid of hidden 1; wide epilogue thread = (slot warp, column lane) of hidden 0
-    const bool gt_dyn_on = tid < dyn.tW, gt_pol_on = tid < pol.tW;
-    const int gw_n = min(n0 + warp, N - 1);
-    const int gwc_dyn = rank * dyn.hs + lane, gwc_pol = rank * pol.hs + lane;
-    const bool gw_dyn_on = lane < dyn.hs && gwc_dyn < dyn.wN, gw_pol_on = lane < pol.hs && gwc_pol < pol.wN;
+    const float x_isx = roleX ? prm.iSx[x_k] : 0.f;
+    const float b_sy = roleB ? prm.Sy[b_d] : 0.f;
 
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
 
@@ -141,7 +180,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     float pf_s1 = 0.f, pf_ls = 0.f, pf_zd = 0.f, pf_gs = 0.f;                 // role B
     float pf_a = 0.f, pf_mu = 0.f, pf_lsp = 0.f, pf_zp = 0.f, pf_ga = 0.f;    // role A
     float pf_r = 0.f, pf_gr = 0.f;                                            // role R
-    float pg_td[CL_PS], pg_tp[CL_PS];                                         // raw gate values of the next step
+    float pg_td[CL_PS], pg_tp[CL_PS];                                         // stored activations of the next step
     float pg_wd = 0.f, pg_wp = 0.f;
 #pragma unroll
     for (int p = 0; p < CL_PS; ++p) pg_td[p] = pg_tp[p] = 0.f;
@@ -168,27 +207,33 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             pf_r = __ldg(prm.rewards + (size_t)tt * N + r_n);
             pf_gr = prm.g_rewards ? __ldg(prm.g_rewards + (size_t)tt * N + r_n) : 0.f;
         }
-        // stored activations that gate the adjoints (plain loads: written by the forward kernel, read-only here)
+        // stored activations that gate the adjoints (the running pointers stand on step tt)
+        const int last = N - 1 - n0;                     // slots past the last particle repeat it
 #pragma unroll
         for (int p = 0; p < CL_PS; ++p) {
-            const size_t row = (size_t)tt * N + min(n0 + p, N - 1);
-            if (gt_dyn_on) pg_td[p] = __ldg(prm.ws + dyn.tsav_off + row * dyn.tW + tid);
-            if (gt_pol_on) pg_tp[p] = __ldg(prm.ws + pol.tsav_off + row * pol.tW + tid);
+            const size_t row = (size_t)min(p, last);
+            if (Rd.thin_on) pg_td[p] = __ldg(Rd.gt_ptr + row * Rd.tW);
+            if (Rp.thin_on) pg_tp[p] = __ldg(Rp.gt_ptr + row * Rp.tW);
         }
-        if (gw_dyn_on) pg_wd = __ldg(prm.ws + dyn.wsav_off + ((size_t)tt * N + gw_n) * dyn.wN + gwc_dyn);
-        if (gw_pol_on) pg_wp = __ldg(prm.ws + pol.wsav_off + ((size_t)tt * N + gw_n) * pol.wN + gwc_pol);
+        if (Rd.wide_on) pg_wd = __ldg(Rd.gw_ptr);
+        if (Rp.wide_on) pg_wp = __ldg(Rp.gw_ptr);
+        Rd.gt_ptr -= Rd.thin_step;
+        Rp.gt_ptr -= Rp.thin_step;
+        Rd.gw_ptr -= Rd.wide_step;
+        Rp.gw_ptr -= Rp.wide_step;
     };
-    unsigned gt_dyn = 0u, gt_pol = 0u;
-    float gw_dyn = 0.f, gw_pol = 0.f;
+    float gtf_dyn[CL_PS], gtf_pol[CL_PS];
+    float gwf_dyn = 0.f, gwf_pol = 0.f;
+#pragma unroll
+    for (int p = 0; p < CL_PS; ++p) gtf_dyn[p] = gtf_pol[p] = 0.f;
     auto latch_gates = [&]() {
-        gt_dyn = gt_pol = 0u;
 #pragma unroll
         for (int p = 0; p < CL_PS; ++p) {
-            gt_dyn |= (pg_td[p] != 0.f ? 1u : 0u) << p;
-            gt_pol |= (pg_tp[p] != 0.f ? 1u : 0u) << p;
+            gtf_dyn[p] = (Rd.thin_on && pg_td[p] != 0.f) ? Rd.tmk[p * Rd.tW] * Rd.tkinv : 0.f;
+            gtf_pol[p] = (Rp.thin_on && pg_tp[p] != 0.f) ? Rp.tmk[p * Rp.tW] * Rp.tkinv : 0.f;
         }
-        gw_dyn = pg_wd;
-        gw_pol = pg_wp;
+        gwf_dyn = pg_wd != 0.f ? Rd.wmk : 0.f;
+        gwf_pol = pg_wp != 0.f ? Rp.wmk : 0.f;
     };
     // first half of the precompute: factors that need no cross-thread data (+ staging of s', a, w)
     auto precompute_a = [&](float *pre) {
@@ -246,11 +291,13 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
 
     const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
     const uint32_t bar_dyn = smem_u32(&xbar[0]), bar_pol = smem_u32(&xbar[1]);
+    float *odel_ptr = nullptr;          // role X (action dims): adjoint of the policy outputs of the current step
+    if (roleX && x_k >= D) odel_ptr = prm.ws + pol.odel_off + ((size_t)(H - 1) * N + min(n0 + x_p, N - 1)) * pol.nraw + (x_k - D);
+    const size_t odel_step = (size_t)N * pol.nraw;
 
     // ---- prologue: everything step H-1 needs ----
     int cur = 0;
     prefetch(H - 1);
-    __syncthreads();            // constants are in place
     precompute_a(pre0);
     __syncthreads();
     precompute_b(pre0);
@@ -260,9 +307,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
 
 #pragma unroll 1
     for (int t = H - 1, it = 0; t >= 0; --t, ++it) {
-        const bool dbg_on = prm.dbg != nullptr && blockIdx.x == 0 && tid == 0 && t == H / 2;
+        const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
         const uint32_t par = (uint32_t)(it & 1);
-        CL_MARK(256);
+        CL_TMARK(32);
         const int nxt = cur ^ 1;
         float *pre = pre0 + cur * CPRE_N * CBL;
         float *pren = pre0 + nxt * CPRE_N * CBL;
@@ -273,19 +320,19 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         if (roleB) {
             const float g = gs[b_p * SD + b_d] + pre[CPRE_RS * CBL + b_p * SD + b_d];
             gsp[b_p * SD + b_d] = g;
-            xd[b_d * CL_PS + b_p] = g * cst[C_SY + b_d];
+            xd[b_d * CL_PS + b_p] = g * b_sy;
             if (dyn.has_density) xd[(D + b_d) * CL_PS + b_p] = g * pre[CPRE_FD * CBL + b_p * SD + b_d];
         }
+        CL_TMARK(33);
         __syncthreads();
-        CL_MARK(257);
         // ================= dynamics net =================
-        cl_net_backward<C, false>(prm, dyn, smem, xd, gt_dyn, gw_dyn, t, n0, nval, rank, inbox_saddr, bar_dyn, dbg_on, 258);
+        cl_net_backward<C, false>(prm, dyn, Rd, smem, xd, gtf_dyn, gwf_dyn, nval, rank, inbox_saddr, bar_dyn, dbg_step, 34);
         if (roleX) {
             // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
             //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
             mbar_wait(&xbar[0], par);
             if (tid == 0) mbar_expect_tx(&xbar[0], bytes_dyn);
-            const float v = cl_gather<C>(inbox_dyn, x_p * dyn.nNp + x_k) * cst[C_ISX + x_k];
+            const float v = cl_gather2<C>(inbox_dyn, x_p, x_k) * x_isx;
             if (x_k < D) {
                 gsp[x_p * SD + x_k] += v;
             } else {
@@ -299,31 +346,31 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
                     xp[(U + u) * CL_PS + x_p] = dls;
                 }
                 if (x_own) {
-                    float *dd = prm.ws + pol.odel_off + ((size_t)t * N + n0 + x_p) * pol.nraw;
-                    dd[u] = du;
-                    if (pol.has_density) dd[U + u] = dls;
+                    odel_ptr[0] = du;
+                    if (pol.has_density) odel_ptr[U] = dls;
                 }
             }
         }
+        odel_ptr -= odel_step;
         if (t > 0) precompute_a(pren);
+        CL_TMARK(37);
         __syncthreads();
-        CL_MARK(262);
         // ================= policy net =================
-        cl_net_backward<C, true>(prm, pol, smem, xp, gt_pol, gw_pol, t, n0, nval, rank,
-                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, dbg_on, 263);
+        cl_net_backward<C, true>(prm, pol, Rp, smem, xp, gtf_pol, gwf_pol, nval, rank,
+                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, dbg_step, 38);
         if (roleB) {
             // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
             mbar_wait(&xbar[1], par);
             if (tid == 128) mbar_expect_tx(&xbar[1], bytes_pol);
-            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather<C>(inbox_pol, b_p * pol.nNp + b_d) +
+            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather2<C>(inbox_pol, b_p, b_d) +
                                  pre[CPRE_GS0 * CBL + b_p * SD + b_d];
         }
         if (t > 0) {
             precompute_b(pren);
             latch_gates();
         }
+        CL_TMARK(41);
         __syncthreads();
-        CL_MARK(267);
         cur = nxt;
     }
     if (prm.dx0 && roleB && b_p < nval && (b_p % C) == rank) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];

@@ -46,12 +46,11 @@ if os.environ.get("PMB_STREAM_MODE", "0") in ("0", "3"):
     for k in sorted(names):
         v = [x - t0 for x in d[8 * k: 8 * k + 8]]
         print("    %-30s min %6d max %6d  | %s" % (names[k], min(v), max(v), " ".join("%6d" % x for x in v)))
-    print("cluster-resident backward sweep (thread 0 marks, cycles):")
-    names = {256: "top", 257: "density adj", 258: "dyn thin", 259: "dyn wide accum", 260: "dyn reduce+narrow",
-             262: "exchange+scaler/squash", 263: "pol thin", 264: "pol wide accum", 265: "pol reduce+narrow", 267: "exchange+gs"}
-    ks = sorted(names)
-    prev = d[ks[0]]
-    for k in ks:
-        if d[k]:
-            print("    %-24s +%6d  (t=%6d)" % (names[k], d[k] - prev, d[k] - d[ks[0]]))
-            prev = d[k]
+    print("cluster-resident backward sweep: per-warp arrival")
+    names = {32: "step top", 33: "density adjoint done", 34: "dyn thin done", 35: "dyn wide accum done",
+             36: "dyn epilogue+narrow+send done", 37: "scaler/squash role done", 38: "pol thin done",
+             39: "pol wide accum done", 40: "pol epilogue+narrow+send done", 41: "gs role done"}
+    t0 = min(x for x in d[256:264] if x)
+    for k in sorted(names):
+        v = [x - t0 for x in d[8 * k: 8 * k + 8]]
+        print("    %-30s min %6d max %6d  | %s" % (names[k], min(v), max(v), " ".join("%6d" % x for x in v)))
