@@ -53,6 +53,7 @@ struct Plan {
     // cluster-resident sweeps (pmb_cluster.cuh): used instead of the streaming sweeps when eligible
     int cluster;              // 0 = streaming sweeps, otherwise CTAs per cluster
     int cl_nclusters;
+    long long cl_pre_off;     // [H][N][2D + 3U] step-local adjoint factors of the cluster-resident reverse sweep
     ClusterParams cfwd, cbwd;
 };
 
@@ -475,6 +476,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     pl.nparam = np;
     pl.part_off = ws.take((long long)pl.nsplit * np);
+    pl.cl_pre_off = ws.take((long long)p->H * p->N * (2 * p->D + 3 * p->U));
     if (mm) {
         const long long HN = (long long)p->H * p->N;
         const int grid = (p->N + P - 1) / P;
@@ -522,6 +524,7 @@ static void resolve(Plan &pl, float *ws) {
     pl.fwd.wpack = ws + pl.wpack_fwd_off;
     pl.bwd.wpack = ws + pl.wpack_bwd_off;
     pl.cfwd.ws = pl.cbwd.ws = ws;
+    pl.cbwd.pre = ws + pl.cl_pre_off;
     pl.cfwd.wpack = ws + pl.wpack_fwd_off;
     pl.cbwd.wpack = ws + pl.wpack_bwd_off;
     if (pl.fwd.mm_states || pl.fwd.mm_rewards) {

@@ -65,7 +65,8 @@ struct ClusterParams {
     float *states, *actions, *rewards;
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
-    long long *dbg;             // clock64() marks of cluster 0 / rank 0 / thread 0 at step H/2 (nullable)
+    float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
+    long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)
     int off_cst, off_xa, off_xb, off_act, off_red, off_h2s, off_part, off_inbox, off_misc;
     int smem_floats;
 };

@@ -5,18 +5,89 @@
 // (H*N) axis afterwards.  Replaces loss.backward() through utils.rollout (reference
 // algorithms/mc_pilco.py:197); the adjoint formulas are those of oracle/rollout_oracle.py::manual_backward.
 //
-// Everything that depends only on forward values (reward adjoint, density / tanh derivative factors, direct
-// cotangents, the ReLU/dropout gates) is fetched ONE STEP AHEAD into registers and turned into a
-// double-buffered "pre" block in shared memory, so the serial chain never waits on global memory.
+// Everything that depends only on forward values (reward adjoint, density / tanh derivative factors) is computed
+// by a fully parallel pre-pass (cluster_bwd_pre_kernel); the sweep fetches those factors, the direct cotangents
+// and the ReLU/dropout gates ONE STEP AHEAD into registers, so the serial chain never waits on global memory
+// and holds no transcendental arithmetic.
 #include "pmb_cluster.cuh"
 #include "pmb_host.h"
 
 namespace pmb {
 
-// float offsets inside the per-particle scratch block (`misc`), in units of one [8][SD] block
-constexpr int CM_GS = 0, CM_GSP = 1, CM_STG_S1 = 2, CM_STG_A = 3, CM_PRE = 4;
-constexpr int CPRE_RS = 0, CPRE_RA = 1, CPRE_FD = 2, CPRE_TP = 3, CPRE_FP = 4, CPRE_GS0 = 5, CPRE_N = 6;
-constexpr int CBL = CL_PS * SD;
+constexpr int CBL = CL_PS * SD;      // one [8][SD] block of the per-particle scratch area (`misc`)
+
+// Step-local adjoint factors for every (step, particle), computed in one fully parallel pass BEFORE the sweep so
+// that the serial chain holds no transcendental or reward arithmetic:
+//   pre[t][n] = [ RS(D) | FD(D) | RA(U) | TP(U) | FP(U) ]
+//   RS = g_r * dr/ds'        reward adjoint on the next state:  w * C^T (Q+Q^T) delta,  w = -0.5 * g_r * (r - offset)
+//   FD = d s'/d log_std      dynamics density:  z * exp(clamped log_std + log Sy) * sigmoid(lmax - log_std)
+//   RA = g_a + g_r * dr/da   direct action cotangent + reward adjoint  w * (R+R^T) a
+//   TP = d a/d u = scale * (1 - tanh(u)^2),   FP = d u/d log_std = z * exp(clamped log_std) * sigmoid(lmax - log_std)
+__global__ void __launch_bounds__(256) cluster_bwd_pre_kernel(const __grid_constant__ ClusterParams prm) {
+    const int N = prm.N, D = prm.D, U = prm.U, KR = prm.KR;
+    const CNet &pol = prm.pol;
+    const CNet &dyn = prm.dyn;
+    const long long total = (long long)prm.H * N;
+    const int PW = 2 * D + 3 * U;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / N), n = (int)(i - (long long)t * N);
+        float *out = prm.pre + i * PW;
+        const float *s1 = prm.states + ((size_t)(t + 1) * N + n) * D;
+        const float *a = prm.actions + ((size_t)t * N + n) * U;
+        const float r = __ldg(prm.rewards + i);
+        const float gr = prm.g_rewards ? __ldg(prm.g_rewards + i) : 0.f;
+        const float w = -0.5f * gr * (r - prm.rew_offset);       // g_r * d r / d cost, r - off = scale*exp(-cost)
+        float dl[PMB_MAX_REWARD_ROWS], qd[PMB_MAX_REWARD_ROWS];
+        for (int k = 0; k < KR; ++k) {
+            float acc = __ldg(prm.rew_c0 + k);
+            for (int d = 0; d < D; ++d) acc = fmaf(__ldg(prm.rew_C + k * D + d), __ldg(s1 + d), acc);
+            dl[k] = acc;
+        }
+        for (int k = 0; k < KR; ++k) {
+            float acc = 0.f;
+            for (int j = 0; j < KR; ++j)
+                acc = fmaf(__ldg(prm.rew_Q + k * KR + j) + __ldg(prm.rew_Q + j * KR + k), dl[j], acc);
+            qd[k] = acc;
+        }
+        for (int d = 0; d < D; ++d) {
+            float acc = 0.f;
+            for (int k = 0; k < KR; ++k) acc = fmaf(qd[k], __ldg(prm.rew_C + k * D + d), acc);
+            out[d] = w * acc;
+            float fd = 0.f;
+            if (dyn.has_density) {
+                const float ls = __ldg(prm.ws + dyn.raw_off + (size_t)i * dyn.nraw + D + d);
+                const float z = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)n * D + d);
+                const float lst = clamp_logstd(ls, dyn.lmax) + logf(__ldg(prm.Sy + d));
+                fd = z * expf(lst) * sigmoid_f(dyn.lmax - ls);
+            }
+            out[D + d] = fd;
+        }
+        for (int u = 0; u < U; ++u) {
+            float acc = 0.f;
+            for (int v = 0; v < U; ++v)
+                acc = fmaf(__ldg(prm.rew_R + u * U + v) + __ldg(prm.rew_R + v * U + u), __ldg(a + v), acc);
+            const float ga = prm.g_actions ? __ldg(prm.g_actions + (size_t)i * U + u) : 0.f;
+            out[2 * D + u] = ga + w * acc;
+            const float *op = prm.ws + pol.raw_off + (size_t)i * pol.nraw;
+            const float mu = __ldg(op + u);
+            const float sc = __ldg(prm.act_scale + u);
+            float tp, fp = 0.f;
+            if (pol.has_density) {
+                const float ls = __ldg(op + U + u);
+                const float z = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)n * U + u);
+                const float el = expf(clamp_logstd(ls, pol.lmax));
+                const float th = tanhf(mu + z * el);
+                tp = sc * (1.f - th * th);
+                fp = z * el * sigmoid_f(pol.lmax - ls);
+            } else {
+                const float th = tanhf(mu);
+                tp = sc * (1.f - th * th);
+            }
+            out[2 * D + U + u] = tp;
+            out[2 * D + 2 * U + u] = fp;
+        }
+    }
+}
 
 // Per-thread constants and running pointers of one net's adjoint pass.
 //   thin layer : thread = column tid of hidden 1;  epilogue of the wide layer: thread = (slot = warp, column = lane)
@@ -125,21 +196,17 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     const int rank = (int)cl_rank();
     const int PG = prm.PG;
     const int n0 = (int)cl_id_x() * PG;
-    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, KR = prm.KR;
+    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
     const int nval = min(PG, N - n0);
     const CNet &pol = prm.pol;
     const CNet &dyn = prm.dyn;
 
     for (int i = tid; i < prm.smem_floats; i += CL_NT) smem[i] = 0.f;
     __syncthreads();
-    float *cst = smem + prm.off_cst;
     float *xd = smem + prm.off_xa;         // [2D][8]  adjoint of the dynamics net's raw outputs
     float *xp = smem + prm.off_xb;         // [2U][8]  adjoint of the policy net's raw outputs
     float *misc = smem + prm.off_misc;
-    float *gs = misc + CM_GS * CBL, *gsp = misc + CM_GSP * CBL;
-    float *stg_s1 = misc + CM_STG_S1 * CBL, *stg_a = misc + CM_STG_A * CBL;
-    float *pre0 = misc + CM_PRE * CBL;                 // two buffers of CPRE_N blocks
-    float *stg_w = pre0 + 2 * CPRE_N * CBL;            // [8]
+    float *gs = misc, *gsp = misc + CBL;               // [8][SD] carried / partial state adjoint
     const float *inbox_dyn = smem + prm.off_inbox;
     const float *inbox_pol = inbox_dyn + C * CL_INBOX;
     const uint32_t bytes_dyn = (uint32_t)(C * PG * dyn.nNp) * 4u, bytes_pol = (uint32_t)(C * PG * pol.nNp) * 4u;
@@ -150,7 +217,6 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         mbar_expect_tx(&xbar[0], bytes_dyn);
         mbar_expect_tx(&xbar[1], bytes_pol);
     }
-    load_constants(prm, cst);
     cl_load_net(prm, dyn, smem, rank, n0, false);
     cl_load_net(prm, pol, smem, rank, n0, false);
     __syncthreads();
@@ -168,44 +234,33 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     const bool roleX = tid < CL_PS * (D + U);                 // (particle slot, dynamics-input dim)
     const int x_p = roleX ? tid / (D + U) : 0, x_k = roleX ? tid - x_p * (D + U) : 0;
     const bool x_own = roleX && x_p < nval && (x_p % C) == rank;
-    const bool roleR = tid >= 224 && tid - 224 < CL_PS;       // particle slot (reward weight)
-    const int r_p = roleR ? tid - 224 : 0;
-    const int r_n = min(n0 + r_p, N - 1);
     const float x_isx = roleX ? prm.iSx[x_k] : 0.f;
     const float b_sy = roleB ? prm.Sy[b_d] : 0.f;
 
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
 
-    // prefetch registers of the one-step-ahead precompute
-    float pf_s1 = 0.f, pf_ls = 0.f, pf_zd = 0.f, pf_gs = 0.f;                 // role B
-    float pf_a = 0.f, pf_mu = 0.f, pf_lsp = 0.f, pf_zp = 0.f, pf_ga = 0.f;    // role A
-    float pf_r = 0.f, pf_gr = 0.f;                                            // role R
-    float pg_td[CL_PS], pg_tp[CL_PS];                                         // stored activations of the next step
+    // step-local factors (bwd_pre_kernel) and gates, fetched one step ahead into registers
+    const int PW = 2 * D + 3 * U;
+    const int x_n = min(n0 + x_p, N - 1);
+    const bool xact = roleX && x_k >= D;
+    float nx_rs = 0.f, nx_fd = 0.f, nx_gs = 0.f;        // role B (slot, state dim)
+    float nx_ra = 0.f, nx_tp = 0.f, nx_fp = 0.f;        // role X, action dims
+    float pg_td[CL_PS], pg_tp[CL_PS];                   // stored activations of the next step
     float pg_wd = 0.f, pg_wp = 0.f;
 #pragma unroll
     for (int p = 0; p < CL_PS; ++p) pg_td[p] = pg_tp[p] = 0.f;
     auto prefetch = [&](int tt) {
         if (roleB) {
-            pf_s1 = __ldg(prm.states + ((size_t)(tt + 1) * N + b_n) * D + b_d);
-            if (dyn.has_density) {
-                pf_ls = __ldg(prm.ws + dyn.raw_off + ((size_t)tt * N + b_n) * dyn.nraw + D + b_d);
-                pf_zd = __ldg(dyn.z + (size_t)tt * dyn.zstride + (size_t)b_n * D + b_d);
-            }
-            pf_gs = prm.g_states ? __ldg(prm.g_states + ((size_t)tt * N + b_n) * D + b_d) : 0.f;
+            const float *q = prm.pre + ((size_t)tt * N + b_n) * PW;
+            nx_rs = __ldg(q + b_d);
+            nx_fd = __ldg(q + D + b_d);
+            nx_gs = prm.g_states ? __ldg(prm.g_states + ((size_t)tt * N + b_n) * D + b_d) : 0.f;
         }
-        if (roleA) {
-            const float *op = prm.ws + pol.raw_off + ((size_t)tt * N + a_n) * pol.nraw;
-            pf_a = __ldg(prm.actions + ((size_t)tt * N + a_n) * U + a_u);
-            pf_mu = __ldg(op + a_u);
-            if (pol.has_density) {
-                pf_lsp = __ldg(op + U + a_u);
-                pf_zp = __ldg(pol.z + (size_t)tt * pol.zstride + (size_t)a_n * U + a_u);
-            }
-            pf_ga = prm.g_actions ? __ldg(prm.g_actions + ((size_t)tt * N + a_n) * U + a_u) : 0.f;
-        }
-        if (roleR) {
-            pf_r = __ldg(prm.rewards + (size_t)tt * N + r_n);
-            pf_gr = prm.g_rewards ? __ldg(prm.g_rewards + (size_t)tt * N + r_n) : 0.f;
+        if (xact) {
+            const float *q = prm.pre + ((size_t)tt * N + x_n) * PW + 2 * D + (x_k - D);
+            nx_ra = __ldg(q);
+            nx_tp = __ldg(q + U);
+            nx_fp = __ldg(q + 2 * U);
         }
         // stored activations that gate the adjoints (the running pointers stand on step tt)
         const int last = N - 1 - n0;                     // slots past the last particle repeat it
@@ -235,60 +290,6 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         gwf_dyn = pg_wd != 0.f ? Rd.wmk : 0.f;
         gwf_pol = pg_wp != 0.f ? Rp.wmk : 0.f;
     };
-    // first half of the precompute: factors that need no cross-thread data (+ staging of s', a, w)
-    auto precompute_a = [&](float *pre) {
-        if (roleB) {
-            stg_s1[b_p * SD + b_d] = pf_s1;
-            float fd = 0.f;
-            if (dyn.has_density) {
-                const float lst = clamp_logstd(pf_ls, dyn.lmax) + cst[C_LSY + b_d];
-                fd = pf_zd * expf(lst) * sigmoid_f(dyn.lmax - pf_ls);     // d s' / d log_std (raw)
-            }
-            pre[CPRE_FD * CBL + b_p * SD + b_d] = fd;
-            pre[CPRE_GS0 * CBL + b_p * SD + b_d] = pf_gs;
-        }
-        if (roleA) {
-            stg_a[a_p * SD + a_u] = pf_a;
-            const float sc = cst[C_SCALE + a_u];
-            float tp, fp = 0.f;
-            if (pol.has_density) {
-                const float el = expf(clamp_logstd(pf_lsp, pol.lmax));
-                const float th = tanhf(pf_mu + pf_zp * el);
-                tp = sc * (1.f - th * th);                                  // d a / d u
-                fp = pf_zp * el * sigmoid_f(pol.lmax - pf_lsp);             // d u / d log_std (raw)
-            } else {
-                const float th = tanhf(pf_mu);
-                tp = sc * (1.f - th * th);
-            }
-            pre[CPRE_TP * CBL + a_p * SD + a_u] = tp;
-            pre[CPRE_FP * CBL + a_p * SD + a_u] = fp;
-        }
-        if (roleR) stg_w[r_p] = -0.5f * pf_gr * (pf_r - prm.rew_offset);   // g_r * d r / d cost, r - off = scale*exp(-cost)
-    };
-    // second half: reward adjoint on (s', a):  w * C^T (Q+Q^T) delta  and  g_a + w * (R+R^T) a
-    auto precompute_b = [&](float *pre) {
-        if (roleB) {
-            float dl[PMB_MAX_REWARD_ROWS];
-            for (int i = 0; i < KR; ++i) {
-                float s = cst[C_C0 + i];
-                for (int d = 0; d < D; ++d) s = fmaf(cst[C_C + i * SD + d], stg_s1[b_p * SD + d], s);
-                dl[i] = s;
-            }
-            float acc = 0.f;
-            for (int i = 0; i < KR; ++i) {
-                float qd = 0.f;
-                for (int j = 0; j < KR; ++j) qd = fmaf(cst[C_QS + i * 4 + j], dl[j], qd);
-                acc = fmaf(qd, cst[C_C + i * SD + b_d], acc);
-            }
-            pre[CPRE_RS * CBL + b_p * SD + b_d] = stg_w[b_p] * acc;
-        }
-        if (roleA) {
-            float s = 0.f;
-            for (int v = 0; v < U; ++v) s = fmaf(cst[C_RS + a_u * SD + v], stg_a[a_p * SD + v], s);
-            pre[CPRE_RA * CBL + a_p * SD + a_u] = pf_ga + stg_w[a_p] * s;
-        }
-    };
-
     const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
     const uint32_t bar_dyn = smem_u32(&xbar[0]), bar_pol = smem_u32(&xbar[1]);
     float *odel_ptr = nullptr;          // role X (action dims): adjoint of the policy outputs of the current step
@@ -296,12 +297,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     const size_t odel_step = (size_t)N * pol.nraw;
 
     // ---- prologue: everything step H-1 needs ----
-    int cur = 0;
+    float c_rs, c_fd, c_gs, c_ra, c_tp, c_fp;
     prefetch(H - 1);
-    precompute_a(pre0);
-    __syncthreads();
-    precompute_b(pre0);
     latch_gates();
+    c_rs = nx_rs; c_fd = nx_fd; c_gs = nx_gs; c_ra = nx_ra; c_tp = nx_tp; c_fp = nx_fp;
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
 
@@ -310,18 +309,15 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
         const uint32_t par = (uint32_t)(it & 1);
         CL_TMARK(32);
-        const int nxt = cur ^ 1;
-        float *pre = pre0 + cur * CPRE_N * CBL;
-        float *pren = pre0 + nxt * CPRE_N * CBL;
-        // ---- one step ahead: scalars and gates of step t-1 ----
+        // ---- one step ahead: factors and gates of step t-1 ----
         if (t > 0) prefetch(t - 1);
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
         if (roleB) {
-            const float g = gs[b_p * SD + b_d] + pre[CPRE_RS * CBL + b_p * SD + b_d];
+            const float g = gs[b_p * SD + b_d] + c_rs;
             gsp[b_p * SD + b_d] = g;
             xd[b_d * CL_PS + b_p] = g * b_sy;
-            if (dyn.has_density) xd[(D + b_d) * CL_PS + b_p] = g * pre[CPRE_FD * CBL + b_p * SD + b_d];
+            if (dyn.has_density) xd[(D + b_d) * CL_PS + b_p] = g * c_fd;
         }
         CL_TMARK(33);
         __syncthreads();
@@ -337,12 +333,11 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
                 gsp[x_p * SD + x_k] += v;
             } else {
                 const int u = x_k - D;
-                const float ga = pre[CPRE_RA * CBL + x_p * SD + u] + v;
-                const float du = ga * pre[CPRE_TP * CBL + x_p * SD + u];
+                const float du = (c_ra + v) * c_tp;
                 xp[u * CL_PS + x_p] = du;
                 float dls = 0.f;
                 if (pol.has_density) {
-                    dls = du * pre[CPRE_FP * CBL + x_p * SD + u];
+                    dls = du * c_fp;
                     xp[(U + u) * CL_PS + x_p] = dls;
                 }
                 if (x_own) {
@@ -352,7 +347,6 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             }
         }
         odel_ptr -= odel_step;
-        if (t > 0) precompute_a(pren);
         CL_TMARK(37);
         __syncthreads();
         // ================= policy net =================
@@ -362,16 +356,14 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
             mbar_wait(&xbar[1], par);
             if (tid == 128) mbar_expect_tx(&xbar[1], bytes_pol);
-            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather2<C>(inbox_pol, b_p, b_d) +
-                                 pre[CPRE_GS0 * CBL + b_p * SD + b_d];
+            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather2<C>(inbox_pol, b_p, b_d) + c_gs;
         }
         if (t > 0) {
-            precompute_b(pren);
             latch_gates();
+            c_rs = nx_rs; c_fd = nx_fd; c_gs = nx_gs; c_ra = nx_ra; c_tp = nx_tp; c_fp = nx_fp;
         }
         CL_TMARK(41);
         __syncthreads();
-        cur = nxt;
     }
     if (prm.dx0 && roleB && b_p < nval && (b_p % C) == rank) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
@@ -386,6 +378,13 @@ static cudaError_t cluster_launch_cfg_b(const void *fn, int C, int smem_bytes) {
 
 cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream) {
     const int smem_bytes = prm.smem_floats * 4;
+    {
+        const long long total = (long long)prm.H * prm.N;
+        const int blocks = (int)min((total + 255) / 256, (long long)148 * 8);
+        cluster_bwd_pre_kernel<<<blocks, 256, 0, stream>>>(prm);
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
