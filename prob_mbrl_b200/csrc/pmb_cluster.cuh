@@ -344,9 +344,19 @@ __device__ __forceinline__ void cl_st_async_b32(uint32_t daddr, float v, uint32_
 //   out[o] = sum_lanes v * nw[o][lane]   for o < NV
 // with a reduce-scatter butterfly (NV values per lane -> 1), four neighbouring holders are gathered into one
 // lane and that lane sends the 16-byte chunk (p, 4 outputs) to every CTA of the cluster.  NV = 4, 8 or 16.
+// Remote addresses: the shared::cluster window of CTA r is the window of CTA 0 shifted by r * stride (checked
+// once per kernel by cl_window_stride), so one mapa per exchange replaces one per destination.
+__device__ __forceinline__ uint32_t cl_window_stride(uint32_t probe_saddr, int C) {
+    const uint32_t a0 = cl_mapa(probe_saddr, 0);
+    const uint32_t stride = cl_mapa(probe_saddr, 1) - a0;
+    for (int r = 2; r < C; ++r)
+        if (cl_mapa(probe_saddr, r) != a0 + (uint32_t)r * stride) __trap();
+    return stride;
+}
+
 template <int C, int NV>
 __device__ __forceinline__ void cl_narrow_send(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
-                                               uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
+                                               uint32_t inbox_saddr, uint32_t bar_saddr, int rank, uint32_t wstride) {
     const int lane = threadIdx.x & 31;
     float pr[NV];
 #pragma unroll
@@ -380,17 +390,22 @@ __device__ __forceinline__ void cl_narrow_send(float v, const float *__restrict_
         if (4 * chunk < nN) {
             const float4 out = make_float4(pr[0], q1, q2, q3);
             const uint32_t off = (uint32_t)(rank * CL_INBOX + p * CL_NO + 4 * chunk) * 4u;
+            const uint32_t a0 = cl_mapa(inbox_saddr + off, 0), b0 = cl_mapa(bar_saddr, 0);
 #pragma unroll
-            for (int dst = 0; dst < C; ++dst) cl_st_async_v4(cl_mapa(inbox_saddr + off, dst), out, cl_mapa(bar_saddr, dst));
+            for (int dst = 0; dst < C; ++dst) cl_st_async_v4(a0 + (uint32_t)dst * wstride, out, b0 + (uint32_t)dst * wstride);
         }
     }
 }
 template <int C>
 __device__ __forceinline__ void cl_narrow_send_any(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
-                                                   uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
-    if (nN <= 4) cl_narrow_send<C, 4>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
-    else if (nN <= 8) cl_narrow_send<C, 8>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
-    else cl_narrow_send<C, 16>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank);
+                                                   uint32_t inbox_saddr, uint32_t bar_saddr, int rank, uint32_t wstride) {
+    if (nN <= 4) cl_narrow_send<C, 4>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
+    else if (nN <= 8) cl_narrow_send<C, 8>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
+    else cl_narrow_send<C, 16>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
+}
+// element (row j, particle slot p) of the swizzled act tile written by cl_store_act
+__device__ __forceinline__ float cl_act_at(const float *act, int j, int p) {
+    return act[j * CL_PS + ((((p >> 2) ^ (j >> 2)) & 1) << 2) + (p & 3)];
 }
 // value (p, o) from the inbox written by cl_narrow_send: C partials added in rank order
 template <int C>

@@ -100,7 +100,7 @@ struct BwdNetRegs {
     const float *gt_ptr, *gw_ptr;    // global: stored activations that gate the adjoints (next step to fetch)
     float *dl_thin, *dl_wide;        // global: policy adjoints kept for the weight gradient (current step)
     size_t thin_step, wide_step;
-    int tW, tK;
+    int tW, tK, tcol;
     __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int n0,
                                          int nval, bool store) {
         const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
@@ -111,10 +111,12 @@ struct BwdNetRegs {
         tw = smem + n.s_tw + tid;
         tmk = smem + n.s_tm + tid;
         tkinv = n.tkeep_inv;
-        thin_store = store && thin_on && tid >= rank * n.tsl && tid < (rank + 1) * n.tsl;
+        // the thin output is stored by warp = particle slot, lane = column of this CTA's share of the columns
+        tcol = rank * n.tsl + lane;
+        thin_store = store && p < nval && lane < n.tsl && tcol < n.tW;
         thin_step = (size_t)N * n.tW;
         gt_ptr = prm.ws + n.tsav_off + ((size_t)(H - 1) * N + n0) * n.tW + tid;
-        dl_thin = store ? prm.ws + n.tdel_off + ((size_t)(H - 1) * N + n0) * n.tW + tid : nullptr;
+        dl_thin = store ? prm.ws + n.tdel_off + ((size_t)(H - 1) * N + n0 + p) * n.tW + tcol : nullptr;
         const int gc = rank * n.hs + lane;
         wide_on = lane < n.hs && gc < n.wN;
         wmk = wide_on ? smem[n.s_wm + p * n.hs + lane] * n.wkeep_inv : 0.f;
@@ -135,7 +137,8 @@ struct BwdNetRegs {
 template <int C, bool kStore>
 __device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const CNet &n, BwdNetRegs &R, float *smem,
                                                 const float *x, const float (&gtf)[CL_PS], float gwf, int nval, int rank,
-                                                uint32_t inbox_saddr, uint32_t bar_saddr, bool dbg_step, int mark0) {
+                                                uint32_t inbox_saddr, uint32_t bar_saddr, uint32_t wstride, bool dbg_step,
+                                                int mark0) {
     float *act = smem + prm.off_act, *red = smem + prm.off_red;
     // ---- thin: adjoint of hidden 1 = (dout W2) * gate ----
     if (R.thin_on) {
@@ -163,15 +166,13 @@ __device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const 
             v[2 * h + 1] = acc[h].y * gtf[2 * h + 1];
         }
         cl_store_act(act, threadIdx.x, v);
-        if (kStore && R.thin_store) {
-#pragma unroll
-            for (int p = 0; p < CL_PS; ++p)
-                if (p < nval) R.dl_thin[(size_t)p * R.tW] = v[p];
-        }
     }
-    if (kStore) R.dl_thin -= R.thin_step;
     CL_TMARK(mark0);
     __syncthreads();
+    if (kStore) {       // adjoint of hidden 1, kept for the weight gradient: one coalesced row segment per warp
+        if (R.thin_store) *R.dl_thin = cl_act_at(act, R.tcol, threadIdx.x >> 5);
+        R.dl_thin -= R.thin_step;
+    }
     // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the warps ----
     cl_wide_accum2(smem + n.s_ww, n.tW, n.hs, act, red);
     CL_TMARK(mark0 + 1);
@@ -183,7 +184,7 @@ __device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const 
             if (R.wide_store) *R.dl_wide = v;
             R.dl_wide -= R.wide_step;
         }
-        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank);
+        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank, wstride);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     };
     const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
     const uint32_t bar_dyn = smem_u32(&xbar[0]), bar_pol = smem_u32(&xbar[1]);
+    const uint32_t wstride = cl_window_stride(bar_dyn, C);
     float *odel_ptr = nullptr;          // role X (action dims): adjoint of the policy outputs of the current step
     if (roleX && x_k >= D) odel_ptr = prm.ws + pol.odel_off + ((size_t)(H - 1) * N + min(n0 + x_p, N - 1)) * pol.nraw + (x_k - D);
     const size_t odel_step = (size_t)N * pol.nraw;
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         CL_TMARK(33);
         __syncthreads();
         // ================= dynamics net =================
-        cl_net_backward<C, false>(prm, dyn, Rd, smem, xd, gtf_dyn, gwf_dyn, nval, rank, inbox_saddr, bar_dyn, dbg_step, 34);
+        cl_net_backward<C, false>(prm, dyn, Rd, smem, xd, gtf_dyn, gwf_dyn, nval, rank, inbox_saddr, bar_dyn, wstride, dbg_step, 34);
         if (roleX) {
             // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
             //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         __syncthreads();
         // ================= policy net =================
         cl_net_backward<C, true>(prm, pol, Rp, smem, xp, gtf_pol, gwf_pol, nval, rank,
-                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, dbg_step, 38);
+                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, wstride, dbg_step, 38);
         if (roleB) {
             // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
             mbar_wait(&xbar[1], par);

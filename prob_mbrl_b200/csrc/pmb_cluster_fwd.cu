@@ -23,6 +23,7 @@ struct FwdNetRegs {
     bool thin_on, thin_store, wide_on, wide_store, send_ok;
     float *sv_thin, *sv_wide;       // running global pointers of the stored activations (advance per step)
     size_t thin_step, wide_step;
+    int tK, tcol;
     __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int n0,
                                          int nval) {
         const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
@@ -32,8 +33,11 @@ struct FwdNetRegs {
         tb = thin_on ? smem[n.s_tb + tid] : 0.f;
 #pragma unroll
         for (int q = 0; q < CL_PS; ++q) tmk[q] = thin_on ? smem[n.s_tm + q * n.tW + tid] * n.tkeep_inv : 0.f;
-        thin_store = thin_on && tid >= rank * n.tsl && tid < (rank + 1) * n.tsl;
-        sv_thin = prm.ws + n.tsav_off + (size_t)n0 * n.tW + tid;
+        tK = n.tK;
+        // the thin output is stored by warp = particle slot, lane = column of this CTA's share of the columns
+        tcol = rank * n.tsl + lane;
+        thin_store = p < nval && lane < n.tsl && tcol < n.tW;
+        sv_thin = prm.ws + n.tsav_off + (size_t)(n0 + p) * n.tW + tcol;
         thin_step = (size_t)prm.N * n.tW;
         const int gc = rank * n.hs + lane;
         wide_on = lane < n.hs;
@@ -52,7 +56,7 @@ struct FwdNetRegs {
 template <int C, int TK>
 __device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const CNet &n, FwdNetRegs<TK> &R, float *smem,
                                                const float *x, int nval, int rank, uint32_t inbox_saddr,
-                                               uint32_t bar_saddr, bool dbg_step, int mark0) {
+                                               uint32_t bar_saddr, uint32_t wstride, bool dbg_step, int mark0) {
     float *act = smem + prm.off_act, *red = smem + prm.off_red;
     // ---- thin: hidden 0 = relu(x W0^T + b0) * mask0 / keep0 (full width, every CTA) ----
     if (R.thin_on) {
@@ -61,12 +65,14 @@ __device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const C
         for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(x + k * CL_PS);
-            const float4 x1 = *reinterpret_cast<const float4 *>(x + k * CL_PS + 4);
-            acc[0] = cl_fma2(R.tw[k], make_float2(x0.x, x0.y), acc[0]);
-            acc[1] = cl_fma2(R.tw[k], make_float2(x0.z, x0.w), acc[1]);
-            acc[2] = cl_fma2(R.tw[k], make_float2(x1.x, x1.y), acc[2]);
-            acc[3] = cl_fma2(R.tw[k], make_float2(x1.z, x1.w), acc[3]);
+            if (k < R.tK) {         // uniform: rows >= tK are zero padding
+                const float4 x0 = *reinterpret_cast<const float4 *>(x + k * CL_PS);
+                const float4 x1 = *reinterpret_cast<const float4 *>(x + k * CL_PS + 4);
+                acc[0] = cl_fma2(R.tw[k], make_float2(x0.x, x0.y), acc[0]);
+                acc[1] = cl_fma2(R.tw[k], make_float2(x0.z, x0.w), acc[1]);
+                acc[2] = cl_fma2(R.tw[k], make_float2(x1.x, x1.y), acc[2]);
+                acc[3] = cl_fma2(R.tw[k], make_float2(x1.z, x1.w), acc[3]);
+            }
         }
         float v[CL_PS];
 #pragma unroll
@@ -77,16 +83,12 @@ __device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const C
 #pragma unroll
         for (int p = 0; p < CL_PS; ++p) v[p] = fmaxf(v[p], 0.f) * R.tmk[p];
         cl_store_act(act, threadIdx.x, v);
-        if (R.thin_store) {
-            const int tW = n.tW;
-#pragma unroll
-            for (int p = 0; p < CL_PS; ++p)
-                if (p < nval) R.sv_thin[(size_t)p * tW] = v[p];
-        }
     }
-    R.sv_thin += R.thin_step;
     CL_TMARK(mark0);
     __syncthreads();
+    // hidden 0 is kept for the reverse sweep: one coalesced row segment per warp (= particle slot), off the tile
+    if (R.thin_store) *R.sv_thin = cl_act_at(act, R.tcol, threadIdx.x >> 5);
+    R.sv_thin += R.thin_step;
     // ---- wide: this CTA's columns of hidden 1, k-split over the warps ----
     cl_wide_accum2(smem + n.s_ww, n.tW, n.hs, act, red);
     CL_TMARK(mark0 + 1);
@@ -97,7 +99,7 @@ __device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const C
         v = fmaxf(v + R.wb, 0.f) * R.wmk;           // idle lanes: wb = wmk = 0 and red holds zeros
         if (R.wide_store) *R.sv_wide = v;
         R.sv_wide += R.wide_step;
-        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank);
+        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank, wstride);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     if (roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)b_n * D + b_d);
     const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
     const uint32_t bar_pol = smem_u32(&xbar[0]), bar_dyn = smem_u32(&xbar[1]);
+    const uint32_t wstride = cl_window_stride(bar_pol, C);
     // running global pointers of the role threads (advance per step)
     float *act_ptr = prm.actions + (size_t)a_n * U + a_u;
     float *rawp_ptr = prm.ws + pol.raw_off + (size_t)a_n * pol.nraw + a_u;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
 
         // ================= policy =================
-        cl_net_forward<C, TK>(prm, pol, Rp, smem, xpol, nval, rank, inbox_saddr, bar_pol, dbg_step, 1);
+        cl_net_forward<C, TK>(prm, pol, Rp, smem, xpol, nval, rank, inbox_saddr, bar_pol, wstride, dbg_step, 1);
         if (roleA) {
             // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243) ----
             mbar_wait(&xbar[0], par);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
 
         // ================= dynamics =================
         cl_net_forward<C, TK>(prm, dyn, Rd, smem, xdyn, nval, rank, inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_dyn,
-                              dbg_step, 5);
+                              wstride, dbg_step, 5);
         if (roleB) {
             // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
             mbar_wait(&xbar[1], par);
