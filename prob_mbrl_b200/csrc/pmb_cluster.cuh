@@ -26,6 +26,9 @@ constexpr int CL_HS = 32;      // widest column slice per CTA
 constexpr int CL_TW = 256;     // widest thin layer (= K of the wide layer)
 constexpr int CL_NO = 16;      // narrow outputs / thin inputs (max)
 constexpr int CL_INBOX = CL_PS * CL_NO;   // floats one CTA sends per exchange (max)
+constexpr int CL_TS = 4;                  // particle slots per tile (= warps per warp group; two tiles per cluster)
+constexpr int CL_GT = 128;                // threads per warp group
+constexpr int CL_MBOX = CL_TS * CL_NO;    // floats one (CTA, group) sends per exchange
 
 // One net in one direction.
 struct CNet {
@@ -110,8 +113,13 @@ __device__ __forceinline__ float2 cl_fma2(float a, float2 w, float2 c) {
 // resident operands of one net: thin matrix, this CTA's column slice of the wide and narrow matrices,
 // biases (forward), the cluster's rows of the dropout masks (1.0 where the layer has no mask)
 // ----------------------------------------------------------------------------------------
+// Mask rows are indexed by the cluster's particle slot q: tile 0 = slots 0..3 holds the particles n0 .. n0+nv0-1,
+// tile 1 = slots 4..7 the particles n0+nv0 ...; slots past the tile's share repeat a valid particle.
+__device__ __forceinline__ int cl_slot_particle(int q, int n0, int nv0, int N) {
+    return min(n0 + (q < CL_TS ? q : nv0 + q - CL_TS), N - 1);
+}
 __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet &n, float *smem, int rank, int n0,
-                                            bool fwd) {
+                                            int nv0, bool fwd) {
     const int tid = threadIdx.x;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     {
@@ -151,12 +159,12 @@ __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet
     }
     for (int i = tid; i < CL_PS * n.tW; i += CL_NT) {
         const int p = i / n.tW, j = i - p * n.tW;
-        const int nn = min(n0 + p, prm.N - 1);
+        const int nn = cl_slot_particle(p, n0, nv0, prm.N);
         smem[n.s_tm + i] = n.tm_off >= 0 ? __ldg(prm.ws + n.tm_off + (long long)nn * n.tW + j) : 1.f;
     }
     for (int i = tid; i < CL_PS * n.hs; i += CL_NT) {
         const int p = i / n.hs, c = i - p * n.hs;
-        const int nn = min(n0 + p, prm.N - 1);
+        const int nn = cl_slot_particle(p, n0, nv0, prm.N);
         const int gc = rank * n.hs + c;
         float v = 0.f;
         if (gc < n.wN) v = n.wm_off >= 0 ? __ldg(prm.ws + n.wm_off + (long long)nn * n.wN + gc) : 1.f;
@@ -165,141 +173,28 @@ __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet
 }
 
 // ----------------------------------------------------------------------------------------
-// thin layer: thread = output column j, all 8 particle slots; x is the [tK][8] input tile.
-// acc[h] holds the particle pairs (2h, 2h+1).  epi(j, acc) finishes column j.
+// Two independent particle tiles per CTA.  The 8 warps of a CTA form two groups of 4 warps; group g of every
+// CTA of the cluster works on the cluster's particle slots [4g, 4g+4) and never synchronises with the other
+// group (named barrier 1+g, its own exchange mailboxes and mbarriers): while one group waits on a barrier, on
+// the exchange or on a dependent-latency chain, the other group's warps keep the LSU / FMA pipes busy.  Both
+// groups read the same resident weights.
 // ----------------------------------------------------------------------------------------
-template <typename Epi>
-__device__ __forceinline__ void cl_thin(const float *__restrict__ tw, int tK, int tW, const float *__restrict__ x, Epi epi) {
-#pragma unroll 1
-    for (int j = threadIdx.x; j < tW; j += CL_NT) {
-        float2 acc[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
-#pragma unroll 4
-        for (int k = 0; k < tK; ++k) {
-            const float w = tw[k * tW + j];
-            const float4 x0 = *reinterpret_cast<const float4 *>(x + k * CL_PS);
-            const float4 x1 = *reinterpret_cast<const float4 *>(x + k * CL_PS + 4);
-            acc[0] = cl_fma2(w, make_float2(x0.x, x0.y), acc[0]);
-            acc[1] = cl_fma2(w, make_float2(x0.z, x0.w), acc[1]);
-            acc[2] = cl_fma2(w, make_float2(x1.x, x1.y), acc[2]);
-            acc[3] = cl_fma2(w, make_float2(x1.z, x1.w), acc[3]);
-        }
-        epi(j, acc);
-    }
-}
-// the thin output is the wide layer's input tile act[k][8]; the two 4-particle halves of a row are swapped
-// on rows with bit 2 set so that a warp's 16-byte stores of consecutive rows hit distinct banks
-__device__ __forceinline__ void cl_store_act(float *act, int j, const float (&v)[CL_PS]) {
-    const int sw = (j >> 2) & 1;
-    *reinterpret_cast<float4 *>(act + j * CL_PS + (sw << 2)) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4 *>(act + j * CL_PS + ((sw ^ 1) << 2)) = make_float4(v[4], v[5], v[6], v[7]);
-}
+#define CT_SYNC(g) asm volatile("bar.sync %0, 128;" ::"r"((g) + 2) : "memory")   // barriers 2, 3 (0, 1 = whole CTA)
 
-// ----------------------------------------------------------------------------------------
-// wide layer, this CTA's column slice: warp w takes the rows k = w, w+8, ... (8-way k-split); lane = (column
-// quad q, particle pair pp).  Per row one LDS.128 of weights + one LDS.64 of activations feed 4 FFMA2.
-// The partial sums go to red[w][p][32]; cl_wide_reduce (after a barrier) returns the finished value of
-// (particle = warp, column = lane).
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void cl_wide_accum(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
-                                              float *__restrict__ red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = lane >> 2, pp = lane & 3;
+// wide layer, this CTA's column slice, one 4-slot tile: 8 k-slices = (warp of the group, half-warp); lane =
+// (row half, column quad q, slot pair pp).  Per row one LDS.128 of weights + one LDS.64 of activations feed
+// 4 FFMA2; two rows in flight per thread.  Partial sums go to red[slice][slot][32].
+__device__ __forceinline__ void ct_wide_accum(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
+                                              float *__restrict__ red, int gtid) {
+    const int lane = gtid & 31, w = gtid >> 5;
+    const int q = (lane >> 1) & 7, pp = lane & 1;
     if (4 * q >= hs) return;
-    float2 a00 = make_float2(0.f, 0.f), a01 = a00, a10 = a00, a11 = a00;
-    const int sw = (warp >> 2) & 1;           // swizzle bit of every row this warp visits
-    const float *wp = ww + warp * hs + 4 * q;
-    const float *ap = act + warp * CL_PS + ((((pp >> 1) ^ sw)) << 2) + ((pp & 1) << 1);
-    const int n = (K - warp + 7) >> 3;
-    const int wstride = 8 * hs;
-#pragma unroll 5
-    for (int i = 0; i < n; ++i) {
-        const float4 w = *reinterpret_cast<const float4 *>(wp);
-        const float2 a = *reinterpret_cast<const float2 *>(ap);
-        wp += wstride;
-        ap += 8 * CL_PS;
-        a00 = cl_fma2(a.x, make_float2(w.x, w.y), a00);
-        a01 = cl_fma2(a.x, make_float2(w.z, w.w), a01);
-        a10 = cl_fma2(a.y, make_float2(w.x, w.y), a10);
-        a11 = cl_fma2(a.y, make_float2(w.z, w.w), a11);
-    }
-    float *r = red + ((warp * CL_PS + 2 * pp) << 5) + 4 * q;
-    *reinterpret_cast<float4 *>(r) = make_float4(a00.x, a00.y, a01.x, a01.y);
-    *reinterpret_cast<float4 *>(r + 32) = make_float4(a10.x, a10.y, a11.x, a11.y);
-}
-__device__ __forceinline__ float cl_wide_reduce(const float *__restrict__ red) {
-    const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    const float *r = red + (p << 5) + lane;
-    float s0 = r[0], s1 = r[1 * CL_PS * 32], s2 = r[2 * CL_PS * 32], s3 = r[3 * CL_PS * 32];
-    s0 += r[4 * CL_PS * 32];
-    s1 += r[5 * CL_PS * 32];
-    s2 += r[6 * CL_PS * 32];
-    s3 += r[7 * CL_PS * 32];
-    return (s0 + s1) + (s2 + s3);
-}
-
-// narrow layer over this CTA's columns: thread (p = tid >> 4, o = tid & 15) forms
-// part[p * nNp + o] = sum_c h2s[p][c] * nw[o][c]   (c < hs)
-__device__ __forceinline__ void cl_narrow_partial(const float *__restrict__ nw, int hs, int nN, int nNp,
-                                                  const float *__restrict__ h2s, float *__restrict__ part) {
-    const int tid = threadIdx.x;
-    if (tid >= CL_PS * CL_NO) return;
-    const int p = tid >> 4, o = tid & 15;
-    if (o >= nNp) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (o < nN) {
-        const float *hp = h2s + (p << 5);
-        const float *wp = nw + o * hs;
-        for (int c = 0; c < hs; c += 4) {
-            const float4 h = *reinterpret_cast<const float4 *>(hp + c);
-            const float4 w = *reinterpret_cast<const float4 *>(wp + c);
-            s0 = fmaf(h.x, w.x, s0);
-            s1 = fmaf(h.y, w.y, s1);
-            s2 = fmaf(h.z, w.z, s2);
-            s3 = fmaf(h.w, w.w, s3);
-        }
-    }
-    part[p * nNp + o] = (s0 + s1) + (s2 + s3);
-}
-
-// send this CTA's partials to every CTA of the cluster (its own included): warp w serves the destination
-// ranks w, w+8, ...; 16 bytes per st.async, inbox slot = sender's rank.
-template <int C>
-__device__ __forceinline__ void cl_send(const float *part, int nchunks, uint32_t inbox_saddr, uint32_t bar_saddr, int rank) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int dst = warp; dst < C; dst += CL_NT / 32) {
-        const uint32_t dbar = cl_mapa(bar_saddr, dst);
-        const uint32_t dbase = cl_mapa(inbox_saddr + (uint32_t)(rank * CL_INBOX) * 4u, dst);
-        for (int ch = lane; ch < nchunks; ch += 32)
-            cl_st_async_v4(dbase + (uint32_t)ch * 16u, *reinterpret_cast<const float4 *>(part + 4 * ch), dbar);
-    }
-}
-// sum of the C partials of value `idx` in rank order
-template <int C>
-__device__ __forceinline__ float cl_gather(const float *inbox, int idx) {
-    float s = inbox[idx];
-#pragma unroll
-    for (int r = 1; r < C; ++r) s += inbox[r * CL_INBOX + idx];
-    return s;
-}
-
-// ----------------------------------------------------------------------------------------
-// v2 building blocks
-// ----------------------------------------------------------------------------------------
-// wide layer with two independent accumulator sets per thread (rows i and i+1 of the warp's k-slice)
-__device__ __forceinline__ void cl_wide_accum2(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
-                                               float *__restrict__ red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = lane >> 2, pp = lane & 3;
-    if (4 * q >= hs) return;
+    const int slice = 2 * w + (lane >> 4);
     const float2 z2 = make_float2(0.f, 0.f);
     float2 a00 = z2, a01 = z2, a10 = z2, a11 = z2, b00 = z2, b01 = z2, b10 = z2, b11 = z2;
-    const int sw = (warp >> 2) & 1;           // swizzle bit of every row this warp visits
-    const float *wp = ww + warp * hs + 4 * q;
-    const float *ap = act + warp * CL_PS + ((((pp >> 1) ^ sw)) << 2) + ((pp & 1) << 1);
-    const int n = (K - warp + 7) >> 3;
+    const float *wp = ww + slice * hs + 4 * q;
+    const float *ap = act + slice * CL_TS + 2 * pp;
+    const int n = (K - slice + 7) >> 3;
     const int wstride = 8 * hs;
     int i = 0;
 #pragma unroll 3
@@ -307,9 +202,9 @@ __device__ __forceinline__ void cl_wide_accum2(const float *__restrict__ ww, int
         const float4 w0 = *reinterpret_cast<const float4 *>(wp);
         const float2 x0 = *reinterpret_cast<const float2 *>(ap);
         const float4 w1 = *reinterpret_cast<const float4 *>(wp + wstride);
-        const float2 x1 = *reinterpret_cast<const float2 *>(ap + 8 * CL_PS);
+        const float2 x1 = *reinterpret_cast<const float2 *>(ap + 8 * CL_TS);
         wp += 2 * wstride;
-        ap += 16 * CL_PS;
+        ap += 16 * CL_TS;
         a00 = cl_fma2(x0.x, make_float2(w0.x, w0.y), a00);
         a01 = cl_fma2(x0.x, make_float2(w0.z, w0.w), a01);
         a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
@@ -327,25 +222,23 @@ __device__ __forceinline__ void cl_wide_accum2(const float *__restrict__ ww, int
         a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
         a11 = cl_fma2(x0.y, make_float2(w0.z, w0.w), a11);
     }
-    float *r = red + ((warp * CL_PS + 2 * pp) << 5) + 4 * q;
+    float *r = red + ((slice * CL_TS + 2 * pp) << 5) + 4 * q;
     *reinterpret_cast<float4 *>(r) = make_float4(a00.x + b00.x, a00.y + b00.y, a01.x + b01.x, a01.y + b01.y);
     *reinterpret_cast<float4 *>(r + 32) = make_float4(a10.x + b10.x, a10.y + b10.y, a11.x + b11.x, a11.y + b11.y);
 }
-
-// 16-byte / 4-byte remote stores used by the exchange
-__device__ __forceinline__ void cl_st_async_b32(uint32_t daddr, float v, uint32_t dbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(daddr),
-                 "r"(__float_as_uint(v)), "r"(dbar)
-                 : "memory");
+// finished value of (slot = warp of the group, column = lane): the 8 k-slices in a fixed order
+__device__ __forceinline__ float ct_wide_reduce(const float *__restrict__ red, int gtid) {
+    const float *r = red + ((gtid >> 5) << 5) + (gtid & 31);
+    float s0 = r[0], s1 = r[1 * CL_TS * 32], s2 = r[2 * CL_TS * 32], s3 = r[3 * CL_TS * 32];
+    s0 += r[4 * CL_TS * 32];
+    s1 += r[5 * CL_TS * 32];
+    s2 += r[6 * CL_TS * 32];
+    s3 += r[7 * CL_TS * 32];
+    return (s0 + s1) + (s2 + s3);
 }
 
-// Narrow layer + exchange fused into the wide layer's epilogue.  Warp = particle slot p, lane = column of this
-// CTA's slice; `v` is the lane's finished hidden value (0 on idle lanes).  The warp forms
-//   out[o] = sum_lanes v * nw[o][lane]   for o < NV
-// with a reduce-scatter butterfly (NV values per lane -> 1), four neighbouring holders are gathered into one
-// lane and that lane sends the 16-byte chunk (p, 4 outputs) to every CTA of the cluster.  NV = 4, 8 or 16.
-// Remote addresses: the shared::cluster window of CTA r is the window of CTA 0 shifted by r * stride (checked
-// once per kernel by cl_window_stride), so one mapa per exchange replaces one per destination.
+// The shared::cluster window of CTA r is the window of CTA 0 shifted by r * stride (checked once per kernel),
+// so one mapa per exchange replaces one per destination.
 __device__ __forceinline__ uint32_t cl_window_stride(uint32_t probe_saddr, int C) {
     const uint32_t a0 = cl_mapa(probe_saddr, 0);
     const uint32_t stride = cl_mapa(probe_saddr, 1) - a0;
@@ -354,9 +247,18 @@ __device__ __forceinline__ uint32_t cl_window_stride(uint32_t probe_saddr, int C
     return stride;
 }
 
+// Narrow layer + exchange fused into the wide layer's epilogue.  Warp = particle slot, lane = column of this
+// CTA's slice; `v` is the lane's finished hidden value (0 on idle lanes).  The warp forms
+//   out[o] = sum_lanes v * nw[o][lane]   for o < NV
+// with a reduce-scatter butterfly (NV values per lane -> 1), four neighbouring holders are gathered into one
+// lane and that lane sends the 16-byte chunk (slot, 4 outputs) to every CTA of the cluster: st.async = DSMEM
+// store + complete_tx on the destination's mbarrier in one instruction.  NV = 4, 8 or 16.
+//   mbox_saddr : this (group, exchange)'s mailbox [C ranks][CL_MBOX] (same offset in every CTA)
+//   slot_off   : byte offset of (sender rank, slot) inside the mailbox
 template <int C, int NV>
-__device__ __forceinline__ void cl_narrow_send(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
-                                               uint32_t inbox_saddr, uint32_t bar_saddr, int rank, uint32_t wstride) {
+__device__ __forceinline__ void ct_narrow_send(float v, const float *__restrict__ nwt, bool send_ok, int nN,
+                                               uint32_t mbox_saddr, uint32_t slot_off, uint32_t bar_saddr,
+                                               uint32_t wstride) {
     const int lane = threadIdx.x & 31;
     float pr[NV];
 #pragma unroll
@@ -389,31 +291,27 @@ __device__ __forceinline__ void cl_narrow_send(float v, const float *__restrict_
         const int chunk = lane / (4 * s);
         if (4 * chunk < nN) {
             const float4 out = make_float4(pr[0], q1, q2, q3);
-            const uint32_t off = (uint32_t)(rank * CL_INBOX + p * CL_NO + 4 * chunk) * 4u;
-            const uint32_t a0 = cl_mapa(inbox_saddr + off, 0), b0 = cl_mapa(bar_saddr, 0);
+            const uint32_t a0 = cl_mapa(mbox_saddr + slot_off + (uint32_t)chunk * 16u, 0), b0 = cl_mapa(bar_saddr, 0);
 #pragma unroll
             for (int dst = 0; dst < C; ++dst) cl_st_async_v4(a0 + (uint32_t)dst * wstride, out, b0 + (uint32_t)dst * wstride);
         }
     }
 }
 template <int C>
-__device__ __forceinline__ void cl_narrow_send_any(float v, const float *__restrict__ nwt, int p, bool send_ok, int nN,
-                                                   uint32_t inbox_saddr, uint32_t bar_saddr, int rank, uint32_t wstride) {
-    if (nN <= 4) cl_narrow_send<C, 4>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
-    else if (nN <= 8) cl_narrow_send<C, 8>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
-    else cl_narrow_send<C, 16>(v, nwt, p, send_ok, nN, inbox_saddr, bar_saddr, rank, wstride);
+__device__ __forceinline__ void ct_narrow_send_any(float v, const float *__restrict__ nwt, bool send_ok, int nN,
+                                                   uint32_t mbox_saddr, uint32_t slot_off, uint32_t bar_saddr,
+                                                   uint32_t wstride) {
+    if (nN <= 4) ct_narrow_send<C, 4>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
+    else if (nN <= 8) ct_narrow_send<C, 8>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
+    else ct_narrow_send<C, 16>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
 }
-// element (row j, particle slot p) of the swizzled act tile written by cl_store_act
-__device__ __forceinline__ float cl_act_at(const float *act, int j, int p) {
-    return act[j * CL_PS + ((((p >> 2) ^ (j >> 2)) & 1) << 2) + (p & 3)];
-}
-// value (p, o) from the inbox written by cl_narrow_send: C partials added in rank order
+// value (slot, o) from a mailbox: the C partials added in rank order (identical on every CTA)
 template <int C>
-__device__ __forceinline__ float cl_gather2(const float *inbox, int p, int o) {
-    const float *q = inbox + p * CL_NO + o;
+__device__ __forceinline__ float ct_gather(const float *mbox, int slot, int o) {
+    const float *q = mbox + slot * CL_NO + o;
     float s = q[0];
 #pragma unroll
-    for (int r = 1; r < C; ++r) s += q[r * CL_INBOX];
+    for (int r = 1; r < C; ++r) s += q[r * CL_MBOX];
     return s;
 }
 

@@ -89,102 +89,101 @@ __global__ void __launch_bounds__(256) cluster_bwd_pre_kernel(const __grid_const
     }
 }
 
-// Per-thread constants and running pointers of one net's adjoint pass.
-//   thin layer : thread = column tid of hidden 1;  epilogue of the wide layer: thread = (slot = warp, column = lane)
+// Per-thread constants and running pointers of one net's adjoint pass (one particle tile = one warp group).
+//   thin layer : thread gtid owns the columns gtid and gtid + 128 of hidden 1
+//   epilogue of the wide layer: thread = (slot = warp of the group, column = lane of this CTA's slice)
 struct BwdNetRegs {
-    bool thin_on, thin_store, wide_on, wide_store, send_ok;
+    bool on0, on1, thin_store, wide_on, wide_store, send_ok;
     float wmk;                       // mask / keep of (slot, column) of hidden 0
-    const float *tw;                 // smem: thin matrix, column of this thread
-    const float *tmk;                // smem: mask rows of hidden 1, column of this thread
+    const float *tw;                 // smem: thin matrix, column gtid (second column: + 128)
+    const float *tmk;                // smem: mask rows of hidden 1 for the tile's slots, column gtid
     float tkinv;
     const float *gt_ptr, *gw_ptr;    // global: stored activations that gate the adjoints (next step to fetch)
     float *dl_thin, *dl_wide;        // global: policy adjoints kept for the weight gradient (current step)
     size_t thin_step, wide_step;
     int tW, tK, tcol;
-    __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int n0,
-                                         int nval, bool store) {
-        const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
+    uint32_t slot_off;
+    __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int g,
+                                         int gtid, int n0g, int nvg, bool store) {
+        const int lane = gtid & 31, sl = gtid >> 5;
+        const int ps = g * CL_TS + sl;
         const int H = prm.H, N = prm.N;
         tW = n.tW;
         tK = n.tK;
-        thin_on = tid < n.tW;
-        tw = smem + n.s_tw + tid;
-        tmk = smem + n.s_tm + tid;
+        on0 = gtid < n.tW;
+        on1 = gtid + CL_GT < n.tW;
+        tw = smem + n.s_tw + gtid;
+        tmk = smem + n.s_tm + (g * CL_TS) * n.tW + gtid;
         tkinv = n.tkeep_inv;
-        // the thin output is stored by warp = particle slot, lane = column of this CTA's share of the columns
         tcol = rank * n.tsl + lane;
-        thin_store = store && p < nval && lane < n.tsl && tcol < n.tW;
+        thin_store = store && sl < nvg && lane < n.tsl && tcol < n.tW;
         thin_step = (size_t)N * n.tW;
-        gt_ptr = prm.ws + n.tsav_off + ((size_t)(H - 1) * N + n0) * n.tW + tid;
-        dl_thin = store ? prm.ws + n.tdel_off + ((size_t)(H - 1) * N + n0 + p) * n.tW + tcol : nullptr;
+        gt_ptr = prm.ws + n.tsav_off + ((size_t)(H - 1) * N + n0g) * n.tW + gtid;
+        dl_thin = store ? prm.ws + n.tdel_off + ((size_t)(H - 1) * N + n0g + sl) * n.tW + tcol : nullptr;
         const int gc = rank * n.hs + lane;
         wide_on = lane < n.hs && gc < n.wN;
-        wmk = wide_on ? smem[n.s_wm + p * n.hs + lane] * n.wkeep_inv : 0.f;
-        wide_store = store && wide_on && p < nval;
+        wmk = wide_on ? smem[n.s_wm + ps * n.hs + lane] * n.wkeep_inv : 0.f;
+        wide_store = store && wide_on && sl < nvg;
         wide_step = (size_t)N * n.wN;
-        const int np = min(n0 + p, N - 1);
+        const int np = min(n0g + sl, N - 1);
         gw_ptr = prm.ws + n.wsav_off + ((size_t)(H - 1) * N + np) * n.wN + gc;
-        dl_wide = store ? prm.ws + n.wdel_off + ((size_t)(H - 1) * N + n0 + p) * n.wN + gc : nullptr;
-        send_ok = p < prm.PG;
+        dl_wide = store ? prm.ws + n.wdel_off + ((size_t)(H - 1) * N + n0g + sl) * n.wN + gc : nullptr;
+        send_ok = sl < nvg;
+        slot_off = (uint32_t)(rank * CL_MBOX + sl * CL_NO) * 4u;
     }
 };
 
-// Adjoint pass through one net up to and including the send of the input-adjoint partials.
-//   x   : [tK][8] adjoint of the net's raw outputs
-//   gtf : per particle slot, (stored activation of hidden 1 != 0) ? mask / keep : 0   for column tid
+// Adjoint pass of one tile through one net up to and including the send of the input-adjoint partials.
+//   x   : [tK][4] adjoint of the net's raw outputs
+//   gtf : [column 0/1][slot] (stored activation of hidden 1 != 0) ? mask / keep : 0
 //   gwf : same for hidden 0 at (slot = warp, column = lane of this CTA's slice)
 // y = relu(pre) * mask / keep  =>  dpre = (dy / keep) * mask * [pre > 0];  y != 0 <=> pre > 0, mask != 0
 template <int C, bool kStore>
-__device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const CNet &n, BwdNetRegs &R, float *smem,
-                                                const float *x, const float (&gtf)[CL_PS], float gwf, int nval, int rank,
-                                                uint32_t inbox_saddr, uint32_t bar_saddr, uint32_t wstride, bool dbg_step,
-                                                int mark0) {
-    float *act = smem + prm.off_act, *red = smem + prm.off_red;
-    // ---- thin: adjoint of hidden 1 = (dout W2) * gate ----
-    if (R.thin_on) {
-        float2 acc[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
+__device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const CNet &n, BwdNetRegs &R, float *smem,
+                                                const float *x, float *act, float *red, const float (&gtf)[2][CL_TS],
+                                                float gwf, int g, int gtid, uint32_t mbox_saddr, uint32_t bar_saddr,
+                                                uint32_t wstride, bool dbg_step, int mark0) {
+    // ---- thin: adjoint of hidden 1 = (dout W2) * gate; two columns per thread ----
+    if (R.on0) {
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
         const float *wp = R.tw;
         const float *xp = x;
+        const int c1 = R.on1 ? CL_GT : 0;        // threads without a second column re-read the first (result unused)
 #pragma unroll 2
         for (int k = 0; k < R.tK; ++k) {
-            const float w = *wp;
-            const float4 x0 = *reinterpret_cast<const float4 *>(xp);
-            const float4 x1 = *reinterpret_cast<const float4 *>(xp + 4);
+            const float w0 = wp[0], w1 = wp[c1];
+            const float4 xv = *reinterpret_cast<const float4 *>(xp);
             wp += R.tW;
-            xp += CL_PS;
-            acc[0] = cl_fma2(w, make_float2(x0.x, x0.y), acc[0]);
-            acc[1] = cl_fma2(w, make_float2(x0.z, x0.w), acc[1]);
-            acc[2] = cl_fma2(w, make_float2(x1.x, x1.y), acc[2]);
-            acc[3] = cl_fma2(w, make_float2(x1.z, x1.w), acc[3]);
+            xp += CL_TS;
+            a0 = cl_fma2(w0, make_float2(xv.x, xv.y), a0);
+            a1 = cl_fma2(w0, make_float2(xv.z, xv.w), a1);
+            b0 = cl_fma2(w1, make_float2(xv.x, xv.y), b0);
+            b1 = cl_fma2(w1, make_float2(xv.z, xv.w), b1);
         }
-        float v[CL_PS];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            v[2 * h] = acc[h].x * gtf[2 * h];
-            v[2 * h + 1] = acc[h].y * gtf[2 * h + 1];
-        }
-        cl_store_act(act, threadIdx.x, v);
+        *reinterpret_cast<float4 *>(act + gtid * CL_TS) =
+            make_float4(a0.x * gtf[0][0], a0.y * gtf[0][1], a1.x * gtf[0][2], a1.y * gtf[0][3]);
+        if (R.on1)
+            *reinterpret_cast<float4 *>(act + (gtid + CL_GT) * CL_TS) =
+                make_float4(b0.x * gtf[1][0], b0.y * gtf[1][1], b1.x * gtf[1][2], b1.y * gtf[1][3]);
     }
     CL_TMARK(mark0);
-    __syncthreads();
+    CT_SYNC(g);
     if (kStore) {       // adjoint of hidden 1, kept for the weight gradient: one coalesced row segment per warp
-        if (R.thin_store) *R.dl_thin = cl_act_at(act, R.tcol, threadIdx.x >> 5);
+        if (R.thin_store) *R.dl_thin = act[R.tcol * CL_TS + (gtid >> 5)];
         R.dl_thin -= R.thin_step;
     }
-    // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the warps ----
-    cl_wide_accum2(smem + n.s_ww, n.tW, n.hs, act, red);
+    // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the half-warps of the group ----
+    ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
     CL_TMARK(mark0 + 1);
-    __syncthreads();
+    CT_SYNC(g);
     // ---- epilogue (warp = particle slot, lane = column) + partial sums of d(input) = delta_0 W_0 + exchange ----
     {
-        const float v = cl_wide_reduce(red) * gwf;      // idle lanes: gwf = 0 and red holds zeros
+        const float v = ct_wide_reduce(red, gtid) * gwf;      // idle lanes: gwf = 0 and red holds zeros
         if (kStore) {
             if (R.wide_store) *R.dl_wide = v;
             R.dl_wide -= R.wide_step;
         }
-        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank, wstride);
+        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -192,64 +191,70 @@ __device__ __forceinline__ void cl_net_backward(const ClusterParams &prm, const 
 template <int C>
 __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_constant__ ClusterParams prm) {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t xbar[2];          // [0] dynamics exchange, [1] policy exchange
+    __shared__ __align__(8) uint64_t xbar[2][2];       // [group][0 dynamics exchange, 1 policy exchange]
     const int tid = threadIdx.x;
+    const int g = tid >> 7, gtid = tid & (CL_GT - 1);
     const int rank = (int)cl_rank();
     const int PG = prm.PG;
     const int n0 = (int)cl_id_x() * PG;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
     const int nval = min(PG, N - n0);
+    const int nv0 = (nval + 1) >> 1;
+    const int n0g = n0 + (g ? nv0 : 0);
+    const int nvg = g ? nval - nv0 : nv0;
     const CNet &pol = prm.pol;
     const CNet &dyn = prm.dyn;
 
     for (int i = tid; i < prm.smem_floats; i += CL_NT) smem[i] = 0.f;
     __syncthreads();
-    float *xd = smem + prm.off_xa;         // [2D][8]  adjoint of the dynamics net's raw outputs
-    float *xp = smem + prm.off_xb;         // [2U][8]  adjoint of the policy net's raw outputs
-    float *misc = smem + prm.off_misc;
-    float *gs = misc, *gsp = misc + CBL;               // [8][SD] carried / partial state adjoint
-    const float *inbox_dyn = smem + prm.off_inbox;
-    const float *inbox_pol = inbox_dyn + C * CL_INBOX;
-    const uint32_t bytes_dyn = (uint32_t)(C * PG * dyn.nNp) * 4u, bytes_pol = (uint32_t)(C * PG * pol.nNp) * 4u;
-    if (tid == 0) {
-        mbar_init(&xbar[0], 1);
-        mbar_init(&xbar[1], 1);
+    const int tw_max = max(pol.tW, dyn.tW);
+    float *xd = smem + prm.off_xa + g * (CL_NO * CL_TS);       // [2D][4]  adjoint of the dynamics net's raw outputs
+    float *xp = smem + prm.off_xb + g * (CL_NO * CL_TS);       // [2U][4]  adjoint of the policy net's raw outputs
+    float *act = smem + prm.off_act + g * (tw_max * CL_TS);
+    float *red = smem + prm.off_red + g * (8 * CL_TS * 32);
+    float *gs = smem + prm.off_misc + g * (2 * CL_TS * SD), *gsp = gs + CL_TS * SD;   // [4][SD] carried / partial state adjoint
+    const float *mbox_dyn = smem + prm.off_inbox + g * (2 * C * CL_MBOX);
+    const float *mbox_pol = mbox_dyn + C * CL_MBOX;
+    const uint32_t bytes_dyn = (uint32_t)(C * nvg * dyn.nNp) * 4u, bytes_pol = (uint32_t)(C * nvg * pol.nNp) * 4u;
+    if (gtid == 0) {
+        mbar_init(&xbar[g][0], 1);
+        mbar_init(&xbar[g][1], 1);
         fence_mbar_init();
-        mbar_expect_tx(&xbar[0], bytes_dyn);
-        mbar_expect_tx(&xbar[1], bytes_pol);
+        mbar_expect_tx(&xbar[g][0], bytes_dyn);
+        mbar_expect_tx(&xbar[g][1], bytes_pol);
     }
-    cl_load_net(prm, dyn, smem, rank, n0, false);
-    cl_load_net(prm, pol, smem, rank, n0, false);
+    cl_load_net(prm, dyn, smem, rank, n0, nv0, false);
+    cl_load_net(prm, pol, smem, rank, n0, nv0, false);
     __syncthreads();
     BwdNetRegs Rd, Rp;
-    Rd.init(prm, dyn, smem, rank, n0, nval, false);
-    Rp.init(prm, pol, smem, rank, n0, nval, true);
+    Rd.init(prm, dyn, smem, rank, g, gtid, n0g, nvg, false);
+    Rp.init(prm, pol, smem, rank, g, gtid, n0g, nvg, true);
 
     // ---- thread roles (fixed for the whole horizon) ----
-    const bool roleA = tid < CL_PS * U;                       // (particle slot, action dim)
-    const int a_p = roleA ? tid / U : 0, a_u = roleA ? tid - a_p * U : 0;
-    const int a_n = min(n0 + a_p, N - 1);
-    const bool roleB = tid >= 128 && tid - 128 < CL_PS * D;   // (particle slot, state dim)
-    const int b_p = roleB ? (tid - 128) / D : 0, b_d = roleB ? (tid - 128) - b_p * D : 0;
-    const int b_n = min(n0 + b_p, N - 1);
-    const bool roleX = tid < CL_PS * (D + U);                 // (particle slot, dynamics-input dim)
-    const int x_p = roleX ? tid / (D + U) : 0, x_k = roleX ? tid - x_p * (D + U) : 0;
-    const bool x_own = roleX && x_p < nval && (x_p % C) == rank;
+    const bool roleB = gtid >= 64 && gtid - 64 < CL_TS * D;   // (particle slot, state dim)
+    const int b_p = roleB ? (gtid - 64) / D : 0, b_d = roleB ? (gtid - 64) - b_p * D : 0;
+    const int b_n = min(n0g + b_p, N - 1);
+    const bool roleX = gtid < CL_TS * (D + U);                // (particle slot, dynamics-input dim)
+    const int x_p = roleX ? gtid / (D + U) : 0, x_k = roleX ? gtid - x_p * (D + U) : 0;
+    const bool x_own = roleX && x_p < nvg && ((g * CL_TS + x_p) % C) == rank;
     const float x_isx = roleX ? prm.iSx[x_k] : 0.f;
     const float b_sy = roleB ? prm.Sy[b_d] : 0.f;
 
     if (roleB) gs[b_p * SD + b_d] = prm.g_states ? __ldg(prm.g_states + ((size_t)H * N + b_n) * D + b_d) : 0.f;
 
-    // step-local factors (bwd_pre_kernel) and gates, fetched one step ahead into registers
+    // step-local factors (cluster_bwd_pre_kernel) and gates, fetched one step ahead into registers
     const int PW = 2 * D + 3 * U;
-    const int x_n = min(n0 + x_p, N - 1);
+    const int x_n = min(n0g + x_p, N - 1);
     const bool xact = roleX && x_k >= D;
     float nx_rs = 0.f, nx_fd = 0.f, nx_gs = 0.f;        // role B (slot, state dim)
     float nx_ra = 0.f, nx_tp = 0.f, nx_fp = 0.f;        // role X, action dims
-    float pg_td[CL_PS], pg_tp[CL_PS];                   // stored activations of the next step
+    float pg_td[2][CL_TS], pg_tp[2][CL_TS];             // stored activations of the next step (thin columns)
     float pg_wd = 0.f, pg_wp = 0.f;
 #pragma unroll
-    for (int p = 0; p < CL_PS; ++p) pg_td[p] = pg_tp[p] = 0.f;
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int p = 0; p < CL_TS; ++p) pg_td[c][p] = pg_tp[c][p] = 0.f;
+    const int last = max(nvg - 1, 0);                   // slots past the tile's last particle repeat it
     auto prefetch = [&](int tt) {
         if (roleB) {
             const float *q = prm.pre + ((size_t)tt * N + b_n) * PW;
@@ -264,12 +269,13 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             nx_fp = __ldg(q + 2 * U);
         }
         // stored activations that gate the adjoints (the running pointers stand on step tt)
-        const int last = N - 1 - n0;                     // slots past the last particle repeat it
 #pragma unroll
-        for (int p = 0; p < CL_PS; ++p) {
+        for (int p = 0; p < CL_TS; ++p) {
             const size_t row = (size_t)min(p, last);
-            if (Rd.thin_on) pg_td[p] = __ldg(Rd.gt_ptr + row * Rd.tW);
-            if (Rp.thin_on) pg_tp[p] = __ldg(Rp.gt_ptr + row * Rp.tW);
+            if (Rd.on0) pg_td[0][p] = __ldg(Rd.gt_ptr + row * Rd.tW);
+            if (Rd.on1) pg_td[1][p] = __ldg(Rd.gt_ptr + row * Rd.tW + CL_GT);
+            if (Rp.on0) pg_tp[0][p] = __ldg(Rp.gt_ptr + row * Rp.tW);
+            if (Rp.on1) pg_tp[1][p] = __ldg(Rp.gt_ptr + row * Rp.tW + CL_GT);
         }
         if (Rd.wide_on) pg_wd = __ldg(Rd.gw_ptr);
         if (Rp.wide_on) pg_wp = __ldg(Rp.gw_ptr);
@@ -278,33 +284,41 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         Rd.gw_ptr -= Rd.wide_step;
         Rp.gw_ptr -= Rp.wide_step;
     };
-    float gtf_dyn[CL_PS], gtf_pol[CL_PS];
+    float gtf_dyn[2][CL_TS], gtf_pol[2][CL_TS];
     float gwf_dyn = 0.f, gwf_pol = 0.f;
 #pragma unroll
-    for (int p = 0; p < CL_PS; ++p) gtf_dyn[p] = gtf_pol[p] = 0.f;
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int p = 0; p < CL_TS; ++p) gtf_dyn[c][p] = gtf_pol[c][p] = 0.f;
     auto latch_gates = [&]() {
 #pragma unroll
-        for (int p = 0; p < CL_PS; ++p) {
-            gtf_dyn[p] = (Rd.thin_on && pg_td[p] != 0.f) ? Rd.tmk[p * Rd.tW] * Rd.tkinv : 0.f;
-            gtf_pol[p] = (Rp.thin_on && pg_tp[p] != 0.f) ? Rp.tmk[p * Rp.tW] * Rp.tkinv : 0.f;
+        for (int p = 0; p < CL_TS; ++p) {
+            gtf_dyn[0][p] = (Rd.on0 && pg_td[0][p] != 0.f) ? Rd.tmk[p * Rd.tW] * Rd.tkinv : 0.f;
+            gtf_dyn[1][p] = (Rd.on1 && pg_td[1][p] != 0.f) ? Rd.tmk[p * Rd.tW + CL_GT] * Rd.tkinv : 0.f;
+            gtf_pol[0][p] = (Rp.on0 && pg_tp[0][p] != 0.f) ? Rp.tmk[p * Rp.tW] * Rp.tkinv : 0.f;
+            gtf_pol[1][p] = (Rp.on1 && pg_tp[1][p] != 0.f) ? Rp.tmk[p * Rp.tW + CL_GT] * Rp.tkinv : 0.f;
         }
         gwf_dyn = pg_wd != 0.f ? Rd.wmk : 0.f;
         gwf_pol = pg_wp != 0.f ? Rp.wmk : 0.f;
     };
-    const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
-    const uint32_t bar_dyn = smem_u32(&xbar[0]), bar_pol = smem_u32(&xbar[1]);
+
+    const uint32_t mbox_dyn_saddr = smem_u32(mbox_dyn), mbox_pol_saddr = smem_u32(mbox_pol);
+    const uint32_t bar_dyn = smem_u32(&xbar[g][0]), bar_pol = smem_u32(&xbar[g][1]);
     const uint32_t wstride = cl_window_stride(bar_dyn, C);
     float *odel_ptr = nullptr;          // role X (action dims): adjoint of the policy outputs of the current step
-    if (roleX && x_k >= D) odel_ptr = prm.ws + pol.odel_off + ((size_t)(H - 1) * N + min(n0 + x_p, N - 1)) * pol.nraw + (x_k - D);
+    if (xact) odel_ptr = prm.ws + pol.odel_off + ((size_t)(H - 1) * N + x_n) * pol.nraw + (x_k - D);
     const size_t odel_step = (size_t)N * pol.nraw;
 
+    __syncthreads();
+    cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
+
+    if (nvg > 0) {
     // ---- prologue: everything step H-1 needs ----
     float c_rs, c_fd, c_gs, c_ra, c_tp, c_fp;
     prefetch(H - 1);
     latch_gates();
     c_rs = nx_rs; c_fd = nx_fd; c_gs = nx_gs; c_ra = nx_ra; c_tp = nx_tp; c_fp = nx_fp;
-    __syncthreads();
-    cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
+    CT_SYNC(g);
 
 #pragma unroll 1
     for (int t = H - 1, it = 0; t >= 0; --t, ++it) {
@@ -316,31 +330,32 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
         if (roleB) {
-            const float g = gs[b_p * SD + b_d] + c_rs;
-            gsp[b_p * SD + b_d] = g;
-            xd[b_d * CL_PS + b_p] = g * b_sy;
-            if (dyn.has_density) xd[(D + b_d) * CL_PS + b_p] = g * c_fd;
+            const float gg = gs[b_p * SD + b_d] + c_rs;
+            gsp[b_p * SD + b_d] = gg;
+            xd[b_d * CL_TS + b_p] = gg * b_sy;
+            if (dyn.has_density) xd[(D + b_d) * CL_TS + b_p] = gg * c_fd;
         }
         CL_TMARK(33);
-        __syncthreads();
+        CT_SYNC(g);
         // ================= dynamics net =================
-        cl_net_backward<C, false>(prm, dyn, Rd, smem, xd, gtf_dyn, gwf_dyn, nval, rank, inbox_saddr, bar_dyn, wstride, dbg_step, 34);
+        ct_net_backward<C, false>(prm, dyn, Rd, smem, xd, act, red, gtf_dyn, gwf_dyn, g, gtid, mbox_dyn_saddr, bar_dyn,
+                                  wstride, dbg_step, 34);
         if (roleX) {
             // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
             //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
-            mbar_wait(&xbar[0], par);
-            if (tid == 0) mbar_expect_tx(&xbar[0], bytes_dyn);
-            const float v = cl_gather2<C>(inbox_dyn, x_p, x_k) * x_isx;
+            mbar_wait(&xbar[g][0], par);
+            if (gtid == 0) mbar_expect_tx(&xbar[g][0], bytes_dyn);
+            const float v = ct_gather<C>(mbox_dyn, x_p, x_k) * x_isx;
             if (x_k < D) {
                 gsp[x_p * SD + x_k] += v;
             } else {
                 const int u = x_k - D;
                 const float du = (c_ra + v) * c_tp;
-                xp[u * CL_PS + x_p] = du;
+                xp[u * CL_TS + x_p] = du;
                 float dls = 0.f;
                 if (pol.has_density) {
                     dls = du * c_fp;
-                    xp[(U + u) * CL_PS + x_p] = dls;
+                    xp[(U + u) * CL_TS + x_p] = dls;
                 }
                 if (x_own) {
                     odel_ptr[0] = du;
@@ -350,24 +365,26 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         }
         odel_ptr -= odel_step;
         CL_TMARK(37);
-        __syncthreads();
+        CT_SYNC(g);
         // ================= policy net =================
-        cl_net_backward<C, true>(prm, pol, Rp, smem, xp, gtf_pol, gwf_pol, nval, rank,
-                                 inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_pol, wstride, dbg_step, 38);
+        ct_net_backward<C, true>(prm, pol, Rp, smem, xp, act, red, gtf_pol, gwf_pol, g, gtid, mbox_pol_saddr, bar_pol,
+                                 wstride, dbg_step, 38);
         if (roleB) {
             // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
-            mbar_wait(&xbar[1], par);
-            if (tid == 128) mbar_expect_tx(&xbar[1], bytes_pol);
-            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + cl_gather2<C>(inbox_pol, b_p, b_d) + c_gs;
+            mbar_wait(&xbar[g][1], par);
+            if (gtid == 64) mbar_expect_tx(&xbar[g][1], bytes_pol);
+            gs[b_p * SD + b_d] = gsp[b_p * SD + b_d] + ct_gather<C>(mbox_pol, b_p, b_d) + c_gs;
         }
         if (t > 0) {
             latch_gates();
             c_rs = nx_rs; c_fd = nx_fd; c_gs = nx_gs; c_ra = nx_ra; c_tp = nx_tp; c_fp = nx_fp;
         }
         CL_TMARK(41);
-        __syncthreads();
+        CT_SYNC(g);
     }
-    if (prm.dx0 && roleB && b_p < nval && (b_p % C) == rank) prm.dx0[(size_t)(n0 + b_p) * D + b_d] = gs[b_p * SD + b_d];
+    if (prm.dx0 && roleB && b_p < nvg && ((g * CL_TS + b_p) % C) == rank)
+        prm.dx0[(size_t)(n0g + b_p) * D + b_d] = gs[b_p * SD + b_d];
+    }
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
 

@@ -12,94 +12,105 @@
 namespace pmb {
 
 // Per-thread constants of a net pass, fixed for the whole horizon (registers).
-//   thin layer : thread = column j = tid of hidden 0: its TK weights, bias, the 8 particle slots' mask / keep
-//   epilogue of the wide layer: thread = (particle slot = warp, column = lane of this CTA's slice)
+//   thin layer : thread gtid of the group owns the columns gtid and gtid + 128 of hidden 0: their TK weights, bias
+//                and the 4 particle slots' mask / keep
+//   epilogue of the wide layer: thread = (particle slot = warp of the group, column = lane of this CTA's slice)
 template <int TK>
 struct FwdNetRegs {
-    float tw[TK];
-    float tb;
-    float tmk[CL_PS];
+    float tw[2][TK];
+    float tb[2];
+    float tmk[2][CL_TS];
     float wb, wmk;
-    bool thin_on, thin_store, wide_on, wide_store, send_ok;
+    bool on0, on1, thin_store, wide_store, send_ok;
     float *sv_thin, *sv_wide;       // running global pointers of the stored activations (advance per step)
     size_t thin_step, wide_step;
     int tK, tcol;
-    __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int n0,
-                                         int nval) {
-        const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
-        thin_on = tid < n.tW;
+    uint32_t slot_off;              // byte offset of (this rank, this slot) inside a mailbox
+    __device__ __forceinline__ void init(const ClusterParams &prm, const CNet &n, const float *smem, int rank, int g,
+                                         int gtid, int n0g, int nvg) {
+        const int lane = gtid & 31, sl = gtid >> 5;     // slot of the tile
+        const int ps = g * CL_TS + sl;                  // slot of the cluster (mask rows)
+        on0 = gtid < n.tW;
+        on1 = gtid + CL_GT < n.tW;
 #pragma unroll
-        for (int k = 0; k < TK; ++k) tw[k] = (thin_on && k < n.tK) ? smem[n.s_tw + k * n.tW + tid] : 0.f;
-        tb = thin_on ? smem[n.s_tb + tid] : 0.f;
+        for (int c = 0; c < 2; ++c) {
+            const bool on = c ? on1 : on0;
+            const int j = gtid + c * CL_GT;
 #pragma unroll
-        for (int q = 0; q < CL_PS; ++q) tmk[q] = thin_on ? smem[n.s_tm + q * n.tW + tid] * n.tkeep_inv : 0.f;
+            for (int k = 0; k < TK; ++k) tw[c][k] = (on && k < n.tK) ? smem[n.s_tw + k * n.tW + j] : 0.f;
+            tb[c] = on ? smem[n.s_tb + j] : 0.f;
+#pragma unroll
+            for (int q = 0; q < CL_TS; ++q) tmk[c][q] = on ? smem[n.s_tm + (g * CL_TS + q) * n.tW + j] * n.tkeep_inv : 0.f;
+        }
         tK = n.tK;
-        // the thin output is stored by warp = particle slot, lane = column of this CTA's share of the columns
+        // hidden 0 is stored by warp = slot, lane = column of this CTA's share of the columns
         tcol = rank * n.tsl + lane;
-        thin_store = p < nval && lane < n.tsl && tcol < n.tW;
-        sv_thin = prm.ws + n.tsav_off + (size_t)(n0 + p) * n.tW + tcol;
+        thin_store = sl < nvg && lane < n.tsl && tcol < n.tW;
+        sv_thin = prm.ws + n.tsav_off + (size_t)(n0g + sl) * n.tW + tcol;
         thin_step = (size_t)prm.N * n.tW;
         const int gc = rank * n.hs + lane;
-        wide_on = lane < n.hs;
+        const bool wide_on = lane < n.hs;
         wb = wide_on ? smem[n.s_wb + lane] : 0.f;
-        wmk = wide_on ? smem[n.s_wm + p * n.hs + lane] * n.wkeep_inv : 0.f;
-        wide_store = wide_on && p < nval && gc < n.wN;
-        sv_wide = prm.ws + n.wsav_off + (size_t)(n0 + p) * n.wN + gc;
+        wmk = wide_on ? smem[n.s_wm + ps * n.hs + lane] * n.wkeep_inv : 0.f;
+        wide_store = wide_on && sl < nvg && gc < n.wN;
+        sv_wide = prm.ws + n.wsav_off + (size_t)(n0g + sl) * n.wN + gc;
         wide_step = (size_t)prm.N * n.wN;
-        send_ok = p < prm.PG;
+        send_ok = sl < nvg;
+        slot_off = (uint32_t)(rank * CL_MBOX + sl * CL_NO) * 4u;
     }
 };
 
-// One net pass up to and including the send of the output partials.
-//   x : [TK][8] input tile (rows >= tK are zero); on return the partial sums of the raw outputs are on their way
-//   to every CTA of the cluster.  Two CTA barriers.
+// One net pass of one tile up to and including the send of the output partials.
+//   x : [TK][4] input tile (rows >= tK are zero); on return the partial sums of the raw outputs are on their way
+//   to every CTA of the cluster.  Two group barriers.
 template <int C, int TK>
-__device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const CNet &n, FwdNetRegs<TK> &R, float *smem,
-                                               const float *x, int nval, int rank, uint32_t inbox_saddr,
-                                               uint32_t bar_saddr, uint32_t wstride, bool dbg_step, int mark0) {
-    float *act = smem + prm.off_act, *red = smem + prm.off_red;
-    // ---- thin: hidden 0 = relu(x W0^T + b0) * mask0 / keep0 (full width, every CTA) ----
-    if (R.thin_on) {
-        float2 acc[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) acc[h] = make_float2(0.f, 0.f);
+__device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const CNet &n, FwdNetRegs<TK> &R, float *smem,
+                                               const float *x, float *act, float *red, int g, int gtid,
+                                               uint32_t mbox_saddr, uint32_t bar_saddr, uint32_t wstride, bool dbg_step,
+                                               int mark0) {
+    // ---- thin: hidden 0 = relu(x W0^T + b0) * mask0 / keep0 (full width, every CTA); two columns per thread ----
+    if (R.on0) {
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
             if (k < R.tK) {         // uniform: rows >= tK are zero padding
-                const float4 x0 = *reinterpret_cast<const float4 *>(x + k * CL_PS);
-                const float4 x1 = *reinterpret_cast<const float4 *>(x + k * CL_PS + 4);
-                acc[0] = cl_fma2(R.tw[k], make_float2(x0.x, x0.y), acc[0]);
-                acc[1] = cl_fma2(R.tw[k], make_float2(x0.z, x0.w), acc[1]);
-                acc[2] = cl_fma2(R.tw[k], make_float2(x1.x, x1.y), acc[2]);
-                acc[3] = cl_fma2(R.tw[k], make_float2(x1.z, x1.w), acc[3]);
+                const float4 xv = *reinterpret_cast<const float4 *>(x + k * CL_TS);
+                a0 = cl_fma2(R.tw[0][k], make_float2(xv.x, xv.y), a0);
+                a1 = cl_fma2(R.tw[0][k], make_float2(xv.z, xv.w), a1);
+                b0 = cl_fma2(R.tw[1][k], make_float2(xv.x, xv.y), b0);
+                b1 = cl_fma2(R.tw[1][k], make_float2(xv.z, xv.w), b1);
             }
         }
-        float v[CL_PS];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            v[2 * h] = acc[h].x + R.tb;
-            v[2 * h + 1] = acc[h].y + R.tb;
+        float4 v;
+        v.x = fmaxf(a0.x + R.tb[0], 0.f) * R.tmk[0][0];
+        v.y = fmaxf(a0.y + R.tb[0], 0.f) * R.tmk[0][1];
+        v.z = fmaxf(a1.x + R.tb[0], 0.f) * R.tmk[0][2];
+        v.w = fmaxf(a1.y + R.tb[0], 0.f) * R.tmk[0][3];
+        *reinterpret_cast<float4 *>(act + gtid * CL_TS) = v;
+        if (R.on1) {
+            v.x = fmaxf(b0.x + R.tb[1], 0.f) * R.tmk[1][0];
+            v.y = fmaxf(b0.y + R.tb[1], 0.f) * R.tmk[1][1];
+            v.z = fmaxf(b1.x + R.tb[1], 0.f) * R.tmk[1][2];
+            v.w = fmaxf(b1.y + R.tb[1], 0.f) * R.tmk[1][3];
+            *reinterpret_cast<float4 *>(act + (gtid + CL_GT) * CL_TS) = v;
         }
-#pragma unroll
-        for (int p = 0; p < CL_PS; ++p) v[p] = fmaxf(v[p], 0.f) * R.tmk[p];
-        cl_store_act(act, threadIdx.x, v);
     }
     CL_TMARK(mark0);
-    __syncthreads();
+    CT_SYNC(g);
     // hidden 0 is kept for the reverse sweep: one coalesced row segment per warp (= particle slot), off the tile
-    if (R.thin_store) *R.sv_thin = cl_act_at(act, R.tcol, threadIdx.x >> 5);
+    if (R.thin_store) *R.sv_thin = act[R.tcol * CL_TS + (gtid >> 5)];
     R.sv_thin += R.thin_step;
-    // ---- wide: this CTA's columns of hidden 1, k-split over the warps ----
-    cl_wide_accum2(smem + n.s_ww, n.tW, n.hs, act, red);
+    // ---- wide: this CTA's columns of hidden 1, k-split over the half-warps of the group ----
+    ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
     CL_TMARK(mark0 + 1);
-    __syncthreads();
+    CT_SYNC(g);
     // ---- epilogue (warp = particle slot, lane = column) + narrow partial sums + exchange ----
     {
-        float v = cl_wide_reduce(red);
+        float v = ct_wide_reduce(red, gtid);
         v = fmaxf(v + R.wb, 0.f) * R.wmk;           // idle lanes: wb = wmk = 0 and red holds zeros
         if (R.wide_store) *R.sv_wide = v;
         R.sv_wide += R.wide_step;
-        cl_narrow_send_any<C>(v, smem + n.s_nwt, threadIdx.x >> 5, R.send_ok, n.nN, inbox_saddr, bar_saddr, rank, wstride);
+        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -107,48 +118,56 @@ __device__ __forceinline__ void cl_net_forward(const ClusterParams &prm, const C
 template <int C, int TK>
 __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_constant__ ClusterParams prm) {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t xbar[2];          // [0] policy exchange, [1] dynamics exchange
+    __shared__ __align__(8) uint64_t xbar[2][2];       // [group][0 policy exchange, 1 dynamics exchange]
     const int tid = threadIdx.x;
+    const int g = tid >> 7, gtid = tid & (CL_GT - 1);  // particle tile (warp group) and thread of the group
     const int rank = (int)cl_rank();
     const int PG = prm.PG;
     const int n0 = (int)cl_id_x() * PG;
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H;
-    const int nval = min(PG, N - n0);
+    const int nval = min(PG, N - n0);                  // particles of this cluster
+    const int nv0 = (nval + 1) >> 1;                   // tile 0 takes the first half (rounded up), tile 1 the rest
+    const int n0g = n0 + (g ? nv0 : 0);                // first particle of this tile
+    const int nvg = g ? nval - nv0 : nv0;              // particles of this tile (0: the group idles)
     const CNet &pol = prm.pol;
     const CNet &dyn = prm.dyn;
 
     for (int i = tid; i < prm.smem_floats; i += CL_NT) smem[i] = 0.f;
     __syncthreads();
     float *cst = smem + prm.off_cst;
-    float *xpol = smem + prm.off_xa;       // [TK][8] policy input (raw state), rows >= D stay zero
-    float *xdyn = smem + prm.off_xb;       // [TK][8] dynamics input (scaled state, scaled action)
-    const float *inbox_pol = smem + prm.off_inbox;
-    const float *inbox_dyn = inbox_pol + C * CL_INBOX;
-    const uint32_t bytes_pol = (uint32_t)(C * PG * pol.nNp) * 4u, bytes_dyn = (uint32_t)(C * PG * dyn.nNp) * 4u;
-    if (tid == 0) {
-        mbar_init(&xbar[0], 1);
-        mbar_init(&xbar[1], 1);
+    const int tw_max = max(pol.tW, dyn.tW);
+    float *xpol = smem + prm.off_xa + g * (CL_NO * CL_TS);     // [TK][4] policy input (raw state), rows >= D stay zero
+    float *xdyn = smem + prm.off_xb + g * (CL_NO * CL_TS);     // [TK][4] dynamics input (scaled state, scaled action)
+    float *act = smem + prm.off_act + g * (tw_max * CL_TS);    // [tW][4] hidden 0 of the tile
+    float *red = smem + prm.off_red + g * (8 * CL_TS * 32);    // [8 k-slices][4][32]
+    const float *mbox_pol = smem + prm.off_inbox + g * (2 * C * CL_MBOX);
+    const float *mbox_dyn = mbox_pol + C * CL_MBOX;
+    const uint32_t bytes_pol = (uint32_t)(C * nvg * pol.nNp) * 4u, bytes_dyn = (uint32_t)(C * nvg * dyn.nNp) * 4u;
+    if (gtid == 0) {
+        mbar_init(&xbar[g][0], 1);
+        mbar_init(&xbar[g][1], 1);
         fence_mbar_init();
-        mbar_expect_tx(&xbar[0], bytes_pol);
-        mbar_expect_tx(&xbar[1], bytes_dyn);
+        mbar_expect_tx(&xbar[g][0], bytes_pol);
+        mbar_expect_tx(&xbar[g][1], bytes_dyn);
     }
     load_constants(prm, cst);
-    cl_load_net(prm, pol, smem, rank, n0, true);
-    cl_load_net(prm, dyn, smem, rank, n0, true);
+    // the mask rows of the cluster's 8 slots: tile 0 = slots 0..3, tile 1 = slots 4..7 -> particle of slot q
+    cl_load_net(prm, pol, smem, rank, n0, nv0, true);
+    cl_load_net(prm, dyn, smem, rank, n0, nv0, true);
     __syncthreads();
     FwdNetRegs<TK> Rp, Rd;
-    Rp.init(prm, pol, smem, rank, n0, nval);
-    Rd.init(prm, dyn, smem, rank, n0, nval);
+    Rp.init(prm, pol, smem, rank, g, gtid, n0g, nvg);
+    Rd.init(prm, dyn, smem, rank, g, gtid, n0g, nvg);
 
     // ---- thread roles for the per-particle stages (fixed for the whole horizon) ----
-    const bool roleA = tid < CL_PS * U;                        // one (particle slot, action dim)
-    const int a_p = roleA ? tid / U : 0, a_u = roleA ? tid - a_p * U : 0;
-    const int a_n = min(n0 + a_p, N - 1);
-    const bool a_own = roleA && a_p < nval && (a_p % C) == rank;
-    const bool roleB = tid >= 128 && tid - 128 < CL_PS * D;    // one (particle slot, state dim)
-    const int b_p = roleB ? (tid - 128) / D : 0, b_d = roleB ? (tid - 128) - b_p * D : 0;
-    const int b_n = min(n0 + b_p, N - 1);
-    const bool b_own = roleB && b_p < nval && (b_p % C) == rank;
+    const bool roleA = gtid < CL_TS * U;                       // one (particle slot, action dim)
+    const int a_p = roleA ? gtid / U : 0, a_u = roleA ? gtid - a_p * U : 0;
+    const int a_n = min(n0g + a_p, N - 1);
+    const bool a_own = roleA && a_p < nvg && ((g * CL_TS + a_p) % C) == rank;
+    const bool roleB = gtid >= 64 && gtid - 64 < CL_TS * D;    // one (particle slot, state dim)
+    const int b_p = roleB ? (gtid - 64) / D : 0, b_d = roleB ? (gtid - 64) - b_p * D : 0;
+    const int b_n = min(n0g + b_p, N - 1);
+    const bool b_own = roleB && b_p < nvg && ((g * CL_TS + b_p) % C) == rank;
 
     float s_reg = 0.f;            // role B: this thread's element of the current state
     float b_mx = 0.f, b_isx = 0.f, b_sy = 0.f, b_my = 0.f, b_nbm = 0.f, b_nbl = 0.f;
@@ -158,8 +177,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         b_nbm = smem[dyn.s_nb + b_d];
         if (dyn.has_density) b_nbl = smem[dyn.s_nb + D + b_d];
         s_reg = prm.x0[(size_t)b_n * D + b_d];
-        xpol[b_d * CL_PS + b_p] = s_reg;
-        xdyn[b_d * CL_PS + b_p] = (s_reg - b_mx) * b_isx;
+        xpol[b_d * CL_TS + b_p] = s_reg;
+        xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
         if (b_own) prm.states[(size_t)b_n * D + b_d] = s_reg;
     }
     if (roleA) {
@@ -171,8 +190,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     float zA = 0.f, zB = 0.f;
     if (roleA && pol.has_density) zA = __ldg(pol.z + (size_t)a_n * U + a_u);
     if (roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)b_n * D + b_d);
-    const uint32_t inbox_saddr = smem_u32(smem + prm.off_inbox);
-    const uint32_t bar_pol = smem_u32(&xbar[0]), bar_dyn = smem_u32(&xbar[1]);
+    const uint32_t mbox_pol_saddr = smem_u32(mbox_pol), mbox_dyn_saddr = smem_u32(mbox_dyn);
+    const uint32_t bar_pol = smem_u32(&xbar[g][0]), bar_dyn = smem_u32(&xbar[g][1]);
     const uint32_t wstride = cl_window_stride(bar_pol, C);
     // running global pointers of the role threads (advance per step)
     float *act_ptr = prm.actions + (size_t)a_n * U + a_u;
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     __syncthreads();
     cl_sync();          // every CTA's barriers are initialised and armed before any peer may signal them
 
+    if (nvg > 0) {
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
@@ -195,19 +215,19 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
 
         // ================= policy =================
-        cl_net_forward<C, TK>(prm, pol, Rp, smem, xpol, nval, rank, inbox_saddr, bar_pol, wstride, dbg_step, 1);
+        ct_net_forward<C, TK>(prm, pol, Rp, smem, xpol, act, red, g, gtid, mbox_pol_saddr, bar_pol, wstride, dbg_step, 1);
         if (roleA) {
             // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243) ----
-            mbar_wait(&xbar[0], par);
-            if (tid == 0) mbar_expect_tx(&xbar[0], bytes_pol);        // arm the next phase
-            const float mu = a_nbm + cl_gather2<C>(inbox_pol, a_p, a_u);
+            mbar_wait(&xbar[g][0], par);
+            if (gtid == 0) mbar_expect_tx(&xbar[g][0], bytes_pol);        // arm the next phase
+            const float mu = a_nbm + ct_gather<C>(mbox_pol, a_p, a_u);
             float uu = mu, ls = 0.f;
             if (pol.has_density) {
-                ls = a_nbl + cl_gather2<C>(inbox_pol, a_p, U + a_u);
+                ls = a_nbl + ct_gather<C>(mbox_pol, a_p, U + a_u);
                 uu += zA * exp_clamped_logstd(ls, pol.lmax, elmax_pol);
             }
             const float a = a_sc * tanhf(uu) + a_bi;
-            xdyn[(D + a_u) * CL_PS + a_p] = (a - a_mx) * a_isx;       // core.py:269,177
+            xdyn[(D + a_u) * CL_TS + a_p] = (a - a_mx) * a_isx;       // core.py:269,177
             if (a_own) {
                 *act_ptr = a;
                 rawp_ptr[0] = mu;
@@ -217,27 +237,26 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         act_ptr += act_step;
         rawp_ptr += rawp_step;
         CL_TMARK(4);
-        __syncthreads();
+        CT_SYNC(g);
 
         // ================= dynamics =================
-        cl_net_forward<C, TK>(prm, dyn, Rd, smem, xdyn, nval, rank, inbox_saddr + (uint32_t)(C * CL_INBOX) * 4u, bar_dyn,
-                              wstride, dbg_step, 5);
+        ct_net_forward<C, TK>(prm, dyn, Rd, smem, xdyn, act, red, g, gtid, mbox_dyn_saddr, bar_dyn, wstride, dbg_step, 5);
         if (roleB) {
             // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
-            mbar_wait(&xbar[1], par);
-            if (tid == 128) mbar_expect_tx(&xbar[1], bytes_dyn);
-            const float mu = b_nbm + cl_gather2<C>(inbox_dyn, b_p, b_d);
+            mbar_wait(&xbar[g][1], par);
+            if (gtid == 64) mbar_expect_tx(&xbar[g][1], bytes_dyn);
+            const float mu = b_nbm + ct_gather<C>(mbox_dyn, b_p, b_d);
             float delta, ls = 0.f;
             if (dyn.has_density) {
-                ls = b_nbl + cl_gather2<C>(inbox_dyn, b_p, D + b_d);
+                ls = b_nbl + ct_gather<C>(mbox_dyn, b_p, D + b_d);
                 // exp(clamped log-std + log Sy) = Sy * exp(clamped log-std)   (densities.py:105)
                 delta = (mu * b_sy + b_my) + zB * (b_sy * exp_clamped_logstd(ls, dyn.lmax, elmax_dyn));
             } else {
                 delta = mu * b_sy + b_my;
             }
             s_reg += delta;
-            xpol[b_d * CL_PS + b_p] = s_reg;
-            xdyn[b_d * CL_PS + b_p] = (s_reg - b_mx) * b_isx;
+            xpol[b_d * CL_TS + b_p] = s_reg;
+            xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
             if (b_own) {
                 *st_ptr = s_reg;
                 rawd_ptr[0] = mu;
@@ -247,16 +266,16 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         st_ptr += st_step;
         rawd_ptr += rawd_step;
         CL_TMARK(8);
-        __syncthreads();
+        CT_SYNC(g);
     }
     // ---- rewards r_t = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset on (s_{t+1}, a_t) for every step
     //      (envs/cartpole/env.py:62-86).  Nothing in the recurrence consumes them: evaluated here, off the serial
-    //      chain, for the particles whose trajectory THIS CTA wrote (slot p with p % C == rank). ----
-    for (int i = tid; i < H * CL_PS; i += CL_NT) {
-        const int tt = i / CL_PS, p = i - tt * CL_PS;
-        if (p >= nval || (p % C) != rank) continue;
-        const float *s1 = prm.states + ((size_t)(tt + 1) * N + n0 + p) * D;
-        const float *a = prm.actions + ((size_t)tt * N + n0 + p) * U;
+    //      chain, for the particles whose trajectory THIS group of THIS CTA wrote. ----
+    for (int i = gtid; i < H * CL_TS; i += CL_GT) {
+        const int tt = i / CL_TS, p = i - tt * CL_TS;
+        if (p >= nvg || ((g * CL_TS + p) % C) != rank) continue;
+        const float *s1 = prm.states + ((size_t)(tt + 1) * N + n0g + p) * D;
+        const float *a = prm.actions + ((size_t)tt * N + n0g + p) * U;
         float dl[PMB_MAX_REWARD_ROWS];
         for (int r = 0; r < prm.KR; ++r) {
             float acc = cst[C_C0 + r];
@@ -274,7 +293,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
             for (int v = 0; v < U; ++v) q = fmaf(a[v], cst[C_R + v * SD + u], q);
             cost = fmaf(q, a[u], cost);
         }
-        prm.rewards[(size_t)tt * N + n0 + p] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
+        prm.rewards[(size_t)tt * N + n0g + p] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
+    }
     }
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
