@@ -227,7 +227,10 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
     if t.stream_mode == 3:
         # particles per cluster (1..8, 0 = auto) and CTAs per cluster (4 or 8, 0 = 8)
-        t.reserved[1] = int(os.environ.get("PMB_CLUSTER_PG", "0")) | (int(os.environ.get("PMB_CLUSTER_C", "0")) << 4)
+        # PMB_CLUSTER_STAGGER: cycles the second particle tile starts after the first (unset = library default)
+        stg = os.environ.get("PMB_CLUSTER_STAGGER")
+        t.reserved[1] = (int(os.environ.get("PMB_CLUSTER_PG", "0")) | (int(os.environ.get("PMB_CLUSTER_C", "0")) << 4)
+                         | ((0 if stg is None else min(0xffff, int(stg) // 16 + 1)) << 8))
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
 

@@ -338,7 +338,7 @@ static int cluster_carve(ClusterParams &P, bool reverse) {
     int tw_max = 4;
     for (int i = 0; i < 2; ++i) {
         CNet &n = *nets[i];
-        n.s_tw = take(n.tK * n.tW);
+        n.s_tw = take(CL_NO * n.tW);        // rows >= tK stay zero (the thin layer runs whole 4-row blocks)
         n.s_ww = take(n.tW * n.hs);
         n.s_nw = take(n.nN * n.hs);
         n.s_nwt = take(CL_NO * CL_HS);
@@ -352,7 +352,7 @@ static int cluster_carve(ClusterParams &P, bool reverse) {
     P.off_xa = take(2 * CL_NO * CL_PS);
     P.off_xb = take(2 * CL_NO * CL_PS);
     P.off_act = take(tw_max * CL_PS);
-    P.off_red = take(8 * CL_PS * 32);
+    P.off_red = take(CL_KS * CL_PS * 32);
     P.off_h2s = take(CL_PS * 32);
     P.off_part = take(CL_INBOX);
     P.off_inbox = take(2 * P.C * CL_INBOX);
@@ -401,6 +401,10 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         if (PG < 1) PG = 1;
     }
     pl.cfwd.PG = pl.cbwd.PG = PG;
+    {
+        const int st = (tune && mode == 3) ? (tune->reserved[1] >> 8) & 0xffff : 0;
+        pl.cfwd.stagger = pl.cbwd.stagger = st ? (st - 1) * 16 : 1600;
+    }
     pl.cl_nclusters = (p->N + PG - 1) / PG;
     pl.cluster = C;
     return PMB_OK;

@@ -56,6 +56,7 @@ struct CNet {
 struct ClusterParams {
     int N, H, D, U;
     int PG;                     // particles per cluster
+    int stagger;                // cycles the second particle tile starts after the first (phase offset of the groups)
     int C;                      // CTAs per cluster
     CNet pol, dyn;
     const float *wpack;         // packed weights of THIS sweep
@@ -181,59 +182,55 @@ __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet
 // ----------------------------------------------------------------------------------------
 #define CT_SYNC(g) asm volatile("bar.sync %0, 128;" ::"r"((g) + 2) : "memory")   // barriers 2, 3 (0, 1 = whole CTA)
 
-// wide layer, this CTA's column slice, one 4-slot tile: 8 k-slices = (warp of the group, half-warp); lane =
-// (row half, column quad q, slot pair pp).  Per row one LDS.128 of weights + one LDS.64 of activations feed
-// 4 FFMA2; two rows in flight per thread.  Partial sums go to red[slice][slot][32].
+// wide layer, this CTA's column slice, one 4-slot tile: 16 k-slices = (warp of the group, quarter-warp); lane =
+// (row quarter, column quad q).  Per row one LDS.128 of weights + one LDS.128 of activations (all 4 slots) feed
+// 8 FFMA2 (4 slots x 4 columns per thread).  Partial sums go to red[slice][slot][32].
+constexpr int CL_KS = 16;                 // k-slices of the wide layer per tile
 __device__ __forceinline__ void ct_wide_accum(const float *__restrict__ ww, int K, int hs, const float *__restrict__ act,
                                               float *__restrict__ red, int gtid) {
     const int lane = gtid & 31, w = gtid >> 5;
-    const int q = (lane >> 1) & 7, pp = lane & 1;
+    const int q = lane & 7;
     if (4 * q >= hs) return;
-    const int slice = 2 * w + (lane >> 4);
+    const int slice = 4 * w + (lane >> 3);
     const float2 z2 = make_float2(0.f, 0.f);
-    float2 a00 = z2, a01 = z2, a10 = z2, a11 = z2, b00 = z2, b01 = z2, b10 = z2, b11 = z2;
+    float2 a0 = z2, a1 = z2, b0 = z2, b1 = z2, c0 = z2, c1 = z2, d0 = z2, d1 = z2;   // slots 0..3 x column pairs
     const float *wp = ww + slice * hs + 4 * q;
-    const float *ap = act + slice * CL_TS + 2 * pp;
-    const int n = (K - slice + 7) >> 3;
-    const int wstride = 8 * hs;
-    int i = 0;
-#pragma unroll 3
-    for (; i + 2 <= n; i += 2) {
-        const float4 w0 = *reinterpret_cast<const float4 *>(wp);
-        const float2 x0 = *reinterpret_cast<const float2 *>(ap);
-        const float4 w1 = *reinterpret_cast<const float4 *>(wp + wstride);
-        const float2 x1 = *reinterpret_cast<const float2 *>(ap + 8 * CL_TS);
-        wp += 2 * wstride;
-        ap += 16 * CL_TS;
-        a00 = cl_fma2(x0.x, make_float2(w0.x, w0.y), a00);
-        a01 = cl_fma2(x0.x, make_float2(w0.z, w0.w), a01);
-        a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
-        a11 = cl_fma2(x0.y, make_float2(w0.z, w0.w), a11);
-        b00 = cl_fma2(x1.x, make_float2(w1.x, w1.y), b00);
-        b01 = cl_fma2(x1.x, make_float2(w1.z, w1.w), b01);
-        b10 = cl_fma2(x1.y, make_float2(w1.x, w1.y), b10);
-        b11 = cl_fma2(x1.y, make_float2(w1.z, w1.w), b11);
+    const float *ap = act + slice * CL_TS;
+    const int n = (K - slice + CL_KS - 1) / CL_KS;
+    const int wstride = CL_KS * hs;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 wv = *reinterpret_cast<const float4 *>(wp);
+        const float4 xv = *reinterpret_cast<const float4 *>(ap);
+        wp += wstride;
+        ap += CL_KS * CL_TS;
+        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
+        a0 = cl_fma2(xv.x, w01, a0);
+        a1 = cl_fma2(xv.x, w23, a1);
+        b0 = cl_fma2(xv.y, w01, b0);
+        b1 = cl_fma2(xv.y, w23, b1);
+        c0 = cl_fma2(xv.z, w01, c0);
+        c1 = cl_fma2(xv.z, w23, c1);
+        d0 = cl_fma2(xv.w, w01, d0);
+        d1 = cl_fma2(xv.w, w23, d1);
     }
-    if (i < n) {
-        const float4 w0 = *reinterpret_cast<const float4 *>(wp);
-        const float2 x0 = *reinterpret_cast<const float2 *>(ap);
-        a00 = cl_fma2(x0.x, make_float2(w0.x, w0.y), a00);
-        a01 = cl_fma2(x0.x, make_float2(w0.z, w0.w), a01);
-        a10 = cl_fma2(x0.y, make_float2(w0.x, w0.y), a10);
-        a11 = cl_fma2(x0.y, make_float2(w0.z, w0.w), a11);
-    }
-    float *r = red + ((slice * CL_TS + 2 * pp) << 5) + 4 * q;
-    *reinterpret_cast<float4 *>(r) = make_float4(a00.x + b00.x, a00.y + b00.y, a01.x + b01.x, a01.y + b01.y);
-    *reinterpret_cast<float4 *>(r + 32) = make_float4(a10.x + b10.x, a10.y + b10.y, a11.x + b11.x, a11.y + b11.y);
+    float *r = red + ((slice * CL_TS) << 5) + 4 * q;
+    *reinterpret_cast<float4 *>(r) = make_float4(a0.x, a0.y, a1.x, a1.y);
+    *reinterpret_cast<float4 *>(r + 32) = make_float4(b0.x, b0.y, b1.x, b1.y);
+    *reinterpret_cast<float4 *>(r + 64) = make_float4(c0.x, c0.y, c1.x, c1.y);
+    *reinterpret_cast<float4 *>(r + 96) = make_float4(d0.x, d0.y, d1.x, d1.y);
 }
-// finished value of (slot = warp of the group, column = lane): the 8 k-slices in a fixed order
+// finished value of (slot = warp of the group, column = lane): the 16 k-slices in a fixed order
 __device__ __forceinline__ float ct_wide_reduce(const float *__restrict__ red, int gtid) {
     const float *r = red + ((gtid >> 5) << 5) + (gtid & 31);
-    float s0 = r[0], s1 = r[1 * CL_TS * 32], s2 = r[2 * CL_TS * 32], s3 = r[3 * CL_TS * 32];
-    s0 += r[4 * CL_TS * 32];
-    s1 += r[5 * CL_TS * 32];
-    s2 += r[6 * CL_TS * 32];
-    s3 += r[7 * CL_TS * 32];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int s = 0; s < CL_KS; s += 4) {
+        s0 += r[(s + 0) * CL_TS * 32];
+        s1 += r[(s + 1) * CL_TS * 32];
+        s2 += r[(s + 2) * CL_TS * 32];
+        s3 += r[(s + 3) * CL_TS * 32];
+    }
     return (s0 + s1) + (s2 + s3);
 }
 
@@ -258,7 +255,7 @@ __device__ __forceinline__ uint32_t cl_window_stride(uint32_t probe_saddr, int C
 template <int C, int NV>
 __device__ __forceinline__ void ct_narrow_send(float v, const float *__restrict__ nwt, bool send_ok, int nN,
                                                uint32_t mbox_saddr, uint32_t slot_off, uint32_t bar_saddr,
-                                               uint32_t wstride) {
+                                               uint32_t wstride, long long *dbgp) {
     const int lane = threadIdx.x & 31;
     float pr[NV];
 #pragma unroll
@@ -282,37 +279,49 @@ __device__ __forceinline__ void ct_narrow_send(float v, const float *__restrict_
     }
 #pragma unroll
     for (; m >= 1; m >>= 1) pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], m);
-    // output o = lane / s sits in every lane of its group of s = 32 / NV lanes
+    // output o = lane / s sits in every lane of its group of s = 32 / NV lanes; gather 4 neighbouring outputs
     constexpr int s = 32 / NV;
     const float q1 = __shfl_sync(0xffffffffu, pr[0], (lane + s) & 31);
     const float q2 = __shfl_sync(0xffffffffu, pr[0], (lane + 2 * s) & 31);
     const float q3 = __shfl_sync(0xffffffffu, pr[0], (lane + 3 * s) & 31);
-    if (send_ok && (lane & (4 * s - 1)) == 0) {
-        const int chunk = lane / (4 * s);
-        if (4 * chunk < nN) {
-            const float4 out = make_float4(pr[0], q1, q2, q3);
-            const uint32_t a0 = cl_mapa(mbox_saddr + slot_off + (uint32_t)chunk * 16u, 0), b0 = cl_mapa(bar_saddr, 0);
-#pragma unroll
-            for (int dst = 0; dst < C; ++dst) cl_st_async_v4(a0 + (uint32_t)dst * wstride, out, b0 + (uint32_t)dst * wstride);
-        }
+    if (dbgp && lane == 0) dbgp[0] = clock64();
+    // chunk c = outputs 4c..4c+3 now sits in lane c * 4s.  Spread it over the 4s lanes of its group so that ONE
+    // st.async instruction serves every destination: lane = (chunk, destination rank).
+    constexpr int G = 4 * s;
+    const int src = lane & ~(G - 1);
+    const float4 out = make_float4(__shfl_sync(0xffffffffu, pr[0], src), __shfl_sync(0xffffffffu, q1, src),
+                                   __shfl_sync(0xffffffffu, q2, src), __shfl_sync(0xffffffffu, q3, src));
+    const int dst = lane & (G - 1), chunk = lane / G;
+    if (send_ok && dst < C && 4 * chunk < nN) {
+        const uint32_t a0 = cl_mapa(mbox_saddr + slot_off + (uint32_t)chunk * 16u, 0), b0 = cl_mapa(bar_saddr, 0);
+        cl_st_async_v4(a0 + (uint32_t)dst * wstride, out, b0 + (uint32_t)dst * wstride);
     }
 }
 template <int C>
 __device__ __forceinline__ void ct_narrow_send_any(float v, const float *__restrict__ nwt, bool send_ok, int nN,
                                                    uint32_t mbox_saddr, uint32_t slot_off, uint32_t bar_saddr,
-                                                   uint32_t wstride) {
-    if (nN <= 4) ct_narrow_send<C, 4>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
-    else if (nN <= 8) ct_narrow_send<C, 8>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
-    else ct_narrow_send<C, 16>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride);
+                                                   uint32_t wstride, long long *dbgp) {
+    if (nN <= 4) ct_narrow_send<C, 4>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride, dbgp);
+    else if (nN <= 8) ct_narrow_send<C, 8>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride, dbgp);
+    else ct_narrow_send<C, 16>(v, nwt, send_ok, nN, mbox_saddr, slot_off, bar_saddr, wstride, dbgp);
 }
-// value (slot, o) from a mailbox: the C partials added in rank order (identical on every CTA)
+// value (slot, o) from a mailbox: the C partials added in a fixed pairwise order (identical on every CTA)
 template <int C>
 __device__ __forceinline__ float ct_gather(const float *mbox, int slot, int o) {
     const float *q = mbox + slot * CL_NO + o;
-    float s = q[0];
+    float v[C];
 #pragma unroll
-    for (int r = 1; r < C; ++r) s += q[r * CL_MBOX];
-    return s;
+    for (int r = 0; r < C; ++r) v[r] = q[r * CL_MBOX];
+#pragma unroll
+    for (int w = 1; w < C; w <<= 1)
+#pragma unroll
+        for (int r = 0; r + w < C; r += 2 * w) v[r] += v[r + w];
+    return v[0];
+}
+// exp(clamp_logstd(l)) on the serial chain of the forward sweep: exp(lmax) / (1 + exp(lmax - l)) with the SFU
+// exponential and reciprocal (a few ulp; the value only scales the density noise)
+__device__ __forceinline__ float ct_exp_clamped_logstd(float l, float lmax, float elmax) {
+    return __fdividef(elmax, 1.f + __expf(lmax - l));
 }
 
 cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);

@@ -109,7 +109,7 @@ struct BwdNetRegs {
         const int ps = g * CL_TS + sl;
         const int H = prm.H, N = prm.N;
         tW = n.tW;
-        tK = n.tK;
+        tK = (n.tK + 3) & ~3;
         on0 = gtid < n.tW;
         on1 = gtid + CL_GT < n.tW;
         tw = smem + n.s_tw + gtid;
@@ -149,7 +149,8 @@ __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const 
         const float *wp = R.tw;
         const float *xp = x;
         const int c1 = R.on1 ? CL_GT : 0;        // threads without a second column re-read the first (result unused)
-#pragma unroll 2
+        // whole 4-row blocks: rows >= tK of the matrix and of x are zero padding
+#pragma unroll 4
         for (int k = 0; k < R.tK; ++k) {
             const float w0 = wp[0], w1 = wp[c1];
             const float4 xv = *reinterpret_cast<const float4 *>(xp);
@@ -183,7 +184,9 @@ __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const 
             if (R.wide_store) *R.dl_wide = v;
             R.dl_wide -= R.wide_step;
         }
-        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride);
+        CL_TMARK(mark0 + 10);
+        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride,
+                              dbg_step ? prm.dbg + (mark0 + 8) * 8 + (threadIdx.x >> 5) : nullptr);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     float *xd = smem + prm.off_xa + g * (CL_NO * CL_TS);       // [2D][4]  adjoint of the dynamics net's raw outputs
     float *xp = smem + prm.off_xb + g * (CL_NO * CL_TS);       // [2U][4]  adjoint of the policy net's raw outputs
     float *act = smem + prm.off_act + g * (tw_max * CL_TS);
-    float *red = smem + prm.off_red + g * (8 * CL_TS * 32);
+    float *red = smem + prm.off_red + g * (CL_KS * CL_TS * 32);
     float *gs = smem + prm.off_misc + g * (2 * CL_TS * SD), *gsp = gs + CL_TS * SD;   // [4][SD] carried / partial state adjoint
     const float *mbox_dyn = smem + prm.off_inbox + g * (2 * C * CL_MBOX);
     const float *mbox_pol = mbox_dyn + C * CL_MBOX;
@@ -313,6 +316,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
 
     if (nvg > 0) {
+    if (g == 1) {       // phase offset: the second tile's LSU-bound phases fall into the first tile's latency-bound ones
+        const long long c0 = clock64();
+        while (clock64() - c0 < prm.stagger) {}
+    }
     // ---- prologue: everything step H-1 needs ----
     float c_rs, c_fd, c_gs, c_ra, c_tp, c_fp;
     prefetch(H - 1);

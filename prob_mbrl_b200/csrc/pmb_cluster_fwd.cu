@@ -73,13 +73,12 @@ __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const C
         float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            if (k < R.tK) {         // uniform: rows >= tK are zero padding
-                const float4 xv = *reinterpret_cast<const float4 *>(x + k * CL_TS);
-                a0 = cl_fma2(R.tw[0][k], make_float2(xv.x, xv.y), a0);
-                a1 = cl_fma2(R.tw[0][k], make_float2(xv.z, xv.w), a1);
-                b0 = cl_fma2(R.tw[1][k], make_float2(xv.x, xv.y), b0);
-                b1 = cl_fma2(R.tw[1][k], make_float2(xv.z, xv.w), b1);
-            }
+            // rows >= tK are zero padding (weights and inputs): no branch, every load is issued up front
+            const float4 xv = *reinterpret_cast<const float4 *>(x + k * CL_TS);
+            a0 = cl_fma2(R.tw[0][k], make_float2(xv.x, xv.y), a0);
+            a1 = cl_fma2(R.tw[0][k], make_float2(xv.z, xv.w), a1);
+            b0 = cl_fma2(R.tw[1][k], make_float2(xv.x, xv.y), b0);
+            b1 = cl_fma2(R.tw[1][k], make_float2(xv.z, xv.w), b1);
         }
         float4 v;
         v.x = fmaxf(a0.x + R.tb[0], 0.f) * R.tmk[0][0];
@@ -110,7 +109,9 @@ __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const C
         v = fmaxf(v + R.wb, 0.f) * R.wmk;           // idle lanes: wb = wmk = 0 and red holds zeros
         if (R.wide_store) *R.sv_wide = v;
         R.sv_wide += R.wide_step;
-        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride);
+        CL_TMARK(mark0 + 10);
+        ct_narrow_send_any<C>(v, smem + n.s_nwt, R.send_ok, n.nN, mbox_saddr, R.slot_off, bar_saddr, wstride,
+                              dbg_step ? prm.dbg + (mark0 + 8) * 8 + (threadIdx.x >> 5) : nullptr);
     }
     CL_TMARK(mark0 + 2);
 }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     float *xpol = smem + prm.off_xa + g * (CL_NO * CL_TS);     // [TK][4] policy input (raw state), rows >= D stay zero
     float *xdyn = smem + prm.off_xb + g * (CL_NO * CL_TS);     // [TK][4] dynamics input (scaled state, scaled action)
     float *act = smem + prm.off_act + g * (tw_max * CL_TS);    // [tW][4] hidden 0 of the tile
-    float *red = smem + prm.off_red + g * (8 * CL_TS * 32);    // [8 k-slices][4][32]
+    float *red = smem + prm.off_red + g * (CL_KS * CL_TS * 32);    // [8 k-slices][4][32]
     const float *mbox_pol = smem + prm.off_inbox + g * (2 * C * CL_MBOX);
     const float *mbox_dyn = mbox_pol + C * CL_MBOX;
     const uint32_t bytes_pol = (uint32_t)(C * nvg * pol.nNp) * 4u, bytes_dyn = (uint32_t)(C * nvg * dyn.nNp) * 4u;
@@ -205,6 +206,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     cl_sync();          // every CTA's barriers are initialised and armed before any peer may signal them
 
     if (nvg > 0) {
+    if (g == 1) {       // phase offset: the second tile's LSU-bound phases fall into the first tile's latency-bound ones
+        const long long c0 = clock64();
+        while (clock64() - c0 < prm.stagger) {}
+    }
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
@@ -219,12 +224,13 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (roleA) {
             // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243) ----
             mbar_wait(&xbar[g][0], par);
+            CL_TMARK(20);
             if (gtid == 0) mbar_expect_tx(&xbar[g][0], bytes_pol);        // arm the next phase
             const float mu = a_nbm + ct_gather<C>(mbox_pol, a_p, a_u);
             float uu = mu, ls = 0.f;
             if (pol.has_density) {
                 ls = a_nbl + ct_gather<C>(mbox_pol, a_p, U + a_u);
-                uu += zA * exp_clamped_logstd(ls, pol.lmax, elmax_pol);
+                uu += zA * ct_exp_clamped_logstd(ls, pol.lmax, elmax_pol);
             }
             const float a = a_sc * tanhf(uu) + a_bi;
             xdyn[(D + a_u) * CL_TS + a_p] = (a - a_mx) * a_isx;       // core.py:269,177
@@ -244,13 +250,14 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (roleB) {
             // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
             mbar_wait(&xbar[g][1], par);
+            CL_TMARK(21);
             if (gtid == 64) mbar_expect_tx(&xbar[g][1], bytes_dyn);
             const float mu = b_nbm + ct_gather<C>(mbox_dyn, b_p, b_d);
             float delta, ls = 0.f;
             if (dyn.has_density) {
                 ls = b_nbl + ct_gather<C>(mbox_dyn, b_p, D + b_d);
                 // exp(clamped log-std + log Sy) = Sy * exp(clamped log-std)   (densities.py:105)
-                delta = (mu * b_sy + b_my) + zB * (b_sy * exp_clamped_logstd(ls, dyn.lmax, elmax_dyn));
+                delta = (mu * b_sy + b_my) + zB * (b_sy * ct_exp_clamped_logstd(ls, dyn.lmax, elmax_dyn));
             } else {
                 delta = mu * b_sy + b_my;
             }

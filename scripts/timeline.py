@@ -39,13 +39,16 @@ for nm, base in (("pol L1", 2), ("dyn L1", 10)):
 
 if os.environ.get("PMB_STREAM_MODE", "0") in ("0", "3"):
     print("cluster-resident forward sweep: per-warp arrival (cycles after the first warp entered the step), cluster 0 / rank 0")
-    names = {0: "step top", 1: "pol thin done", 2: "pol wide accum done", 3: "pol epilogue+narrow+send done",
-             4: "squash role done", 5: "dyn thin done", 6: "dyn wide accum done", 7: "dyn epilogue+narrow+send done",
+    names = {0: "step top", 1: "pol thin done", 2: "pol wide accum done", 11: "  pol reduce+epilogue done",
+             9: "  pol butterfly+gather done", 3: "pol epilogue+narrow+send done", 20: "  pol exchange arrived",
+             4: "squash role done", 5: "dyn thin done", 6: "dyn wide accum done", 15: "  dyn reduce+epilogue done",
+             13: "  dyn butterfly+gather done", 7: "dyn epilogue+narrow+send done", 21: "  dyn exchange arrived",
              8: "density role done"}
+    order = [0, 1, 2, 11, 9, 3, 20, 4, 5, 6, 15, 13, 7, 21, 8]
     t0 = min(x for x in d[0:8] if x)
-    for k in sorted(names):
-        v = [x - t0 for x in d[8 * k: 8 * k + 8]]
-        print("    %-30s min %6d max %6d  | %s" % (names[k], min(v), max(v), " ".join("%6d" % x for x in v)))
+    for k in order:
+        v = [x - t0 if x else -1 for x in d[8 * k: 8 * k + 8]]
+        print("    %-30s | %s" % (names[k], " ".join("%6d" % x for x in v)))
     print("cluster-resident backward sweep: per-warp arrival")
     names = {32: "step top", 33: "density adjoint done", 34: "dyn thin done", 35: "dyn wide accum done",
              36: "dyn epilogue+narrow+send done", 37: "scaler/squash role done", 38: "pol thin done",
