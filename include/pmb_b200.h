@@ -94,8 +94,8 @@ typedef struct pmb_tuning {
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
                                 4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default; with
                                 stream_mode 3: bits 0-3 particles per cluster (1..8, 0 = auto), bits 4-7 CTAs per
-                                cluster (4 or 8, 0 = 8), bits 8-23 phase offset of the second particle tile
-                                (1 + cycles / 16; 0 = default).
+                                cluster (4 or 8, 0 = 8), bits 8-23: 1 = the two particle tiles of a CTA run
+                                unsynchronised, 2 (and 0 = default) = they alternate on the shared-memory-bound phases.
                                 reserved[2..3]: low/high half of a device pointer to >= 64 int64 that receives
                                 clock64() timeline marks of one step (profiling aid), 0 = off.
                                 reserved[4]: hidden x hidden weight gradient on tcgen05 (TF32 x3 split): 0 = auto (when a split-K

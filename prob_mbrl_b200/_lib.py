@@ -227,10 +227,11 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
     if t.stream_mode == 3:
         # particles per cluster (1..8, 0 = auto) and CTAs per cluster (4 or 8, 0 = 8)
-        # PMB_CLUSTER_STAGGER: cycles the second particle tile starts after the first (unset = library default)
-        stg = os.environ.get("PMB_CLUSTER_STAGGER")
+        # PMB_CLUSTER_PINGPONG=0 lets the two particle tiles of a CTA run unsynchronised (default: they alternate on
+        # the shared-memory-bound phases)
+        pp = os.environ.get("PMB_CLUSTER_PINGPONG")
         t.reserved[1] = (int(os.environ.get("PMB_CLUSTER_PG", "0")) | (int(os.environ.get("PMB_CLUSTER_C", "0")) << 4)
-                         | ((0 if stg is None else min(0xffff, int(stg) // 16 + 1)) << 8))
+                         | ((0 if pp is None else int(pp) + 1) << 8))
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
 

@@ -56,7 +56,7 @@ struct CNet {
 struct ClusterParams {
     int N, H, D, U;
     int PG;                     // particles per cluster
-    int stagger;                // cycles the second particle tile starts after the first (phase offset of the groups)
+    int stagger;                // != 0: the two particle tiles of a CTA alternate on the LSU-bound phases
     int C;                      // CTAs per cluster
     CNet pol, dyn;
     const float *wpack;         // packed weights of THIS sweep
@@ -181,6 +181,11 @@ __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet
 // groups read the same resident weights.
 // ----------------------------------------------------------------------------------------
 #define CT_SYNC(g) asm volatile("bar.sync %0, 128;" ::"r"((g) + 2) : "memory")   // barriers 2, 3 (0, 1 = whole CTA)
+// LSU hand-over between the two tiles of a CTA (barriers 4, 5; both groups' threads are counted): the thin + wide
+// phases are bound by shared-memory bandwidth, the epilogue / exchange / per-particle phases by latency, so the two
+// groups alternate: a group enters its thin phase only after the other one finished its wide accumulate.
+#define CT_LSU_ACQUIRE(g) asm volatile("bar.sync %0, 256;" ::"r"((g) + 4) : "memory")
+#define CT_LSU_RELEASE(g) asm volatile("bar.arrive %0, 256;" ::"r"(5 - (g)) : "memory")
 
 // wide layer, this CTA's column slice, one 4-slot tile: 16 k-slices = (warp of the group, quarter-warp); lane =
 // (row quarter, column quad q).  Per row one LDS.128 of weights + one LDS.128 of activations (all 4 slots) feed

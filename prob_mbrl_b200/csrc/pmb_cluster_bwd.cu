@@ -142,7 +142,8 @@ template <int C, bool kStore>
 __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const CNet &n, BwdNetRegs &R, float *smem,
                                                 const float *x, float *act, float *red, const float (&gtf)[2][CL_TS],
                                                 float gwf, int g, int gtid, uint32_t mbox_saddr, uint32_t bar_saddr,
-                                                uint32_t wstride, bool dbg_step, int mark0) {
+                                                uint32_t wstride, bool dbg_step, int mark0, bool pingpong) {
+    if (pingpong) CT_LSU_ACQUIRE(g);
     // ---- thin: adjoint of hidden 1 = (dout W2) * gate; two columns per thread ----
     if (R.on0) {
         float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -175,6 +176,7 @@ __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const 
     }
     // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the half-warps of the group ----
     ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
+    if (pingpong) CT_LSU_RELEASE(g);
     CL_TMARK(mark0 + 1);
     CT_SYNC(g);
     // ---- epilogue (warp = particle slot, lane = column) + partial sums of d(input) = delta_0 W_0 + exchange ----
@@ -315,11 +317,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
 
+    const bool pingpong = prm.stagger != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
-    if (g == 1) {       // phase offset: the second tile's LSU-bound phases fall into the first tile's latency-bound ones
-        const long long c0 = clock64();
-        while (clock64() - c0 < prm.stagger) {}
-    }
+    if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
     // ---- prologue: everything step H-1 needs ----
     float c_rs, c_fd, c_gs, c_ra, c_tp, c_fp;
     prefetch(H - 1);
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         CT_SYNC(g);
         // ================= dynamics net =================
         ct_net_backward<C, false>(prm, dyn, Rd, smem, xd, act, red, gtf_dyn, gwf_dyn, g, gtid, mbox_dyn_saddr, bar_dyn,
-                                  wstride, dbg_step, 34);
+                                  wstride, dbg_step, 34, pingpong);
         if (roleX) {
             // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +
             //      policy density adjoint: a = scale*tanh(u)+bias, u = mu + z*exp(lstd) ----
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         CT_SYNC(g);
         // ================= policy net =================
         ct_net_backward<C, true>(prm, pol, Rp, smem, xp, act, red, gtf_pol, gwf_pol, g, gtid, mbox_pol_saddr, bar_pol,
-                                 wstride, dbg_step, 38);
+                                 wstride, dbg_step, 38, pingpong);
         if (roleB) {
             // ---- dL/ds_t = carried + through dynamics input + through policy input + direct cotangent ----
             mbar_wait(&xbar[g][1], par);

@@ -67,7 +67,8 @@ template <int C, int TK>
 __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const CNet &n, FwdNetRegs<TK> &R, float *smem,
                                                const float *x, float *act, float *red, int g, int gtid,
                                                uint32_t mbox_saddr, uint32_t bar_saddr, uint32_t wstride, bool dbg_step,
-                                               int mark0) {
+                                               int mark0, bool pingpong) {
+    if (pingpong) CT_LSU_ACQUIRE(g);
     // ---- thin: hidden 0 = relu(x W0^T + b0) * mask0 / keep0 (full width, every CTA); two columns per thread ----
     if (R.on0) {
         float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -101,6 +102,7 @@ __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const C
     R.sv_thin += R.thin_step;
     // ---- wide: this CTA's columns of hidden 1, k-split over the half-warps of the group ----
     ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
+    if (pingpong) CT_LSU_RELEASE(g);
     CL_TMARK(mark0 + 1);
     CT_SYNC(g);
     // ---- epilogue (warp = particle slot, lane = column) + narrow partial sums + exchange ----
@@ -205,11 +207,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     __syncthreads();
     cl_sync();          // every CTA's barriers are initialised and armed before any peer may signal them
 
+    const bool pingpong = prm.stagger != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
-    if (g == 1) {       // phase offset: the second tile's LSU-bound phases fall into the first tile's latency-bound ones
-        const long long c0 = clock64();
-        while (clock64() - c0 < prm.stagger) {}
-    }
+    if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
 
         // ================= policy =================
-        ct_net_forward<C, TK>(prm, pol, Rp, smem, xpol, act, red, g, gtid, mbox_pol_saddr, bar_pol, wstride, dbg_step, 1);
+        ct_net_forward<C, TK>(prm, pol, Rp, smem, xpol, act, red, g, gtid, mbox_pol_saddr, bar_pol, wstride, dbg_step, 1, pingpong);
         if (roleA) {
             // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243) ----
             mbar_wait(&xbar[g][0], par);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         CT_SYNC(g);
 
         // ================= dynamics =================
-        ct_net_forward<C, TK>(prm, dyn, Rd, smem, xdyn, act, red, g, gtid, mbox_dyn_saddr, bar_dyn, wstride, dbg_step, 5);
+        ct_net_forward<C, TK>(prm, dyn, Rd, smem, xdyn, act, red, g, gtid, mbox_dyn_saddr, bar_dyn, wstride, dbg_step, 5, pingpong);
         if (roleB) {
             // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
             mbar_wait(&xbar[g][1], par);
