@@ -345,9 +345,9 @@ def main():
         flops = fm["bwd_data" if dom == "bwd_sweep_ms" else "fwd"] * work
         achieved = flops / (kern[dom] * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
-        P = eng.tune.particles_per_cta or (8 if n_per > 8 * 148 else 4 if n_per > 2 * 148 else 2 if n_per > 148 else 1)
-        ctas = (n_per + P - 1) // P
-        kname = "rollout_bwd_kernel" if dom == "bwd_sweep_ms" else "rollout_fwd_kernel"
+        plan = _lib.describe_plan(eng.prob, eng.tune)       # sweep variant + launch geometry the planner chose
+        ctas = plan["ctas"]
+        kname = ("cluster_" if plan["variant"] == 1 else "rollout_") + ("bwd_kernel" if dom == "bwd_sweep_ms" else "fwd_kernel")
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # dram__bytes_read+write per launch, from
         if cfg == "c2" and os.path.exists(tpath):                             # the committed `ncu --set full` capture
@@ -356,11 +356,20 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16 burst (kernel timed alone)" % peaks["source"], "traffic": traffic,
                 "algorithmic_flops_per_launch": flops, "launch_ms": kern[dom],
+                "sweeps": {"variant": "cluster-resident" if plan["variant"] == 1 else "streaming", "ctas": ctas,
+                           "cluster_size": plan["cluster_size"], "particles_per_group": plan["particles_per_group"],
+                           "smem_bytes_per_cta": plan["smem_bwd_bytes" if dom == "bwd_sweep_ms" else "smem_fwd_bytes"]},
                 "sms_occupied": min(ctas, 148),
                 "frac_of_occupied_sm_peak": achieved / (peak * min(ctas, 148) / 148.0),
                 "arithmetic": "fp32 FFMA (CUDA cores); fp32 SIMT peak of the occupied SMs = %.2f TFLOP/s"
                               % (min(ctas, 148) * 128 * 2 * 1.9e9 / 1e12)}
 
+    launches_per_iter = None
+    try:
+        pi = _lib.describe_plan(eng.prob, eng.tune)
+        launches_per_iter = pi["launches_fwd"] + pi["launches_bwd"] + 2
+    except Exception:
+        pass
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(cfg)
@@ -377,7 +386,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rollout-steps/s",
                     "h2d_bytes_per_step": int(x0_glob_host.numel() * 4), "d2h_bytes_per_step": 4,
                     "api": "prob_mbrl_b200.mc_pilco(x0_host, dynamics, policy, H, opt, exp, K, pegasus=True)"},
-            "gpu_launches": args.steps * (3 + nlin + 3),   # pack, fwd, bwd, wgrad/layer, reduce, norm, adam
+            # per iteration: pack + forward sweep; [adjoint-factor pre-pass] + reverse sweep + one weight-gradient
+            # kernel per policy layer + partial reduction; gradient norm + Adam
+            "gpu_launches": args.steps * (launches_per_iter if launches_per_iter else 3 + nlin + 3),
             "kernels_ms": kern, "roofline": roof, "loss": loss_val,
         }
         if cb is not None:

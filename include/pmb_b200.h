@@ -112,6 +112,21 @@ int pmb_check_problem(const pmb_problem *p, const pmb_tuning *tune);
  * reverse sweep, packed weights, per-layer deltas, split-K partials). */
 size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune);
 
+/* What the planner chose for `p` (no device work): which sweep variant pmb_rollout_forward/backward will launch
+ * and with which geometry.  Used by hosts for reporting (bench.py's roofline) and by the tests. */
+typedef struct pmb_plan_info {
+    int variant;             /* 0 = streaming sweeps (TMA weight ring), 1 = cluster-resident sweeps */
+    int ctas;                /* CTAs of one sweep launch */
+    int threads_per_cta;
+    int cluster_size;        /* CTAs per thread-block cluster (1 for the streaming sweeps) */
+    int particles_per_group; /* particles per CTA (streaming) / per cluster (cluster-resident) */
+    int smem_fwd_bytes;      /* dynamic shared memory per CTA of the forward / reverse sweep */
+    int smem_bwd_bytes;
+    int launches_fwd;        /* kernels one pmb_rollout_forward / pmb_rollout_backward call launches */
+    int launches_bwd;
+} pmb_plan_info;
+int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_info *info);
+
 /* Number of floats of the flat policy gradient: sum over linear layers of W (+ b when present), in
  * policy.parameters() order  W0, b0, W1, b1, ... */
 size_t pmb_policy_param_count(const pmb_problem *p);

@@ -63,7 +63,14 @@ class PmbAdamTensor(C.Structure):
                 ("exp_avg_sq", C.c_void_p), ("n", C.c_longlong)]
 
 
+class PmbPlanInfo(C.Structure):
+    _fields_ = [("variant", C.c_int), ("ctas", C.c_int), ("threads_per_cta", C.c_int), ("cluster_size", C.c_int),
+                ("particles_per_group", C.c_int), ("smem_fwd_bytes", C.c_int), ("smem_bwd_bytes", C.c_int),
+                ("launches_fwd", C.c_int), ("launches_bwd", C.c_int)]
+
+
 EXPORTS = ("pmb_abi_version", "pmb_last_error", "pmb_check_problem", "pmb_workspace_bytes", "pmb_policy_param_count",
+           "pmb_plan_describe",
            "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step")
 
 _lib = None
@@ -92,6 +99,8 @@ def load():
     lib.pmb_check_problem.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)]
     lib.pmb_workspace_bytes.restype = C.c_size_t
     lib.pmb_workspace_bytes.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)]
+    lib.pmb_plan_describe.restype = C.c_int
+    lib.pmb_plan_describe.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning), C.POINTER(PmbPlanInfo)]
     lib.pmb_policy_param_count.restype = C.c_size_t
     lib.pmb_policy_param_count.argtypes = [C.POINTER(PmbProblem)]
     lib.pmb_rollout_forward.restype = C.c_int
@@ -234,6 +243,18 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
                          | ((0 if pp is None else int(pp) + 1) << 8))
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
+
+
+def describe_plan(prob, tune):
+    """Sweep variant and launch geometry the planner chose for `prob` (dict of the pmb_plan_info fields)."""
+    from .operands import NotEligible
+    info = PmbPlanInfo()
+    lib = load()
+    rc = lib.pmb_plan_describe(C.byref(prob), C.byref(tune), C.byref(info))
+    if rc == PMB_E_UNSUPPORTED:
+        raise NotEligible(lib.pmb_last_error().decode("utf-8", "replace"))
+    check(rc)
+    return {f: getattr(info, f) for f, _ in PmbPlanInfo._fields_}
 
 
 def current_stream_ptr():

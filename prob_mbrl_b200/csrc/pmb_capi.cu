@@ -569,6 +569,36 @@ size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune) {
     return (size_t)pl.ws_floats * sizeof(float);
 }
 
+int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_info *info) {
+    if (!info) return fail(PMB_E_INVALID, "info is NULL");
+    Plan pl;
+    int rc = build_plan(p, tune, pl);
+    if (rc != PMB_OK) return rc;
+    memset(info, 0, sizeof(*info));
+    if (pl.cluster) {
+        info->variant = 1;
+        info->ctas = pl.cl_nclusters * pl.cluster;
+        info->threads_per_cta = CL_NT;
+        info->cluster_size = pl.cluster;
+        info->particles_per_group = pl.cfwd.PG;
+        info->smem_fwd_bytes = pl.cfwd.smem_floats * 4;
+        info->smem_bwd_bytes = pl.cbwd.smem_floats * 4;
+    } else {
+        info->variant = 0;
+        info->ctas = (p->N + pl.P - 1) / pl.P;
+        info->threads_per_cta = NT_LAUNCH;
+        info->cluster_size = 1;
+        info->particles_per_group = pl.P;
+        info->smem_fwd_bytes = pl.smem_fwd_bytes;
+        info->smem_bwd_bytes = pl.smem_bwd_bytes;
+    }
+    // pack + sweep (+ reward matching); [reward matching adjoint] + [adjoint-factor pre-pass] + sweep +
+    // one weight-gradient kernel per policy layer + partial reduction
+    info->launches_fwd = 2 + (p->mm_rewards ? 1 : 0);
+    info->launches_bwd = (p->mm_rewards ? 1 : 0) + (pl.cluster ? 1 : 0) + 1 + pl.n_wg + 1;
+    return PMB_OK;
+}
+
 size_t pmb_policy_param_count(const pmb_problem *p) {
     if (!p) return 0;
     size_t n = 0;

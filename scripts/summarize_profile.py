@@ -37,7 +37,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "launch__cluster_dim_x", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__icc_request_hit_rate.pct",
         "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_barrier",
@@ -46,7 +46,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle"]
 traffic = {}
 with open(os.path.join(out, tag + "_sweeps_ncu_full.txt"), "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:rollout_ -s 2 -c 2 python scripts/profile_target.py c2 2\n")
+    f.write("ncu --set full --clock-control none --import-source on -k 'regex:cluster_(fwd|bwd)_kernel|rollout_' -s 2 -c 2 python scripts/profile_target.py c2 2\n")
     f.write("units row: " + ", ".join("%s=%s" % (h, rows[1][hdr.index(h)]) for h in want[1:8] if h in hdr) + "\n\n")
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]

@@ -113,6 +113,32 @@ def test_planner_accepts_the_baseline_configs(lib):
     assert lib.pmb_policy_param_count(C.byref(_fake_problem())) == 200 * 5 + 200 + 200 * 200 + 200 + 2 * 200 + 2
 
 
+def test_planner_picks_the_sweep_variant(lib, monkeypatch):
+    """Two hidden layers of <= 256 units without state moment matching run on the cluster-resident sweeps (weights in
+    the shared memory of an 8-CTA cluster, two 4-slot particle tiles per CTA); everything else on the streaming
+    sweeps.  stream_mode 2 forces streaming, 3 requires cluster-resident."""
+    from prob_mbrl_b200 import _lib
+    from prob_mbrl_b200.operands import NotEligible
+    monkeypatch.delenv("PMB_STREAM_MODE", raising=False)
+    auto = _lib.make_tuning()
+    c2 = _lib.describe_plan(_fake_problem(), auto)
+    assert c2["variant"] == 1 and c2["cluster_size"] == 8 and c2["threads_per_cta"] == 256
+    assert 1 <= c2["particles_per_group"] <= 8 and c2["ctas"] % 8 == 0
+    assert c2["ctas"] // 8 * c2["particles_per_group"] >= 100
+    assert c2["smem_fwd_bytes"] <= 232448 and c2["smem_bwd_bytes"] <= 232448
+    assert c2["launches_fwd"] == 2 and c2["launches_bwd"] == 1 + 1 + 3 + 1
+    for kw in (dict(N=100, H=400, mm=True), dict(N=125, H=600, D=8, hid=(400, 400, 400)), dict(N=250, H=1000, hid=(512, 512))):
+        info = _lib.describe_plan(_fake_problem(**kw), auto)
+        assert info["variant"] == 0 and info["cluster_size"] == 1, kw
+    ring = _lib.describe_plan(_fake_problem(), _lib.make_tuning(stream_mode=2))
+    assert ring["variant"] == 0 and ring["launches_bwd"] == 1 + 3 + 1
+    with pytest.raises(NotEligible):
+        _lib.describe_plan(_fake_problem(hid=(400, 400, 400)), _lib.make_tuning(stream_mode=3))
+    # ragged particle counts: the last cluster is partly filled
+    small = _lib.describe_plan(_fake_problem(N=7, H=12, hid=(37, 37)), auto)
+    assert small["variant"] == 1 and small["ctas"] // 8 * small["particles_per_group"] >= 7
+
+
 def test_planner_rejects_what_the_kernels_cannot_run(lib):
     from prob_mbrl_b200 import _lib
     from prob_mbrl_b200.operands import NotEligible
