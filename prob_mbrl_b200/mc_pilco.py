@@ -71,10 +71,12 @@ class FusedIteration:
         self.nbytes = self.lib.pmb_workspace_bytes(C.byref(self.prob), C.byref(self.tune))
         self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev)
         self.nparam = int(self.lib.pmb_policy_param_count(C.byref(self.prob)))
-        self.grad_flat = torch.zeros(self.nparam, **f32)
+        # flat policy gradient + the loss in one buffer: ONE all-reduce per iteration when sharded
+        self.reduced = torch.zeros(self.nparam + 1, **f32)
+        self.grad_flat = self.reduced[:self.nparam]
         self.dx0 = torch.empty(N, D, **f32)
         self.scratch = torch.zeros(1024, **f32)
-        self.loss = torch.zeros((), **f32)
+        self.loss = self.reduced[self.nparam]
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         # p.grad become views of the flat gradient (what NCCL reduces and clip+Adam consume)
         off = 0
@@ -175,7 +177,7 @@ class FusedIteration:
         torch.mul(self.rewards, self.g_rewards, out=self.weighted)
         torch.sum(self.weighted.view(-1), 0, out=self.loss)
         if self.grad_sync is not None:
-            self.grad_sync(self.grad_flat, self.loss)
+            self.grad_sync(self.reduced, None)
         _lib.check(lib.pmb_clip_adam_step(self.adam_table.data_ptr(), len(self.params), self.clip, self.lr,
                                           self.b1, self.b2, self.eps, 0, self.step_dev.data_ptr(),
                                           self.scratch.data_ptr(), st))
@@ -183,6 +185,8 @@ class FusedIteration:
     def step(self, x0):
         """Run one iteration from particles ``x0`` (device tensor [N, D]); returns the loss tensor."""
         self.x0.copy_(x0, non_blocking=True)
+        # single GPU: one CUDA graph per iteration.  Sharded: the iteration runs un-graphed around the NCCL
+        # all-reduce (capturing the collective with torch 2.11 / NCCL 2.28 hung on 2xB200, so it is not offered).
         use_graph = os.environ.get("PMB_CUDA_GRAPH", "1") != "0" and self.grad_sync is None
         if use_graph:
             if self.graph is None:
