@@ -403,7 +403,7 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
     pl.cfwd.PG = pl.cbwd.PG = PG;
     {
         const int st = (tune && mode == 3) ? (tune->reserved[1] >> 8) & 0xffff : 0;
-        pl.cfwd.stagger = pl.cbwd.stagger = st ? (st - 1) : 1;
+        pl.cfwd.pingpong = pl.cbwd.pingpong = st ? (st - 1) : 1;
     }
     pl.cl_nclusters = (p->N + PG - 1) / PG;
     pl.cluster = C;

@@ -56,7 +56,7 @@ struct CNet {
 struct ClusterParams {
     int N, H, D, U;
     int PG;                     // particles per cluster
-    int stagger;                // != 0: the two particle tiles of a CTA alternate on the LSU-bound phases
+    int pingpong;               // != 0: the two particle tiles of a CTA alternate on the LSU-bound phases
     int C;                      // CTAs per cluster
     CNet pol, dyn;
     const float *wpack;         // packed weights of THIS sweep
@@ -284,18 +284,15 @@ __device__ __forceinline__ void ct_narrow_send(float v, const float *__restrict_
     }
 #pragma unroll
     for (; m >= 1; m >>= 1) pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], m);
-    // output o = lane / s sits in every lane of its group of s = 32 / NV lanes; gather 4 neighbouring outputs
+    // output o = lane / s sits in every lane of its group of s = 32 / NV lanes.  Lane = (chunk, destination rank)
+    // inside a group of G = 4s lanes fetches the chunk's four outputs straight from their holders, so that ONE
+    // st.async instruction serves every destination.
     constexpr int s = 32 / NV;
-    const float q1 = __shfl_sync(0xffffffffu, pr[0], (lane + s) & 31);
-    const float q2 = __shfl_sync(0xffffffffu, pr[0], (lane + 2 * s) & 31);
-    const float q3 = __shfl_sync(0xffffffffu, pr[0], (lane + 3 * s) & 31);
-    if (dbgp && lane == 0) dbgp[0] = clock64();
-    // chunk c = outputs 4c..4c+3 now sits in lane c * 4s.  Spread it over the 4s lanes of its group so that ONE
-    // st.async instruction serves every destination: lane = (chunk, destination rank).
     constexpr int G = 4 * s;
     const int src = lane & ~(G - 1);
-    const float4 out = make_float4(__shfl_sync(0xffffffffu, pr[0], src), __shfl_sync(0xffffffffu, q1, src),
-                                   __shfl_sync(0xffffffffu, q2, src), __shfl_sync(0xffffffffu, q3, src));
+    const float4 out = make_float4(__shfl_sync(0xffffffffu, pr[0], src), __shfl_sync(0xffffffffu, pr[0], src + s),
+                                   __shfl_sync(0xffffffffu, pr[0], src + 2 * s), __shfl_sync(0xffffffffu, pr[0], src + 3 * s));
+    if (dbgp && lane == 0) dbgp[0] = clock64();
     const int dst = lane & (G - 1), chunk = lane / G;
     if (send_ok && dst < C && 4 * chunk < nN) {
         const uint32_t a0 = cl_mapa(mbox_saddr + slot_off + (uint32_t)chunk * 16u, 0), b0 = cl_mapa(bar_saddr, 0);

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
 
-    const bool pingpong = prm.stagger != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
+    const bool pingpong = prm.pingpong != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
     if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
     // ---- prologue: everything step H-1 needs ----

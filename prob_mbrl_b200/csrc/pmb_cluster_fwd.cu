@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     __syncthreads();
     cl_sync();          // every CTA's barriers are initialised and armed before any peer may signal them
 
-    const bool pingpong = prm.stagger != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
+    const bool pingpong = prm.pingpong != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
     if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
 #pragma unroll 1
@@ -328,15 +328,18 @@ cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStre
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    const int tk = max(prm.pol.tK, prm.dyn.tK) <= 8 ? 8 : 16;
+    const int tkm = max(prm.pol.tK, prm.dyn.tK);
+    const int tk = tkm <= 6 ? 6 : tkm <= 8 ? 8 : 16;
 #define PMB_CL_FWD(CC, TT)                                                                                      \
     if (prm.C == CC && tk == TT) {                                                                              \
         if ((e = cluster_launch_cfg((const void *)cluster_fwd_kernel<CC, TT>, CC, smem_bytes)) != cudaSuccess)  \
             return e;                                                                                           \
         return cudaLaunchKernelEx(&cfg, cluster_fwd_kernel<CC, TT>, prm);                                       \
     }
+    PMB_CL_FWD(8, 6)
     PMB_CL_FWD(8, 8)
     PMB_CL_FWD(8, 16)
+    PMB_CL_FWD(4, 6)
     PMB_CL_FWD(4, 8)
     PMB_CL_FWD(4, 16)
 #undef PMB_CL_FWD
