@@ -340,7 +340,6 @@ static int cluster_carve(ClusterParams &P, bool reverse) {
         CNet &n = *nets[i];
         n.s_tw = take(CL_NO * n.tW);        // rows >= tK stay zero (the thin layer runs whole 4-row blocks)
         n.s_ww = take(n.tW * n.hs);
-        n.s_nw = take(n.nN * n.hs);
         n.s_nwt = take(CL_NO * CL_HS);
         n.s_tb = take(n.tW);
         n.s_wb = take(n.hs);
@@ -353,9 +352,7 @@ static int cluster_carve(ClusterParams &P, bool reverse) {
     P.off_xb = take(2 * CL_NO * CL_PS);
     P.off_act = take(tw_max * CL_PS);
     P.off_red = take(CL_KS * CL_PS * 32);
-    P.off_h2s = take(CL_PS * 32);
-    P.off_part = take(CL_INBOX);
-    P.off_inbox = take(2 * P.C * CL_INBOX);
+    P.off_inbox = take(2 * 2 * P.C * CL_MBOX);        // [tile][exchange][sender rank][4 slots x 16]
     P.off_misc = take(reverse ? (4 + 2 * 6) * CL_PS * SD + 32 : CL_PS * SD);
     P.smem_floats = off;
     return off;

@@ -25,7 +25,6 @@ constexpr int CL_PS = 8;       // particle slots of a cluster tile
 constexpr int CL_HS = 32;      // widest column slice per CTA
 constexpr int CL_TW = 256;     // widest thin layer (= K of the wide layer)
 constexpr int CL_NO = 16;      // narrow outputs / thin inputs (max)
-constexpr int CL_INBOX = CL_PS * CL_NO;   // floats one CTA sends per exchange (max)
 constexpr int CL_TS = 4;                  // particle slots per tile (= warps per warp group; two tiles per cluster)
 constexpr int CL_GT = 128;                // threads per warp group
 constexpr int CL_MBOX = CL_TS * CL_NO;    // floats one (CTA, group) sends per exchange
@@ -49,7 +48,7 @@ struct CNet {
     float lmax;
     const float *z;
     long long zstride;
-    int s_tw, s_ww, s_nw, s_tb, s_wb, s_nb, s_tm, s_wm;   // shared-memory offsets (floats)
+    int s_tw, s_ww, s_tb, s_wb, s_nb, s_tm, s_wm;         // shared-memory offsets (floats)
     int s_nwt;                // narrow matrix of this CTA's columns as [4][CL_HS][4]: (o >> 2, column, o & 3)
 };
 
@@ -71,7 +70,7 @@ struct ClusterParams {
     float *dx0;
     float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
     long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)
-    int off_cst, off_xa, off_xb, off_act, off_red, off_h2s, off_part, off_inbox, off_misc;
+    int off_cst, off_xa, off_xb, off_act, off_red, off_inbox, off_misc;
     int smem_floats;
 };
 
@@ -106,7 +105,6 @@ __device__ __forceinline__ float2 cl_fma2(float a, float2 w, float2 c) {
     return __ffma2_rn(make_float2(a, a), w, c);
 }
 
-#define CL_MARK(i) do { if (dbg_on) prm.dbg[(i)] = clock64(); } while (0)
 // per-warp arrival marks (lane 0 of every warp), placed BEFORE barriers: dbg[i * 8 + warp]
 #define CL_TMARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0) prm.dbg[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
 
@@ -135,13 +133,6 @@ __device__ __forceinline__ void cl_load_net(const ClusterParams &prm, const CNet
         float4 v = z4;
         if (gc < n.wN) v = __ldg(reinterpret_cast<const float4 *>(prm.wpack + n.w_goff + (long long)k * n.wN + gc));
         *reinterpret_cast<float4 *>(smem + n.s_ww + k * n.hs + 4 * c4) = v;
-    }
-    for (int i = tid; i < n.nN * hs4; i += CL_NT) {
-        const int o = i / hs4, c4 = i - o * hs4;
-        const int gc = rank * n.hs + 4 * c4;
-        float4 v = z4;
-        if (gc < n.wN) v = __ldg(reinterpret_cast<const float4 *>(prm.wpack + n.n_goff + (long long)o * n.wN + gc));
-        *reinterpret_cast<float4 *>(smem + n.s_nw + o * n.hs + 4 * c4) = v;
     }
     for (int i = tid; i < CL_NO * CL_HS; i += CL_NT) {
         const int o = i / CL_HS, c = i - o * CL_HS;

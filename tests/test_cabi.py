@@ -139,6 +139,33 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     assert small["variant"] == 1 and small["ctas"] // 8 * small["particles_per_group"] >= 7
 
 
+def test_cluster_tunables_from_the_environment(lib, monkeypatch):
+    """PMB_STREAM_MODE=3 + PMB_CLUSTER_PG / PMB_CLUSTER_C / PMB_CLUSTER_PINGPONG reach the planner through
+    pmb_tuning.reserved[1]; bad values are rejected by the library, not silently clamped."""
+    from prob_mbrl_b200 import _lib
+    monkeypatch.setenv("PMB_STREAM_MODE", "3")
+    monkeypatch.setenv("PMB_CLUSTER_PG", "5")
+    monkeypatch.setenv("PMB_CLUSTER_C", "8")
+    monkeypatch.setenv("PMB_CLUSTER_PINGPONG", "0")
+    t = _lib.make_tuning()
+    assert t.stream_mode == 3 and t.reserved[1] == (5 | (8 << 4) | (1 << 8))
+    info = _lib.describe_plan(_fake_problem(), t)
+    assert info["variant"] == 1 and info["particles_per_group"] == 5 and info["ctas"] == 20 * 8
+    monkeypatch.setenv("PMB_CLUSTER_C", "4")         # 200 columns / 4 CTAs = 52 per CTA > 32: outside the kernels
+    from prob_mbrl_b200.operands import NotEligible
+    with pytest.raises(NotEligible):
+        _lib.describe_plan(_fake_problem(), _lib.make_tuning())
+    monkeypatch.setenv("PMB_CLUSTER_C", "8")
+    monkeypatch.setenv("PMB_CLUSTER_PG", "9")
+    with pytest.raises(RuntimeError):
+        _lib.describe_plan(_fake_problem(), _lib.make_tuning())
+    # narrow nets fit a 4-CTA cluster
+    monkeypatch.setenv("PMB_CLUSTER_PG", "2")
+    monkeypatch.setenv("PMB_CLUSTER_C", "4")
+    info = _lib.describe_plan(_fake_problem(N=7, H=12, hid=(37, 37)), _lib.make_tuning())
+    assert info["cluster_size"] == 4 and info["ctas"] == 4 * 4
+
+
 def test_planner_rejects_what_the_kernels_cannot_run(lib):
     from prob_mbrl_b200 import _lib
     from prob_mbrl_b200.operands import NotEligible
