@@ -169,6 +169,37 @@ def cpu_baseline(cfg, budget_s=15.0, threads=None, iters_min=2):
     return best
 
 
+def gpu_eager_baseline(cfg, device, iters=3, Hs=40):
+    """The same mc_pilco iteration as a plain PyTorch module loop + autograd on `device` (what the reference does
+    with `--use_cuda`: ~220 ATen kernels per imagined step), on a bounded sample: same nets and particle count,
+    horizon cut to Hs.  Context for the fused numbers, not a target."""
+    import prob_mbrl_b200 as pm
+    _, D, U, _, hid, n, H = CONFIGS[cfg]
+    dyn, pol, x0, _ = build_workload(cfg, n, device)
+    opt = torch.optim.Adam(pol.parameters(), 1e-4)
+    old = os.environ.get("PROB_MBRL_BACKEND")
+    os.environ["PROB_MBRL_BACKEND"] = "eager"
+    try:
+        kw = dict(pegasus=True, mm_states=False, mm_rewards=False, maximize=True, clip_grad=1.0,
+                  resampling_period=10 ** 9, init_state_noise=0.0)
+        x0 = x0.to(device)
+        pm.mc_pilco(x0, dyn, pol, Hs, opt, None, 1, **kw)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pm.mc_pilco(x0, dyn, pol, Hs, opt, None, iters, **kw)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        if old is None:
+            os.environ.pop("PROB_MBRL_BACKEND", None)
+        else:
+            os.environ["PROB_MBRL_BACKEND"] = old
+    return {"value": n * Hs * iters / dt, "unit": "rollout-steps/s", "kind": "PyTorch eager module loop + autograd on the GPU",
+            "sample": "%d mc_pilco iterations, N=%d, H=%d (of %d)" % (iters, n, Hs, H)}
+
+
 def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return
@@ -393,6 +424,10 @@ def main():
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(cfg, dev)
+            except Exception as e:                      # context only: never fail the bench line over it
+                line["gpu_eager_baseline"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
