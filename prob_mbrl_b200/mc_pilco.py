@@ -296,6 +296,7 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
             and _on_device_loop_ok(value_func, cvar_eps, reg_weight, prioritized_replay, opt, policy,
                                    on_rollout, debug, rollout_kwargs))
     engine = None
+    readback, pending = None, None
     pbar = tqdm.tqdm(range(opt_iters), total=opt_iters, disable=os.environ.get("PMB_NO_PBAR") == "1")
     pbar_every = max(1, int(os.environ.get("PMB_PBAR_EVERY", "1")))
     sign = -1.0 if maximize else 1.0
@@ -309,7 +310,9 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
         x0_ = x0
         if mm_groups is not None and x0_.shape[0] == mm_groups:
             x0_ = tile(x0_, int(N_particles / mm_groups))
-        x0_ = x0_.to(dev, dt)
+        # non_blocking: a pinned host batch (exp.sample_states(...)) is uploaded without stalling the host on the
+        # previous iteration still running on the stream
+        x0_ = x0_.to(dev, dt, non_blocking=True)
         x0_ = x0_ + init_state_noise * torch.randn_like(x0_)
         if sharder is not None:
             # every rank holds the full-N noise (identical seeds); take this rank's rows of everything
@@ -418,17 +421,34 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
             continue
         n_opt_steps += 1
         if (i + 1) % pbar_every == 0 or i + 1 == opt_iters:
-            pbar.set_description((msg % float(R.detach().sum(0).mean())) + " [{0}]".format(R.shape[0]))
+            if R.is_cuda:
+                # progress line without a pipeline bubble: the predicted return goes to pinned host memory
+                # asynchronously and is shown once the NEXT iteration is already queued (the loop end flushes)
+                if readback is None:
+                    readback = [(torch.empty((), dtype=torch.float32, pin_memory=True), torch.cuda.Event())
+                                for _ in range(2)]
+                buf, ev = readback[i & 1]
+                buf.copy_(R.detach().sum(0).mean(), non_blocking=True)
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    pbar.set_description((msg % float(pending[0])) + " [{0}]".format(R.shape[0]))
+                pending = (buf, ev)
+            else:
+                pbar.set_description((msg % float(R.detach().sum(0).mean())) + " [{0}]".format(R.shape[0]))
         if callable(on_iteration):
             lists = _as_lists(S, A, R)
             on_iteration(i, loss, lists[0], lists[1], lists[2], disc)
         if exp is not None:
             nsamp = mm_groups if mm_groups is not None else N_particles
-            x0 = exp.sample_states(nsamp, timestep=step_idx_to_sample).to(dev, dt)
+            x0 = exp.sample_states(nsamp, timestep=step_idx_to_sample).to(dev, dt, non_blocking=True)
             init_states = x0
         else:
             x0 = init_states.detach()
 
+    if pending is not None:
+        pending[1].synchronize()
+        pbar.set_description((msg % float(pending[0])) + " [{0}]".format(H))
     if sharder is not None:
         sharder.widen()
     policy.eval()
