@@ -164,7 +164,8 @@ class FusedIteration:
         return [id(p) for p in g["params"]] == [id(p) for p in params]
 
     # -- one iteration -------------------------------------------------------------------------
-    def _enqueue(self):
+    def _enqueue_sweeps(self):
+        """Forward sweep, reverse sweep + weight gradient, loss: everything before the gradient is complete."""
         lib, st = self.lib, _lib.current_stream_ptr()
         pb, tb = C.byref(self.prob), C.byref(self.tune)
         _lib.check(lib.pmb_rollout_forward(pb, tb, self.x0.data_ptr(), self.states.data_ptr(),
@@ -176,37 +177,58 @@ class FusedIteration:
                                             self.nbytes, st))
         torch.mul(self.rewards, self.g_rewards, out=self.weighted)
         torch.sum(self.weighted.view(-1), 0, out=self.loss)
+
+    def _enqueue_update(self):
+        """Gradient clip + Adam on the (reduced) flat gradient."""
+        _lib.check(self.lib.pmb_clip_adam_step(self.adam_table.data_ptr(), len(self.params), self.clip, self.lr,
+                                               self.b1, self.b2, self.eps, 0, self.step_dev.data_ptr(),
+                                               self.scratch.data_ptr(), _lib.current_stream_ptr()))
+
+    def _enqueue(self):
+        self._enqueue_sweeps()
         if self.grad_sync is not None:
             self.grad_sync(self.reduced, None)
-        _lib.check(lib.pmb_clip_adam_step(self.adam_table.data_ptr(), len(self.params), self.clip, self.lr,
-                                          self.b1, self.b2, self.eps, 0, self.step_dev.data_ptr(),
-                                          self.scratch.data_ptr(), st))
+        self._enqueue_update()
+
+    def _capture(self, fns):
+        """Warm up outside capture (cudaFuncSetAttribute, lazy module load, NCCL communicator), then capture one
+        CUDA graph per function of `fns`; the optimiser / parameter state is restored afterwards."""
+        self._sync_adam_counter()
+        saved = [t.clone() for t in self._mutable_state()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, v in zip(self._mutable_state(), saved):
+            t.copy_(v)
+        graphs = []
+        for fn in fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            graphs.append(g)
+        for t, v in zip(self._mutable_state(), saved):
+            t.copy_(v)
+        return graphs
 
     def step(self, x0):
         """Run one iteration from particles ``x0`` (device tensor [N, D]); returns the loss tensor."""
         self.x0.copy_(x0, non_blocking=True)
-        # single GPU: one CUDA graph per iteration.  Sharded: the iteration runs un-graphed around the NCCL
-        # all-reduce (capturing the collective with torch 2.11 / NCCL 2.28 hung on 2xB200, so it is not offered).
-        use_graph = os.environ.get("PMB_CUDA_GRAPH", "1") != "0" and self.grad_sync is None
-        if use_graph:
+        # Single GPU: the whole iteration replays from ONE CUDA graph.  Sharded: two graphs (sweeps / clip+Adam)
+        # around the NCCL all-reduce, which stays an ordinary stream-ordered call (capturing the collective itself
+        # hung with torch 2.11 / NCCL 2.28 on 2xB200).  PMB_CUDA_GRAPH=0: plain launches.
+        if os.environ.get("PMB_CUDA_GRAPH", "1") != "0":
             if self.graph is None:
-                # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
-                self._sync_adam_counter()
-                saved = [t.clone() for t in self._mutable_state()]
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    self._enqueue()
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                for t, v in zip(self._mutable_state(), saved):
-                    t.copy_(v)
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._enqueue()
-                for t, v in zip(self._mutable_state(), saved):
-                    t.copy_(v)
-            self.graph.replay()
+                if self.grad_sync is None:
+                    self.graph = self._capture([self._enqueue])
+                else:
+                    self.graph = self._capture([self._enqueue_sweeps, self._enqueue_update])
+            self.graph[0].replay()
+            if self.grad_sync is not None:
+                self.grad_sync(self.reduced, None)
+                self.graph[1].replay()
         else:
             self._enqueue()
         self.adam_step += 1
