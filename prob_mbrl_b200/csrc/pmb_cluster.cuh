@@ -21,7 +21,7 @@
 namespace pmb {
 
 constexpr int CL_NT = 256;     // threads per CTA (8 warps, all compute)
-constexpr int CL_PS = 8;       // particle slots of a cluster tile
+constexpr int CL_PS = 8;       // particle slots per cluster (two tiles of CL_TS slots)
 constexpr int CL_HS = 32;      // widest column slice per CTA
 constexpr int CL_TW = 256;     // widest thin layer (= K of the wide layer)
 constexpr int CL_NO = 16;      // narrow outputs / thin inputs (max)

@@ -167,6 +167,21 @@ def test_particles_per_cluster_variants(PG, C):
     assert gu.rel_l2(r["dx0"], g["nomm_dx0"]) < 1e-5
 
 
+def test_planner_runs_the_bench_workload_on_the_cluster_resident_sweeps(monkeypatch):
+    """On the device the planner sizes the clusters from the co-residency query: c2 (100 particles, 2x[200]) lands on
+    the cluster-resident sweeps with all 100 particles in flight at once (one wave of 8-CTA clusters)."""
+    from prob_mbrl_b200 import _lib
+    monkeypatch.delenv("PMB_STREAM_MODE", raising=False)
+    ops, g = gu.load("cartpole_200x2_n100_h400")
+    o = _ops_cuda(ops)
+    prob, keep = _lib.make_problem(o, 100, int(g["H"]))
+    info = _lib.describe_plan(prob, _lib.make_tuning())
+    assert info["variant"] == 1 and info["cluster_size"] == 8
+    assert info["ctas"] <= 148 and info["ctas"] // 8 * info["particles_per_group"] >= 100
+    mm = _lib.make_problem(o, 100, int(g["H"]), mm_states=True, z_mm=torch.zeros(500, o.D, device="cuda"))[0]
+    assert _lib.describe_plan(mm, _lib.make_tuning())["variant"] == 0      # moment matching: streaming sweeps
+
+
 def test_sweep_variants_agree():
     """The streaming and the cluster-resident sweeps give the same trajectory and gradient to fp32 rounding."""
     ops, g = gu.load("cartpole_200x2_n25_h40")
