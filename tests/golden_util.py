@@ -76,3 +76,42 @@ def modules_from_ops(ops, device="cpu"):
     dyn.eval()
     pol.train()
     return dyn.to(device), pol.to(device)
+
+
+def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32):
+    """Random operand bundle with the fixtures' key schema for shapes the reference's environments do not offer
+    (e.g. U > 1): checked against the oracle instead of a golden file."""
+    g = torch.Generator().manual_seed(seed)
+
+    def r(*s):
+        return torch.randn(*s, generator=g)
+
+    ops = {"D": D, "U": U, "pol_L": len(hid), "dyn_L": len(hid)}
+    for tag, nin, nout in (("pol", D, 2 * U), ("dyn", D + U, 2 * D)):
+        dims = [nin] + list(hid) + [nout]
+        for i in range(len(dims) - 1):
+            scale = (2.0 / dims[i]) ** 0.5 * (0.3 if (i == len(dims) - 2 and tag == "dyn") else 1.0)
+            ops["%s_W%d" % (tag, i)] = r(dims[i + 1], dims[i]) * scale
+            ops["%s_b%d" % (tag, i)] = 0.1 * r(dims[i + 1])
+        for i, h in enumerate(hid):
+            ops["%s_mask%d" % (tag, i)] = (torch.rand(N, h, generator=g) < 0.9).float()
+            ops["%s_p%d" % (tag, i)] = 0.9 if tag == "pol" else 1.0
+        ops[tag + "_has_density"] = 1
+        ops[tag + "_z"] = r(N, U if tag == "pol" else D)
+        ops[tag + "_lmax"] = float(torch.tensor(5.0).log())
+    ops["act_scale"] = torch.tensor([2.0, 0.5, 1.0, 3.0][:U])
+    ops["act_bias"] = torch.tensor([0.0, 0.1, -0.2, 0.3][:U])
+    ops["mx"] = 0.1 * r(D + U)
+    ops["iSx"] = 1.0 / (0.5 + torch.rand(D + U, generator=g))
+    ops["my"] = 0.01 * r(D)
+    ops["Sy"] = 0.05 * (0.5 + torch.rand(D, generator=g))
+    ops["rew_C"] = r(2, D)
+    ops["rew_c0"] = 0.1 * r(2)
+    Q = r(2, 2)
+    ops["rew_Q"] = Q @ Q.T + torch.eye(2)
+    R = 0.1 * r(U, U)
+    ops["rew_R"] = R @ R.T + 1e-2 * torch.eye(U)
+    ops["rew_scale"] = 1.0
+    ops["rew_offset"] = 0.0
+    x0 = 0.3 * r(N, D)
+    return {k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in ops.items()}, x0.to(dtype)
