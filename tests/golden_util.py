@@ -78,7 +78,7 @@ def modules_from_ops(ops, device="cpu"):
     return dyn.to(device), pol.to(device)
 
 
-def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32):
+def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32, pol_density=True, dyn_density=True):
     """Random operand bundle with the fixtures' key schema for shapes the reference's environments do not offer
     (e.g. U > 1): checked against the oracle instead of a golden file."""
     g = torch.Generator().manual_seed(seed)
@@ -87,7 +87,8 @@ def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32):
         return torch.randn(*s, generator=g)
 
     ops = {"D": D, "U": U, "pol_L": len(hid), "dyn_L": len(hid)}
-    for tag, nin, nout in (("pol", D, 2 * U), ("dyn", D + U, 2 * D)):
+    for tag, nin, nout, dens in (("pol", D, 2 * U if pol_density else U, pol_density),
+                                 ("dyn", D + U, 2 * D if dyn_density else D, dyn_density)):
         dims = [nin] + list(hid) + [nout]
         for i in range(len(dims) - 1):
             scale = (2.0 / dims[i]) ** 0.5 * (0.3 if (i == len(dims) - 2 and tag == "dyn") else 1.0)
@@ -96,8 +97,9 @@ def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32):
         for i, h in enumerate(hid):
             ops["%s_mask%d" % (tag, i)] = (torch.rand(N, h, generator=g) < 0.9).float()
             ops["%s_p%d" % (tag, i)] = 0.9 if tag == "pol" else 1.0
-        ops[tag + "_has_density"] = 1
-        ops[tag + "_z"] = r(N, U if tag == "pol" else D)
+        ops[tag + "_has_density"] = int(dens)
+        if dens:
+            ops[tag + "_z"] = r(N, U if tag == "pol" else D)
         ops[tag + "_lmax"] = float(torch.tensor(5.0).log())
     ops["act_scale"] = torch.tensor([2.0, 0.5, 1.0, 3.0][:U])
     ops["act_bias"] = torch.tensor([0.0, 0.1, -0.2, 0.3][:U])

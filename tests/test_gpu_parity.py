@@ -212,6 +212,25 @@ def test_multi_dimensional_actions_match_oracle(D, U, sweeps):
     assert gu.rel_l2(rc["dx0"], auto[-1]) < 2e-5
 
 
+@pytest.mark.parametrize("sweeps", ["ring", "cluster"])
+@pytest.mark.parametrize("pol_density,dyn_density", [(False, True), (True, False), (False, False)])
+def test_nets_without_output_density_match_oracle(pol_density, dyn_density, sweeps):
+    """Deterministic policy (plain Linear output, models/core.py:243 applies tanh to it) and / or a dynamics model
+    without output_density (models/core.py:185: outs * Sy + my): against the fp64 oracle."""
+    kw = dict(D=3, U=2, hid=(24, 20), N=9, pol_density=pol_density, dyn_density=dyn_density)
+    ops, x0 = gu.synthetic_ops(**kw)
+    ops64, x064 = gu.synthetic_ops(dtype=torch.float64, **kw)
+    H = 7
+    r = _run(ops, x0, H, env=SWEEPS[sweeps])
+    ref = orc.loss_and_grads(ops64, x064, H)
+    keys = orc.policy_param_keys(ops64)
+    assert (r["S"].double() - torch.stack(ref["states"])).abs().max() < 5e-6
+    assert (r["A"].double() - torch.stack(ref["actions"])).abs().max() < 2e-5
+    assert abs(float(r["obj"]) - float(ref["loss"])) < 2e-6
+    assert gu.rel_l2(r["grads"], [ref["grads"][k] for k in keys]) < 2e-5
+    assert gu.rel_l2(r["dx0"], ref["dx0"]) < 2e-5
+
+
 def test_sweep_variants_agree():
     """The streaming and the cluster-resident sweeps give the same trajectory and gradient to fp32 rounding."""
     ops, g = gu.load("cartpole_200x2_n25_h40")
