@@ -174,7 +174,7 @@ __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const 
         if (R.thin_store) *R.dl_thin = act[R.tcol * CL_TS + (gtid >> 5)];
         R.dl_thin -= R.thin_step;
     }
-    // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split over the half-warps of the group ----
+    // ---- wide: this CTA's columns of the adjoint of hidden 0, k-split 16 ways over the quarter-warps of the group ----
     ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
     if (pingpong) CT_LSU_RELEASE(g);
     CL_TMARK(mark0 + 1);

@@ -100,7 +100,7 @@ __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const C
     // hidden 0 is kept for the reverse sweep: one coalesced row segment per warp (= particle slot), off the tile
     if (R.thin_store) *R.sv_thin = act[R.tcol * CL_TS + (gtid >> 5)];
     R.sv_thin += R.thin_step;
-    // ---- wide: this CTA's columns of hidden 1, k-split over the half-warps of the group ----
+    // ---- wide: this CTA's columns of hidden 1, k-split 16 ways over the quarter-warps of the group ----
     ct_wide_accum(smem + n.s_ww, n.tW, n.hs, act, red, gtid);
     if (pingpong) CT_LSU_RELEASE(g);
     CL_TMARK(mark0 + 1);
