@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PMB_ABI_VERSION 1
+#define PMB_ABI_VERSION 2
 #define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
 #define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
 #define PMB_MAX_REWARD_ROWS 4 /* rows of the tip map C */
@@ -170,10 +170,14 @@ typedef struct pmb_adam_tensor {
  *   step        1-based step count of THIS update (bias correction), used when step_dev is NULL
  *   step_dev    optional device counter: when non-NULL it is incremented on the device and used as
  *               the step count, so the call can be replayed from a CUDA graph
- *   scratch_dev device scratch of >= 1024 floats; scratch_dev[0] receives the total grad norm. */
+ *   scratch_dev device scratch of >= 1024 floats; scratch_dev[0] receives the total grad norm.
+ *   skip_if_nonzero optional device int32 (the status word of pmb_rollout_forward): when it is non-zero at
+ *               execution time the whole update is a no-op (parameters, moments and step_dev untouched) --
+ *               the reference raises inside rollout and skips the iteration without an update
+ *               (algorithms/mc_pilco.py:122-131). */
 int pmb_clip_adam_step(const pmb_adam_tensor *table_dev, int n_tensors, float max_norm,
                        float lr, float beta1, float beta2, float eps, long long step,
-                       long long *step_dev, float *scratch_dev, void *stream);
+                       long long *step_dev, float *scratch_dev, const int *skip_if_nonzero, void *stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpmb_b200.so")
 PMB_MAX_LINEAR = 6
 PMB_MAX_WIDTH = 1024
 PMB_MAX_STATE = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = C.POINTER(C.c_float)
 
@@ -77,7 +77,17 @@ _lib = None
 
 
 class LibraryMissing(RuntimeError):
-    pass
+    """libpmb_b200.so is absent / has the wrong ABI.  Never a numerical failure: mc_pilco re-raises it."""
+
+
+class LibraryError(RuntimeError):
+    """A library call returned a PMB_E_* code (bad descriptor, workspace, CUDA runtime failure).
+    Distinct from the numerical failures the reference's ``except RuntimeError`` is meant for
+    (algorithms/mc_pilco.py:122-131): mc_pilco re-raises it instead of skipping the iteration."""
+
+    def __init__(self, code, msg):
+        super().__init__("libpmb_b200 error %d: %s" % (code, msg))
+        self.code = code
 
 
 def load():
@@ -111,7 +121,7 @@ def load():
                                         [C.c_size_t, C.c_void_p]
     lib.pmb_clip_adam_step.restype = C.c_int
     lib.pmb_clip_adam_step.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
-                                       C.c_float, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_float, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.pmb_abi_version() != ABI_VERSION:
         raise LibraryMissing("ABI version mismatch: library %d, binding %d" % (lib.pmb_abi_version(), ABI_VERSION))
     _lib = lib
@@ -121,7 +131,7 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().pmb_last_error().decode("utf-8", "replace")
-        raise RuntimeError("libpmb_b200 error %d: %s" % (rc, msg))
+        raise LibraryError(rc, msg)
 
 
 PMB_E_UNSUPPORTED = -2
@@ -143,14 +153,14 @@ def _ptr(t):
 
 def _f32c(t, what):
     if t.dtype != torch.float32 or not t.is_cuda:
-        raise RuntimeError("%s must be a CUDA float32 tensor (got %s on %s)" % (what, t.dtype, t.device))
+        raise LibraryError(-1, "%s must be a CUDA float32 tensor (got %s on %s)" % (what, t.dtype, t.device))
     return t if t.is_contiguous() else t.contiguous()
 
 
 def _fill_net(dst, net, n_rows, out_dims, keepalive):
     L = len(net.W) - 1
     if L + 1 > PMB_MAX_LINEAR:
-        raise RuntimeError("network has %d linear layers, the fused path supports %d" % (L + 1, PMB_MAX_LINEAR))
+        raise LibraryError(-2, "network has %d linear layers, the fused path supports %d" % (L + 1, PMB_MAX_LINEAR))
     dst.n_linear = L + 1
     dst.dims[0] = net.W[0].shape[1]
     for i, w in enumerate(net.W):
@@ -168,7 +178,7 @@ def _fill_net(dst, net, n_rows, out_dims, keepalive):
         if net.mask[i] is not None:
             m = _f32c(net.mask[i], "dropout mask")
             if m.shape[0] < n_rows or m.shape[1] != net.W[i].shape[0]:
-                raise RuntimeError("dropout mask %d has shape %s" % (i, tuple(m.shape)))
+                raise LibraryError(-1, "dropout mask %d has shape %s" % (i, tuple(m.shape)))
             keepalive.append(m)
             dst.mask[i] = m.data_ptr()
         else:
@@ -184,7 +194,7 @@ def _fill_net(dst, net, n_rows, out_dims, keepalive):
         else:
             dst.z_step_stride = 0
         if z.shape[-1] != out_dims or z.shape[-2] < n_rows:
-            raise RuntimeError("density noise has shape %s" % (tuple(z.shape),))
+            raise LibraryError(-1, "density noise has shape %s" % (tuple(z.shape),))
         if z.dim() == 2 and z.shape[0] != n_rows:
             # rows beyond N are never read, but the row stride must be out_dims: fine as is
             pass

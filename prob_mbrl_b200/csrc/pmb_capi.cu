@@ -389,8 +389,13 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
     int PG = (tune && mode == 3) ? tune->reserved[1] & 15 : 0;
     if (PG < 0 || PG > CL_PS) return fail(PMB_E_INVALID, "particles per cluster must be 1..%d", CL_PS);
     if (PG == 0) {
-        static int cached[2] = {-1, -1};
-        int &mc = cached[C == 8];
+        // co-resident clusters of this kernel, queried once per (device, cluster size)
+        static int cached[32][2];
+        static bool cached_init = false;
+        if (!cached_init) { for (auto &c : cached) c[0] = c[1] = -1; cached_init = true; }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+        int &mc = cached[dev][C == 8];
         if (mc < 0) mc = cluster_max_active(C, max(pl.cfwd.smem_floats, pl.cbwd.smem_floats) * 4, true);
         const int maxc = mc > 0 ? mc : (C == 8 ? 16 : 32);
         PG = (p->N + maxc - 1) / maxc;
@@ -696,11 +701,11 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
 
 int pmb_clip_adam_step(const pmb_adam_tensor *table_dev, int n_tensors, float max_norm, float lr, float beta1,
                        float beta2, float eps, long long step, long long *step_dev, float *scratch_dev,
-                       void *stream) {
+                       const int *skip_if_nonzero, void *stream) {
     if (!table_dev || n_tensors < 1 || !scratch_dev || (!step_dev && step < 1))
         return fail(PMB_E_INVALID, "bad optimiser arguments");
     PMB_CUDA(launch_clip_adam(table_dev, n_tensors, max_norm, lr, beta1, beta2, eps, step, step_dev, scratch_dev,
-                              (cudaStream_t)stream));
+                              skip_if_nonzero, (cudaStream_t)stream));
     return PMB_OK;
 }
 

@@ -29,6 +29,7 @@ cudaError_t launch_reward_mm_fwd(const float *rpre, float *rout, const float *z_
 cudaError_t launch_reward_mm_bwd(const float *gout, const float *rpre, const float *z_rr, const float *rstat, float *gin,
                                  int N, int H, int G, cudaStream_t stream);
 cudaError_t launch_clip_adam(const pmb_adam_tensor *tab, int nt, float max_norm, float lr, float beta1, float beta2,
-                             float eps, long long step, long long *step_dev, float *scratch, cudaStream_t stream);
+                             float eps, long long step, long long *step_dev, float *scratch, const int *skip,
+                             cudaStream_t stream);
 
 }  // namespace pmb

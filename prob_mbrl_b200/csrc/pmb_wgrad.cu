@@ -347,8 +347,10 @@ cudaError_t launch_reduce_partials(const float *part, long long n, int nsplit, f
 constexpr int NORM_BLOCKS = 128;
 
 __global__ void __launch_bounds__(256) gradnorm_kernel(const pmb_adam_tensor *__restrict__ tab, int nt,
-                                                       float *__restrict__ scratch, long long *step_dev) {
+                                                       float *__restrict__ scratch, long long *step_dev,
+                                                       const int *__restrict__ skip) {
     __shared__ float sm[8];
+    if (skip && *skip != 0) return;      // failed rollout (status word): no update at all
     if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) step_dev[0] += 1;   // read by adam_kernel (next launch)
     float s = 0.f;
     for (int t = 0; t < nt; ++t) {
@@ -373,8 +375,10 @@ __global__ void __launch_bounds__(256) gradnorm_kernel(const pmb_adam_tensor *__
 __global__ void __launch_bounds__(256) adam_kernel(const pmb_adam_tensor *__restrict__ tab, int nt, float max_norm,
                                                    float beta1, float beta2, float eps, float lr, float step_size,
                                                    float bc2_sqrt, const long long *__restrict__ step_dev,
-                                                   float *__restrict__ scratch, int norm_blocks) {
+                                                   float *__restrict__ scratch, int norm_blocks,
+                                                   const int *__restrict__ skip) {
     __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    if (skip && *skip != 0) return;
     if (threadIdx.x == 0) {
         if (step_dev) {   // bias corrections from the device-side step counter (CUDA-graph replay)
             double st = (double)step_dev[0];
@@ -419,16 +423,16 @@ __global__ void __launch_bounds__(256) adam_kernel(const pmb_adam_tensor *__rest
 }
 
 cudaError_t launch_clip_adam(const pmb_adam_tensor *tab, int nt, float max_norm, float lr, float beta1, float beta2,
-                             float eps, long long step, long long *step_dev, float *scratch,
+                             float eps, long long step, long long *step_dev, float *scratch, const int *skip,
                              cudaStream_t stream) {
-    gradnorm_kernel<<<NORM_BLOCKS, 256, 0, stream>>>(tab, nt, scratch, step_dev);
+    gradnorm_kernel<<<NORM_BLOCKS, 256, 0, stream>>>(tab, nt, scratch, step_dev, skip);
     if (step < 1) step = 1;
     double bc1 = 1.0 - pow((double)beta1, (double)step);
     double bc2 = 1.0 - pow((double)beta2, (double)step);
     float step_size = (float)((double)lr / bc1);
     float bc2_sqrt = (float)sqrt(bc2);
     adam_kernel<<<NORM_BLOCKS, 256, 0, stream>>>(tab, nt, max_norm, beta1, beta2, eps, lr, step_size, bc2_sqrt,
-                                                 step_dev, scratch, NORM_BLOCKS);
+                                                 step_dev, scratch, NORM_BLOCKS, skip);
     return cudaGetLastError();
 }
 

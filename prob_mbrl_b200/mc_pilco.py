@@ -101,8 +101,24 @@ class FusedIteration:
         buf.copy_(t)
         return buf
 
+    @staticmethod
+    def _signature(ops):
+        """Everything the problem descriptor bakes in besides the engine-owned static buffers: the storage of every
+        weight / bias (the modules re-bind them with ``.data =`` in Regressor.load / Policy.load, reference
+        models/core.py:154-159,214-219) and the scalar fields."""
+        sig = []
+        for net in (ops.pol, ops.dyn):
+            for w, b in zip(net.W, net.b):
+                sig += [w.data_ptr(), tuple(w.shape), None if b is None else b.data_ptr()]
+            sig += [tuple(float(x) for x in net.p), bool(net.has_density), float(net.lmax)]
+        sig += [float(ops.rew.scale), float(ops.rew.offset), tuple(ops.rew.C.shape)]
+        return tuple(sig)
+
     def refresh(self):
-        """(Re)read the modules after a resample(); rebuilds the descriptor only when a pointer moved."""
+        """(Re)read the modules (after a resample(), at the start of another mc_pilco call).  Masks, noise, scalers
+        and the reward operands are COPIED into engine-owned buffers, so a module that re-binds them (resample():
+        models/modules.py:44; set_dataset(): models/core.py:142-149) only changes values the captured graph reads;
+        the descriptor and the graph are rebuilt when a weight moved or a shape / scalar changed."""
         N = self.N
         try:
             ops = operands.extract(self.dynamics, self.policy, N)
@@ -121,6 +137,14 @@ class FusedIteration:
         for k in ("z_mm", "z_rr"):
             if mm.get(k) is not None:
                 mm[k] = self._static_copy(k, mm[k][:N])
+        for name in ("act_scale", "act_bias", "mx", "iSx", "my", "Sy"):
+            setattr(ops, name, self._static_copy(name, getattr(ops, name)))
+        for name in ("C", "c0", "Q", "R"):
+            setattr(ops.rew, name, self._static_copy("rew_" + name, getattr(ops.rew, name)))
+        sig = self._signature(ops)
+        if sig != getattr(self, "_sig", None):
+            self._sig = sig
+            self.prob = None
         self.ops = ops
         if self.prob is None:
             self.prob, self.keep = _lib.make_problem(ops, N, self.H, **mm)
@@ -128,10 +152,23 @@ class FusedIteration:
             self.graph = None
 
     # -- optimiser -----------------------------------------------------------------------------
+    def _hyper_now(self):
+        g = self.opt.param_groups[0]
+        return (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]))
+
+    def _adam_sig_now(self):
+        sig = []
+        for p in self.params:
+            st = self.opt.state[p]
+            if len(st) == 0:
+                return None
+            sig += [p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()]
+        return tuple(sig)
+
     def _init_adam(self):
         opt = self.opt
-        g = opt.param_groups[0]
-        self.lr, (self.b1, self.b2), self.eps = float(g["lr"]), g["betas"], float(g["eps"])
+        self._hyper = self._hyper_now()
+        self.lr, self.b1, self.b2, self.eps = self._hyper
         entries = (_lib.PmbAdamTensor * len(self.params))()
         for i, p in enumerate(self.params):
             st = opt.state[p]
@@ -148,7 +185,8 @@ class FusedIteration:
         self.adam_table = raw.to(self.dev)
         self.adam_step = int(float(opt.state[self.params[0]]["step"]))
         self.step_dev.fill_(self.adam_step)
-        self._adam_ptr0 = opt.state[self.params[0]]["exp_avg"].data_ptr()
+        self._adam_sig = self._adam_sig_now()
+        self.graph = None
 
     @staticmethod
     def adam_is_plain(opt, params):
@@ -179,10 +217,13 @@ class FusedIteration:
         torch.sum(self.weighted.view(-1), 0, out=self.loss)
 
     def _enqueue_update(self):
-        """Gradient clip + Adam on the (reduced) flat gradient."""
+        """Gradient clip + Adam on the (reduced) flat gradient.  With moment matching the update is predicated on
+        the device status word: a failed Cholesky leaves parameters, moments and the step counter untouched, like
+        the reference which raises inside rollout and skips the iteration (algorithms/mc_pilco.py:122-131)."""
+        guard = self.status.data_ptr() if (self.mm.get("mm_states") or self.mm.get("mm_rewards")) else None
         _lib.check(self.lib.pmb_clip_adam_step(self.adam_table.data_ptr(), len(self.params), self.clip, self.lr,
                                                self.b1, self.b2, self.eps, 0, self.step_dev.data_ptr(),
-                                               self.scratch.data_ptr(), _lib.current_stream_ptr()))
+                                               self.scratch.data_ptr(), guard, _lib.current_stream_ptr()))
 
     def _enqueue(self):
         self._enqueue_sweeps()
@@ -216,6 +257,12 @@ class FusedIteration:
     def step(self, x0):
         """Run one iteration from particles ``x0`` (device tensor [N, D]); returns the loss tensor."""
         self.x0.copy_(x0, non_blocking=True)
+        if self._hyper_now() != self._hyper:
+            # lr / betas / eps are by-value kernel arguments baked into the captured graph: re-read and re-capture
+            # when the user (or an LR scheduler) changed them
+            self._hyper = self._hyper_now()
+            self.lr, self.b1, self.b2, self.eps = self._hyper
+            self.graph = None
         # Single GPU: the whole iteration replays from ONE CUDA graph.  Sharded: two graphs (sweeps / clip+Adam)
         # around the NCCL all-reduce, which stays an ordinary stream-ordered call (capturing the collective itself
         # hung with torch 2.11 / NCCL 2.28 on 2xB200).  PMB_CUDA_GRAPH=0: plain launches.
@@ -237,6 +284,13 @@ class FusedIteration:
             self.opt.state[p]["step"] += 1
         return self.loss
 
+    def undo_step_count(self):
+        """The device skipped the update of the last step() (status word set): take the host-side step counters
+        back as well."""
+        self.adam_step -= 1
+        for p in self.params:
+            self.opt.state[p]["step"] -= 1
+
     def _mutable_state(self):
         out = [self.step_dev]
         for p in self.params:
@@ -250,10 +304,8 @@ class FusedIteration:
     def resync(self):
         """Re-attach to the modules / optimiser at the start of another mc_pilco call."""
         self.refresh()
-        st = self.opt.state[self.params[0]]
-        if len(st) == 0 or st["exp_avg"].data_ptr() != self._adam_ptr0:
-            self._init_adam()        # optimiser state was reset or reloaded
-            self.graph = None
+        if self._adam_sig_now() != self._adam_sig:
+            self._init_adam()        # optimiser state reset / reloaded, or the parameters were re-bound (Policy.load)
         self.adam_step = int(float(self.opt.state[self.params[0]]["step"]))
         self._sync_adam_counter()
 
@@ -348,57 +400,69 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
                 sharder.narrow()
             x0_ = x0_[sharder.row0:sharder.row0 + sharder.n]
         Nloc = x0_.shape[0]
-        try:
-            if fast and pegasus:
-                if engine is None or engine.N != Nloc:
-                    weights = tuple(sign * disc(t) for t in range(H))
-                    key = (id(policy), id(dynamics), id(opt), Nloc, H, clip_grad, weights, world,
-                           bool(mm_states), bool(mm_rewards), mm_groups)
-                    hit = _ENGINES.get(key)
-                    if hit is not None and hit[0]() is policy and hit[1]() is opt:
-                        engine = hit[2]
-                        engine.mm.update(z_mm=z_mm if mm_states else None, z_rr=z_rr if mm_rewards else None)
-                        engine.x0.copy_(x0_)
-                        engine.resync()
-                    else:
-                        g_r = torch.tensor(weights, dtype=torch.float32, device=dev)
-                        g_r = (g_r / (Nloc * world))[:, None].expand(H, Nloc).contiguous()
-                        sync = dist.allreduce_gradient if world > 1 else None
-                        engine = FusedIteration(dynamics, policy, x0_, H, opt, g_r, clip_grad,
-                                                dict(mm_states=mm_states, mm_rewards=mm_rewards, mm_groups=mm_groups,
-                                                     z_mm=z_mm if mm_states else None,
-                                                     z_rr=z_rr if mm_rewards else None), sync)
-                        if len(_ENGINES) > 8:
-                            _ENGINES.clear()
-                        _ENGINES[key] = (weakref.ref(policy), weakref.ref(opt), engine)
-                elif need_resample:
-                    engine.refresh()
-                loss = engine.step(x0_)
-                S, A, R = engine.states, engine.actions, engine.rewards
-                if mm_states or mm_rewards:
-                    bad = int(engine.status.item())
-                    if bad:
-                        raise RuntimeError("moment matching: covariance not positive-definite at step %d" % (bad - 1))
-            else:
-                policy.zero_grad()
-                dynamics.zero_grad()
-                opt.zero_grad()
+        # Only a NUMERICAL failure of the rollout is caught (the reference wraps just utils.rollout,
+        # algorithms/mc_pilco.py:101-131): non-PD particle covariance -> resample all random numbers and skip the
+        # iteration without an update.  Library / CUDA errors and ineligible configurations propagate.
+        failed = None
+        if fast and pegasus:
+            if engine is None or engine.N != Nloc:
+                weights = tuple(sign * disc(t) for t in range(H))
+                key = (id(policy), id(dynamics), id(opt), Nloc, H, clip_grad, weights, world,
+                       bool(mm_states), bool(mm_rewards), mm_groups)
+                hit = _ENGINES.get(key)
+                if hit is not None and hit[0]() is policy and hit[1]() is opt:
+                    engine = hit[2]
+                    engine.mm.update(z_mm=z_mm if mm_states else None, z_rr=z_rr if mm_rewards else None)
+                    engine.x0.copy_(x0_)
+                    engine.resync()
+                else:
+                    g_r = torch.tensor(weights, dtype=torch.float32, device=dev)
+                    g_r = (g_r / (Nloc * world))[:, None].expand(H, Nloc).contiguous()
+                    sync = dist.allreduce_gradient if world > 1 else None
+                    engine = FusedIteration(dynamics, policy, x0_, H, opt, g_r, clip_grad,
+                                            dict(mm_states=mm_states, mm_rewards=mm_rewards, mm_groups=mm_groups,
+                                                 z_mm=z_mm if mm_states else None,
+                                                 z_rr=z_rr if mm_rewards else None), sync)
+                    if len(_ENGINES) > 8:
+                        _ENGINES.clear()
+                    _ENGINES[key] = (weakref.ref(policy), weakref.ref(opt), engine)
+            elif need_resample:
+                engine.refresh()
+            loss = engine.step(x0_)
+            S, A, R = engine.states, engine.actions, engine.rewards
+            if mm_states or mm_rewards:
+                bad = int(engine.status.item())
+                if bad:
+                    # the device predicated clip + Adam on the status word: nothing was updated
+                    engine.undo_step_count()
+                    failed = "moment matching: covariance not positive-definite at step %d" % (bad - 1)
+        else:
+            policy.zero_grad()
+            dynamics.zero_grad()
+            opt.zero_grad()
+            lists = None
+            try:
                 if mode == "eager":
-                    traj = rollout(x0_, dynamics, policy, H, resample_state_noise=not pegasus,
-                                   resample_action_noise=not pegasus, mm_states=mm_states, mm_rewards=mm_rewards,
-                                   z_mm=z_mm if pegasus else None, z_rr=z_rr if pegasus else None,
-                                   mm_groups=mm_groups, **rollout_kwargs)
-                    S, A = torch.stack(traj[0]), torch.stack(traj[1])
-                    R = torch.stack(traj[2]).squeeze(-1)
-                    lists = traj
+                    lists = rollout(x0_, dynamics, policy, H, resample_state_noise=not pegasus,
+                                    resample_action_noise=not pegasus, mm_states=mm_states, mm_rewards=mm_rewards,
+                                    z_mm=z_mm if pegasus else None, z_rr=z_rr if pegasus else None,
+                                    mm_groups=mm_groups, **rollout_kwargs)
+                    S, A = torch.stack(lists[0]), torch.stack(lists[1])
+                    R = torch.stack(lists[2]).squeeze(-1)
                 else:
                     S, A, R, status = fused_rollout_tensors(
                         x0_, dynamics, policy, H, mm_states, mm_rewards, z_mm if pegasus else None,
                         z_rr if pegasus else None, mm_groups, not pegasus, not pegasus)
-                    lists = None
                     if (mm_states or mm_rewards) and int(status.item()):
-                        raise RuntimeError("moment matching: covariance not positive-definite at step %d"
-                                           % (int(status.item()) - 1))
+                        failed = ("moment matching: covariance not positive-definite at step %d"
+                                  % (int(status.item()) - 1))
+            except RuntimeError as e:
+                if isinstance(e, (_lib.LibraryMissing, _lib.LibraryError)):
+                    raise
+                import traceback
+                traceback.print_exc()
+                failed = str(e)
+            if failed is None:
                 if callable(on_rollout):
                     lists = lists or _as_lists(S, A, R)
                     on_rollout(i, lists[0], lists[1], lists[2], disc)
@@ -426,10 +490,8 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
                 if clip_grad is not None:
                     torch.nn.utils.clip_grad_norm_(policy.parameters(), clip_grad)
                 opt.step()
-        except RuntimeError:
-            import traceback
-            traceback.print_exc()
-            print("RuntimeError")
+        if failed is not None:
+            print("RuntimeError: %s" % failed)
             if sharder is not None:
                 sharder.widen()
             resample()

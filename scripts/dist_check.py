@@ -1,4 +1,4 @@
-"""2-rank NCCL check (torchrun): particle-sharded fused iteration == single-GPU iteration on the same
+"""N-rank NCCL check (torchrun; 24 particles: N = 2, 4 or 8): particle-sharded fused iteration == single-GPU iteration on the same
 global batch.  Rank 0 prints PASS/FAIL."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,7 +32,8 @@ def run(distributed):
             pm.dist.world = saved
     return torch.cat([p.detach().flatten() for p in pol.parameters()]), losses
 
-dist.init_process_group("nccl", device_id=dev)
+import datetime
+dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 p_single, l_single = run(False)
 p_shard, l_shard = run(True)
 err = float((p_single - p_shard).abs().max())

@@ -11,7 +11,7 @@ import prob_mbrl_b200 as pm
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n = bench.CONFIGS[cfg][5]
-dyn, pol, x0, H = bench.build_workload(cfg, n, "cuda")
+dyn, pol, x0, H, mm = bench.build_workload(cfg, n, "cuda")
 opt = torch.optim.Adam(pol.parameters(), 1e-4)
 g_r = torch.full((H, n), -1.0 / (H * n), device="cuda")
 eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0)

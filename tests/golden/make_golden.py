@@ -82,15 +82,30 @@ def save(name, ops, extra):
     print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
 
 
-def fixture_rollout(name, envname, hid, N, H, kat=None, with_mm=True, thin=None, mm_groups=None):
+def whiten_rows(z, N):
+    """Zero-mean, identity-sample-covariance copy of the first N rows of z (with the raw
+    table the reference's own moment-matched rollout explodes by construction, App. D-7)."""
+    zz = z[:N].double()
+    zz = zz - zz.mean(0, keepdim=True)
+    L = torch.linalg.cholesky(zz.T @ zz / (N - 1))
+    zz = torch.linalg.solve_triangular(L, zz.T, upper=False).T
+    out = z.clone()
+    out[:N] = zz.float()
+    return out
+
+
+def fixture_rollout(name, envname, hid, N, H, kat=None, with_mm=True, thin=None, mm_groups=None, whiten=False,
+                    with_nomm=True):
     env, dyn, pol, x0, z_mm, z_rr = build(envname, hid, N, H)
+    if whiten:
+        z_mm = whiten_rows(z_mm, N)
     ops = operands.extract(dyn, pol, N)
     extra = {"x0": x0, "z_mm": z_mm, "z_rr": z_rr, "H": H, "N": N}
-    res = run_reference(dyn, pol, x0, H, False, z_mm, z_rr)
+    res = run_reference(dyn, pol, x0, H, False, z_mm, z_rr) if with_nomm else None
     if kat is not None:
         assert abs(float(res["loss"]) - kat) < 5e-9, (float(res["loss"]), kat)
         print("  KAT (SURVEY App. C.3) reproduced: loss32 = %.11f" % float(res["loss"]))
-    modes = [("nomm", res)]
+    modes = [("nomm", res)] if with_nomm else []
     if with_mm:
         modes.append(("mm", run_reference(dyn, pol, x0, H, True, z_mm, z_rr)))
         if mm_groups:
@@ -145,7 +160,16 @@ def fixture_mc_pilco(name, envname, hid, N, H, iters, lr, mm=False):
     print("  losses:", losses)
 
 
+def main_c3():
+    # c3: configs[2] -- c2 with moment matching of states and rewards, z_mm[:N] whitened
+    fixture_rollout("cartpole_200x2_n100_h400_mm", "Cartpole", [200, 200], 100, 400, with_mm=True, thin=25,
+                    whiten=True, with_nomm=False)
+
+
 if __name__ == "__main__":
+    if "--c3" in sys.argv:
+        main_c3()
+        sys.exit(0)
     # c1: BASELINE.json configs[0] -- Cartpole 2x[200], 25 particles, H=40
     fixture_rollout("cartpole_200x2_n25_h40", "Cartpole", [200, 200], 25, 40, kat=-0.12317804247)
     # small double-pole (D=8, 3 hidden layers) with mm_groups
@@ -158,3 +182,4 @@ if __name__ == "__main__":
     # mc_pilco iterations (reference's own loop + torch Adam)
     fixture_mc_pilco("mcpilco_cartpole_32x2_n16_h10", "Cartpole", [32, 32], 16, 10, iters=6, lr=1e-3)
     fixture_mc_pilco("mcpilco_mm_cartpole_32x2_n16_h10", "Cartpole", [32, 32], 16, 10, iters=4, lr=1e-3, mm=True)
+    main_c3()

@@ -1,121 +1,16 @@
-"""Import shim that lets the UNMODIFIED reference (mcgillmrl/prob_mbrl, mounted
-read-only at /root/reference) import under Python 3.12 / torch 2.11 in the build
-container.  Fixture-generation / cross-check infrastructure only: it is used by
-`make_golden.py` and by the CPU tests that compare against the live reference
-when `/root/reference` is present.  Nothing on the product path imports it, and
-it is never used on the GPU box (the reference does not exist there).
-
-What it papers over:
-  * `collections.Iterable` was removed in Python 3.10 (reference: utils/core.py:8,
-    models/core.py:7, utils/experience_dataset.py:241);
-  * third-party modules imported at package-import time that the rollout path never
-    touches: matplotlib, gym, Box2D, tensorboardX.
-"""
-import collections
-import collections.abc
+"""The import shim for the unmodified reference lives in baseline/ref_shim.py (it is shared with the
+reference arm of bench.py and the acceptance runner); re-exported here for the fixture generators."""
 import os
 import sys
-import types
 
-import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "baseline"))
+import importlib.util as _ilu
 
-REFERENCE_ROOT = os.environ.get("PROB_MBRL_REFERENCE", "/root/reference")
-
-
-def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "prob_mbrl"))
-
-
-def _lenient(factory):
-    def getter(name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return factory()
-    return getter
-
-
-def _stub(name, **attrs):
-    mod = types.ModuleType(name)
-    mod.__dict__.update(attrs)
-    sys.modules[name] = mod
-    return mod
-
-
-class _Anything:
-    """Class whose instances swallow every call/attribute (plot/Box2D stand-ins)."""
-
-    def __init__(self, *a, **k):
-        pass
-
-    def __call__(self, *a, **k):
-        return _Anything()
-
-    def __getattr__(self, item):
-        if item.startswith("__"):
-            raise AttributeError(item)
-        return _Anything()
-
-
-class _Box:
-    def __init__(self, low, high, shape=None, dtype=np.float32):
-        self.low = np.asarray(low, dtype=dtype)
-        self.high = np.asarray(high, dtype=dtype)
-        self.shape = self.low.shape
-        self.dtype = dtype
-
-    def sample(self):
-        return np.random.uniform(self.low, self.high).astype(self.dtype)
-
-
-class _Env:
-    spec = None
-    metadata = {}
-    reward_range = (-float("inf"), float("inf"))
-
-    def seed(self, seed=None):
-        return [seed]
-
-
-class _EzPickle:
-    def __init__(self, *a, **k):
-        pass
-
-
-def _np_random(seed=None):
-    return np.random.RandomState(seed), seed
-
-
-def install():
-    """Install the stubs and put the reference on sys.path. Idempotent."""
-    if not available():
-        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
-    import torch  # noqa: F401  (import before the stubs exist: torch introspects sys.modules)
-    if not hasattr(collections, "Iterable"):
-        collections.Iterable = collections.abc.Iterable
-    if "matplotlib" not in sys.modules:
-        plt = _stub("matplotlib.pyplot")
-        plt.__getattr__ = _lenient(_Anything)
-        mpl = _stub("matplotlib", pyplot=plt)
-        mpl.__getattr__ = _lenient(_Anything)
-    if "gym" not in sys.modules:
-        spaces = _stub("gym.spaces", Box=_Box)
-        seeding = _stub("gym.utils.seeding", np_random=_np_random)
-        gutils = _stub("gym.utils", seeding=seeding, EzPickle=_EzPickle)
-        _stub("gym", Env=_Env, spaces=spaces, utils=gutils)
-    if "Box2D" not in sys.modules:
-        names = ("edgeShape", "circleShape", "fixtureDef", "polygonShape",
-                 "revoluteJointDef", "contactListener")
-        b2 = _stub("Box2D.b2", **{n: _Anything for n in names})
-        box2d = _stub("Box2D", b2=b2, **{"b2" + n[0].upper() + n[1:]: _Anything for n in names})
-        box2d.__getattr__ = _lenient(lambda: _Anything)
-    if "tensorboardX" not in sys.modules:
-        class SummaryWriter(_Anything):
-            pass
-        _stub("tensorboardX", SummaryWriter=SummaryWriter)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    import warnings
-    warnings.filterwarnings("ignore", category=UserWarning)
-    warnings.filterwarnings("ignore", category=DeprecationWarning)
-    import prob_mbrl  # noqa: F401
-    return prob_mbrl
+_spec = _ilu.spec_from_file_location(
+    "pmb_baseline_ref_shim",
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "baseline", "ref_shim.py"))
+_mod = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_mod)
+REFERENCE_ROOT = _mod.REFERENCE_ROOT
+available = _mod.available
+install = _mod.install

@@ -34,7 +34,7 @@ def test_other_baseline_shapes_match_oracle(cfg, N, H):
     """3x[400] double-pole (D=8) and 2x[512] nets: wide layers with 2 / 1 k-split groups, three hidden
     layers, larger rings -- against the fp32 and fp64 CPU oracle on the same seeded inputs."""
     from prob_mbrl_b200 import operands
-    dyn, pol, x0, _ = bench.build_workload(cfg, N, "cpu")
+    dyn, pol, x0, _, _ = bench.build_workload(cfg, N, "cpu")
     flat = operands.extract(dyn, pol, N).to_flat()
     ops32 = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in flat.items()}
     ops64 = {k: (v.detach().double() if torch.is_tensor(v) else v) for k, v in flat.items()}
@@ -56,7 +56,7 @@ def test_full_size_c5_shard_properties():
     properties -- particles are independent (a sub-batch reproduces its rows), the reverse sweep is linear
     in the cotangent, results are finite and deterministic."""
     cfg, N, H = "c5", 250, 1000
-    dyn, pol, x0, _ = bench.build_workload(cfg, N, "cuda")
+    dyn, pol, x0, _, _ = bench.build_workload(cfg, N, "cuda")
     S, A, R, g1, dx1, _ = _fused(dyn, pol, x0, H)
     assert torch.isfinite(S).all() and torch.isfinite(R).all() and all(torch.isfinite(g).all() for g in g1)
     assert S.abs().max() < 50 and (R >= 0).all() and (R <= 1).all()
@@ -81,7 +81,7 @@ def test_full_size_c5_shard_properties():
 
 def test_full_size_c4_shard_runs_and_is_finite():
     """configs[3] per-GPU shard (DoubleCartpole 3x[400], 125 particles, H=600)."""
-    dyn, pol, x0, _ = bench.build_workload("c4", 125, "cuda")
+    dyn, pol, x0, _, _ = bench.build_workload("c4", 125, "cuda")
     S, A, R, g, dx, _ = _fused(dyn, pol, x0, 600)
     assert torch.isfinite(S).all() and torch.isfinite(R).all() and all(torch.isfinite(t).all() for t in g)
     assert A.abs().max() <= 20.0 + 1e-4 and (R >= 0).all() and (R <= 1).all()

@@ -67,6 +67,21 @@ def test_c2_full_horizon_matches_reference():
     assert gu.rel_l2([res["grads"][k] for k in keys], gu.policy_grad_list(g, "nomm", ops)) < 1e-5
 
 
+def test_c3_full_horizon_moment_matching_matches_reference():
+    """BASELINE.json configs[2] (c2 with mm_states + mm_rewards, z_mm[:N] whitened per SURVEY.md section 8d):
+    oracle vs the reference's thinned trajectory + gradient.  (fp32-vs-fp64 on this fixture: states 1.8e-6,
+    gradient 3e-6.)"""
+    ops, g = gu.load("cartpole_200x2_n100_h400_mm")
+    res = orc.loss_and_grads(ops, g["x0"], int(g["H"]), mm_states=True, mm_rewards=True, z_mm=g["z_mm"],
+                             z_rr=g["z_rr"])
+    thin = int(g["thin"])
+    assert (torch.stack(res["states"])[::thin] - g["mm_states"]).abs().max() < 2e-5
+    assert abs(float(res["loss"]) - float(g["mm_loss"])) < 1e-7
+    keys = orc.policy_param_keys(ops)
+    assert gu.rel_l2([res["grads"][k] for k in keys], gu.policy_grad_list(g, "mm", ops)) < 2e-5
+    assert float(g["mm_states"].abs().max()) < 5.0          # bounded (the unwhitened table reaches 1e10)
+
+
 def test_fp64_twin_error_budget():
     """fp32 oracle vs fp64 oracle reproduces the reference's own fp32-vs-fp64 error scale
     (grad rel-L2 ~8.5e-8)."""
