@@ -86,10 +86,14 @@ typedef struct pmb_problem {
 /* Tunables (0 = library default). */
 typedef struct pmb_tuning {
     int particles_per_cta;   /* 1, 2, 4 or 8 */
-    int stream_mode;         /* sweep variant: 0 = auto (cluster-resident sweeps when the nets fit, else 2),
+    int stream_mode;         /* sweep variant: 0 = auto (FFMA2 cluster-resident sweeps for two-hidden-layer nets <= 256
+                                wide with <= 128 particles and no moment matching of the states; otherwise the
+                                tensor-core cluster sweeps when eligible; otherwise 2),
                                 1/2 = streaming sweeps (hidden x hidden weights through a TMA + mbarrier ring),
                                 3 = cluster-resident sweeps required (all weights in the shared memory of a
-                                thread-block cluster; PMB_E_UNSUPPORTED when the problem is outside them) */
+                                thread-block cluster; PMB_E_UNSUPPORTED when the problem is outside them),
+                                4 = tensor-core cluster sweeps required (tcgen05 3xTF32 hidden x hidden layers,
+                                16-CTA cluster per 128-particle tile; PMB_E_UNSUPPORTED when outside them) */
     int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
                                 4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default; with
@@ -115,11 +119,12 @@ size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune);
 /* What the planner chose for `p` (no device work): which sweep variant pmb_rollout_forward/backward will launch
  * and with which geometry.  Used by hosts for reporting (bench.py's roofline) and by the tests. */
 typedef struct pmb_plan_info {
-    int variant;             /* 0 = streaming sweeps (TMA weight ring), 1 = cluster-resident sweeps */
+    int variant;             /* 0 = streaming sweeps (TMA weight ring), 1 = cluster-resident FFMA2 sweeps,
+                                2 = tensor-core cluster sweeps */
     int ctas;                /* CTAs of one sweep launch */
     int threads_per_cta;
     int cluster_size;        /* CTAs per thread-block cluster (1 for the streaming sweeps) */
-    int particles_per_group; /* particles per CTA (streaming) / per cluster (cluster-resident) */
+    int particles_per_group; /* particles per CTA (streaming) / per cluster (cluster-resident, tensor-core) */
     int smem_fwd_bytes;      /* dynamic shared memory per CTA of the forward / reverse sweep */
     int smem_bwd_bytes;
     int launches_fwd;        /* kernels one pmb_rollout_forward / pmb_rollout_backward call launches */

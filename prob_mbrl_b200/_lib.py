@@ -242,7 +242,8 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t.reserved[1] = int(os.environ.get("PMB_STAGES", "0"))
     t.reserved[4] = int(os.environ.get("PMB_WGRAD_UMMA", "0"))
     t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))
-    # 0 = auto (cluster-resident sweeps when eligible), 1/2 = streaming sweeps, 3 = cluster-resident (required)
+    # 0 = auto, 1/2 = streaming sweeps, 3 = cluster-resident FFMA2 sweeps (required), 4 = tensor-core cluster
+    # sweeps (required)
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
     if t.stream_mode == 3:
         # particles per cluster (1..8, 0 = auto) and CTAs per cluster (4 or 8, 0 = 8)
@@ -251,6 +252,9 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
         pp = os.environ.get("PMB_CLUSTER_PINGPONG")
         t.reserved[1] = (int(os.environ.get("PMB_CLUSTER_PG", "0")) | (int(os.environ.get("PMB_CLUSTER_C", "0")) << 4)
                          | ((0 if pp is None else int(pp) + 1) << 8))
+    if t.stream_mode == 4:
+        # tensor-core cluster sweeps required; tuning aid: k-blocks per ring stage (bits 0-7), ring stages (bits 8-11)
+        t.reserved[1] = int(os.environ.get("PMB_TC_KBS", "0")) | (int(os.environ.get("PMB_TC_STAGES", "0")) << 8)
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
 

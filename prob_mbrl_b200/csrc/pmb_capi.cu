@@ -10,6 +10,8 @@
 #include "pmb_internal.cuh"
 #include "pmb_mm.cuh"
 #include "pmb_cluster.cuh"
+#include "pmb_tc.cuh"
+#include "pmb_tc_mm.cuh"
 
 namespace pmb {
 
@@ -55,6 +57,13 @@ struct Plan {
     int cl_nclusters;
     long long cl_pre_off;     // [H][N][2D + 3U] step-local adjoint factors of the cluster-resident reverse sweep
     ClusterParams cfwd, cbwd;
+    // tensor-core cluster sweeps (pmb_tc.cuh): used instead of both when chosen
+    int tc;                   // 0 = off, otherwise CTAs per cluster
+    TcParams tfwd, tbwd;
+    TcPackJobs tjobs;         // hi/lo weight slices of both sweep directions
+    PackJobs sjobs;           // the workspace-resident small operands only (padded biases, masks)
+    long long tc_wpack_off, tc_xbuf_off, tc_opart_off;
+    ClusterParams tpre;       // arguments of the adjoint-factor pre-pass (cluster_bwd_pre_kernel)
 };
 
 struct Alloc {
@@ -412,6 +421,169 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
     return PMB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core cluster sweeps: eligibility, operand tables, shared-memory carve-up, workspace (pmb_tc.cuh).
+// Eligible: >= 1 hidden layer per net, hidden widths <= 1024, <= 32 raw outputs, D+U <= 16; with moment matching
+// of the states the whole particle set must fit one tile (N <= 128, <= 16 groups).
+// ---------------------------------------------------------------------------------------------
+static int tc_slice_width(int maxw, int C) {
+    const int per = (maxw + C - 1) / C;
+    return per <= 16 ? 16 : per <= 32 ? 32 : per <= 64 ? 64 : 0;
+}
+
+static bool tc_eligible(const pmb_problem *p, int C) {
+    const pmb_net *nets[2] = {&p->pol, &p->dyn};
+    int maxw = 0;
+    for (int i = 0; i < 2; ++i) {
+        const pmb_net &n = *nets[i];
+        if (n.n_linear < 2) return false;
+        if (n.dims[0] > 16 || n.dims[n.n_linear] > TC_NOUT) return false;
+        for (int l = 1; l < n.n_linear; ++l) maxw = max(maxw, n.dims[l]);
+    }
+    if (tc_slice_width(maxw, C) == 0) return false;
+    if (p->mm_states) {
+        const int G = p->mm_groups > 1 ? p->mm_groups : 1;
+        if (p->N > TC_M || G > TCMM_MAXG) return false;
+    }
+    return true;
+}
+
+static void tc_net(const pmb_net &net, const NetSweep &F, bool reverse, bool is_policy, TcNet &n) {
+    memset(&n, 0, sizeof(n));
+    n.L = net.n_linear - 1;
+    n.nin = net.dims[0];
+    n.nout = net.dims[net.n_linear];
+    for (int l = 0; l < n.L; ++l) {
+        n.width[l] = net.dims[l + 1];
+        n.npad[l] = round4(net.dims[l + 1]);
+        n.kb[l] = (net.dims[l + 1] + 7) / 8;
+        n.mask_off[l] = F.mask_off[l];
+        n.keep_inv[l] = 1.f / F.keep[l];
+        n.saved_off[l] = F.saved_off[l];
+    }
+    for (int l = 0; l <= n.L; ++l) {
+        n.bias_off[l] = reverse ? -1 : F.lin[l].boff;
+        n.delta_off[l] = is_policy ? F.delta_off[l] : -1;
+    }
+    n.W_first = net.W[0];
+    n.W_last = net.W[n.L];
+    n.raw_off = F.outsaved_off;
+    n.has_density = net.has_density;
+    n.lmax = net.max_log_std;
+    n.z = net.z;
+    n.zstride = net.z_step_stride;
+}
+
+// fills pl.tc / pl.tfwd / pl.tbwd; `ws` allocates the extra workspace regions
+static int plan_tc(const pmb_problem *p, const pmb_tuning *tune, Plan &pl, Alloc &ws) {
+    pl.tc = 0;
+    const int mode = tune ? tune->stream_mode : 0;
+    if (mode == 1 || mode == 2 || mode == 3) return PMB_OK;
+    const int C = 16;
+    if (!tc_eligible(p, C)) {
+        if (mode == 4) return fail(PMB_E_UNSUPPORTED, "problem is outside the tensor-core cluster sweeps");
+        return PMB_OK;
+    }
+    if (mode == 0) {
+        // auto: the FFMA2 cluster-resident sweeps keep the shapes they were built for (two hidden layers <= 256 wide,
+        // few particles: BASELINE c1 / c2); everything else that is eligible runs here
+        if (!p->mm_states && cluster_eligible(p, 8) && p->N <= TC_M) return PMB_OK;
+    }
+    int maxw = 0, nop = 1;
+    const pmb_net *nets[2] = {&p->pol, &p->dyn};
+    for (int i = 0; i < 2; ++i) {
+        for (int l = 1; l < nets[i]->n_linear; ++l) maxw = max(maxw, nets[i]->dims[l]);
+        nop = max(nop, max(nets[i]->dims[0], nets[i]->dims[nets[i]->n_linear]));
+    }
+    const int ns = tc_slice_width(maxw, C);
+    const int ntiles = (p->N + TC_M - 1) / TC_M;
+    const int TP = (p->N + ntiles - 1) / ntiles;
+    // ---- hi/lo weight slices of every hidden x hidden layer, both directions ----
+    Alloc wa;
+    pl.tjobs.n = 0;
+    pl.tjobs.C = C;
+    pl.tjobs.ns = ns;
+    for (int pass = 0; pass < 2; ++pass) {
+        TcParams &T = pass ? pl.tbwd : pl.tfwd;
+        memset(&T, 0, sizeof(T));
+        T.N = p->N; T.H = p->H; T.D = p->D; T.U = p->U; T.C = C; T.TP = TP; T.ntiles = ntiles; T.ns = ns;
+        T.kbmax = C * ns / 8;
+        T.nop = nop;
+        tc_net(p->pol, pl.fwd.pol, pass == 1, true, T.pol);
+        tc_net(p->dyn, pl.fwd.dyn, pass == 1, false, T.dyn);
+        for (int i = 0; i < 2; ++i) {
+            TcNet &n = i ? T.dyn : T.pol;
+            const pmb_net &src = *nets[i];
+            for (int l = 1; l < n.L; ++l) {
+                // forward: K = width of hidden l-1; reverse: K = width of hidden l (B[n][k] = W_l[k][n])
+                const int kb = pass ? n.kb[l] : n.kb[l - 1];
+                n.wp_off[l] = wa.take((long long)C * 2 * kb * ns * 8);
+                TcPackJob &j = pl.tjobs.job[pl.tjobs.n++];
+                j.W = src.W[l]; j.out = src.dims[l + 1]; j.in = src.dims[l]; j.transpose = pass; j.dst_off = n.wp_off[l]; j.kb = kb;
+            }
+        }
+        T.act_scale = p->act_scale; T.act_bias = p->act_bias; T.mx = p->mx; T.iSx = p->iSx; T.my = p->my; T.Sy = p->Sy;
+        T.KR = p->rew_rows; T.rew_C = p->rew_C; T.rew_c0 = p->rew_c0; T.rew_Q = p->rew_Q; T.rew_R = p->rew_R;
+        T.rew_scale = p->rew_scale; T.rew_offset = p->rew_offset;
+        T.mm_states = p->mm_states; T.mm_G = pl.mm_G; T.mm_Ng = p->N / pl.mm_G; T.z_mm = p->z_mm;
+        // ---- shared memory ----
+        int off = 0;
+        auto take = [&](int nfl) { int o = off; off += (nfl + 31) & ~31; return o; };
+        T.off_cst = take(C_TOTAL);
+        T.off_res = off;
+        for (int i = 0; i < 2; ++i) {
+            TcNet &n = i ? T.dyn : T.pol;
+            n.s_wfirst = take(16 * ns);
+            n.s_wlast = take(TC_NOUT * ns);
+            n.s_bias = take((MAXL + 1) * TC_MAXNS);
+        }
+        T.off_xin = take(TC_M * (TC_NOUT + 1));
+        T.off_st = take(2 * TC_M * TC_SDP);
+        T.off_aux = take(2 * nop * TC_M);
+        T.off_ring = off;
+        const int budget = SMEM_LIMIT_FLOATS - 256 - off;          // 1 KB of slack for the static barriers
+        const int per_kb = 2 * 1024 + 2 * ns * 8;
+        int nstage = 2, kbs = budget / nstage / per_kb;
+        {
+            const int e = tune ? tune->reserved[1] : 0;           // tuning aid: bits 0-7 k-blocks per stage, 8-11 stages
+            if (mode == 4 && (e & 0xff)) kbs = min(kbs, e & 0xff);
+            if (mode == 4 && ((e >> 8) & 15) >= 2 && ((e >> 8) & 15) <= TC_MAXSTAGE) {
+                nstage = (e >> 8) & 15;
+                kbs = min((e & 0xff) ? (e & 0xff) : 64, budget / nstage / per_kb);
+            }
+        }
+        if (kbs > 16) kbs = 16;
+        if (kbs < 1) return mode == 4 ? fail(PMB_E_UNSUPPORTED, "tensor-core plan does not fit in shared memory") : PMB_OK;
+        T.kb_stage = kbs;
+        T.nstage = nstage;
+        T.stage_floats = kbs * per_kb;
+        off += nstage * T.stage_floats;
+        if (p->mm_states && nstage * T.stage_floats < TCMM_FLOATS)
+            return mode == 4 ? fail(PMB_E_UNSUPPORTED, "moment-matching scratch does not fit the operand ring") : PMB_OK;
+        T.smem_floats = off;
+    }
+    pl.tc_wpack_off = ws.take(wa.top);
+    pl.tc_xbuf_off = ws.take((long long)ntiles * 4 * (C * ns / 8) * 1024);
+    pl.tc_opart_off = ws.take((long long)ntiles * 2 * C * nop * TC_M);
+    // the workspace-resident small operands (padded biases, masks): the streaming weight images are not needed
+    pl.sjobs.n = 0;
+    for (int i = 0; i < pl.jobs.n; ++i)
+        if ((pl.job_dst_off[i] >> 60) == 2) pl.sjobs.job[pl.sjobs.n++] = pl.jobs.job[i];
+    // adjoint-factor pre-pass
+    ClusterParams &P = pl.tpre;
+    memset(&P, 0, sizeof(P));
+    P.N = p->N; P.H = p->H; P.D = p->D; P.U = p->U;
+    P.pol.raw_off = pl.fwd.pol.outsaved_off; P.pol.nraw = pl.fwd.pol.nout; P.pol.has_density = p->pol.has_density;
+    P.pol.lmax = p->pol.max_log_std; P.pol.z = p->pol.z; P.pol.zstride = p->pol.z_step_stride;
+    P.dyn.raw_off = pl.fwd.dyn.outsaved_off; P.dyn.nraw = pl.fwd.dyn.nout; P.dyn.has_density = p->dyn.has_density;
+    P.dyn.lmax = p->dyn.max_log_std; P.dyn.z = p->dyn.z; P.dyn.zstride = p->dyn.z_step_stride;
+    P.act_scale = p->act_scale; P.Sy = p->Sy;
+    P.KR = p->rew_rows; P.rew_C = p->rew_C; P.rew_c0 = p->rew_c0; P.rew_Q = p->rew_Q; P.rew_R = p->rew_R;
+    P.rew_scale = p->rew_scale; P.rew_offset = p->rew_offset;
+    pl.tc = C;
+    return PMB_OK;
+}
+
 static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     if (!p) return fail(PMB_E_INVALID, "problem is NULL");
     if (p->N < 1 || p->H < 1 || p->D < 1 || p->U < 1) return fail(PMB_E_INVALID, "N, H, D, U must be >= 1");
@@ -450,8 +622,8 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     pl.P = P;
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
-    if (pl.stream_mode < 1 || pl.stream_mode > 3) return fail(PMB_E_INVALID, "stream_mode must be 0..3");
-    if (pl.stream_mode == 3) pl.stream_mode = 2;
+    if (pl.stream_mode < 1 || pl.stream_mode > 4) return fail(PMB_E_INVALID, "stream_mode must be 0..4");
+    if (pl.stream_mode >= 3) pl.stream_mode = 2;
     pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : 64;
     if (pl.nsplit < 1 || pl.nsplit > 1024) return fail(PMB_E_INVALID, "wgrad_splits outside [1,1024]");
 
@@ -494,6 +666,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.rstat_off = ws.take((long long)p->H * G * 4);
         pl.geff_off = ws.take(HN);
     }
+    if ((rc = plan_tc(p, tune, pl, ws)) != PMB_OK) return rc;
     pl.ws_floats = ws.top;
 
     for (int pass = 0; pass < 2; ++pass) {
@@ -508,6 +681,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     const NetSweep *fo[2] = {&F.pol, &F.dyn};
     const NetSweep *bo[2] = {&B.dyn, &B.pol};
+    if (pl.tc) return PMB_OK;
     if ((rc = plan_cluster(p, tune, pl)) != PMB_OK) return rc;
     if (pl.cluster) return PMB_OK;
     const int nst = tune ? tune->reserved[1] : 0;
@@ -529,6 +703,25 @@ static void resolve(Plan &pl, float *ws) {
     pl.fwd.ws = pl.bwd.ws = ws;
     pl.fwd.wpack = ws + pl.wpack_fwd_off;
     pl.bwd.wpack = ws + pl.wpack_bwd_off;
+    if (pl.tc) {
+        for (int pass = 0; pass < 2; ++pass) {
+            TcParams &T = pass ? pl.tbwd : pl.tfwd;
+            T.ws = ws;
+            T.wpack = ws + pl.tc_wpack_off;
+            T.xbuf = ws + pl.tc_xbuf_off;
+            T.opart = ws + pl.tc_opart_off;
+            T.pre = ws + pl.cl_pre_off;
+            if (T.mm_states) {
+                T.s1pre = ws + pl.s1pre_off;
+                T.mmstat = ws + pl.mmstat_off;
+            }
+        }
+        pl.tpre.ws = ws;
+        pl.tpre.pre = ws + pl.cl_pre_off;
+        pl.tpre.s1pre = pl.tfwd.mm_states ? ws + pl.s1pre_off : nullptr;
+        for (int i = 0, k = 0; i < pl.jobs.n; ++i)
+            if ((pl.job_dst_off[i] >> 60) == 2) pl.sjobs.job[k++].dst = ws + (pl.job_dst_off[i] & ((1LL << 60) - 1));
+    }
     pl.cfwd.ws = pl.cbwd.ws = ws;
     pl.cbwd.pre = ws + pl.cl_pre_off;
     pl.cfwd.wpack = ws + pl.wpack_fwd_off;
@@ -577,7 +770,15 @@ int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_inf
     int rc = build_plan(p, tune, pl);
     if (rc != PMB_OK) return rc;
     memset(info, 0, sizeof(*info));
-    if (pl.cluster) {
+    if (pl.tc) {
+        info->variant = 2;
+        info->ctas = pl.tfwd.ntiles * pl.tc;
+        info->threads_per_cta = TC_NT;
+        info->cluster_size = pl.tc;
+        info->particles_per_group = pl.tfwd.TP;
+        info->smem_fwd_bytes = pl.tfwd.smem_floats * 4;
+        info->smem_bwd_bytes = pl.tbwd.smem_floats * 4;
+    } else if (pl.cluster) {
         info->variant = 1;
         info->ctas = pl.cl_nclusters * pl.cluster;
         info->threads_per_cta = CL_NT;
@@ -596,8 +797,8 @@ int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_inf
     }
     // pack + sweep (+ reward matching); [reward matching adjoint] + [adjoint-factor pre-pass] + sweep +
     // one weight-gradient kernel per policy layer + partial reduction
-    info->launches_fwd = 2 + (p->mm_rewards ? 1 : 0);
-    info->launches_bwd = (p->mm_rewards ? 1 : 0) + (pl.cluster ? 1 : 0) + 1 + pl.n_wg + 1;
+    info->launches_fwd = 2 + (pl.tc ? 1 : 0) + (p->mm_rewards ? 1 : 0);
+    info->launches_bwd = (p->mm_rewards ? 1 : 0) + ((pl.cluster || pl.tc) ? 1 : 0) + 1 + pl.n_wg + 1;
     return PMB_OK;
 }
 
@@ -624,15 +825,26 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     resolve(pl, (float *)workspace);
     const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 1 pack, 2 sweep
     if (status_dev) PMB_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
-    if (phases & 1) PMB_CUDA(launch_pack(pl.jobs, st));
+    if (phases & 1) {
+        if (pl.tc) {
+            PMB_CUDA(launch_pack(pl.sjobs, st));
+            PMB_CUDA(launch_tc_pack(pl.tjobs, (float *)workspace + pl.tc_wpack_off, st));
+        } else {
+            PMB_CUDA(launch_pack(pl.jobs, st));
+        }
+    }
     SweepParams &F = pl.fwd;
     float *wsf = (float *)workspace;
     F.x0 = x0; F.states = states; F.actions = actions; F.status = status_dev;
     // with mm_rewards the sweep writes the pre-matching rewards; a whole-horizon kernel matches them
     F.rewards = p->mm_rewards ? wsf + pl.rpre_off : rewards;
-    if (p->mm_states) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
+    if (p->mm_states && !pl.tc) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
     F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
-    if (pl.cluster) {
+    if (pl.tc) {
+        TcParams &T = pl.tfwd;
+        T.x0 = x0; T.states = states; T.actions = actions; T.rewards = F.rewards; T.status = status_dev; T.dbg = F.dbg;
+        if (phases & 2) PMB_CUDA(launch_tc_fwd(T, st));
+    } else if (pl.cluster) {
         ClusterParams &CF = pl.cfwd;
         CF.x0 = x0; CF.states = states; CF.actions = actions; CF.rewards = F.rewards; CF.dbg = F.dbg;
         if (phases & 2) PMB_CUDA(launch_cluster_fwd(CF, pl.cl_nclusters, st));
@@ -672,10 +884,21 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
             B.g_rewards = ws + pl.geff_off;
         }
     }
-    if (p->mm_states) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
+    if (p->mm_states && !pl.tc) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
-    if (pl.cluster) {
+    if (pl.tc) {
+        TcParams &T = pl.tbwd;
+        T.states = B.states; T.actions = B.actions; T.rewards = B.rewards;
+        T.g_states = B.g_states; T.g_actions = B.g_actions; T.g_rewards = B.g_rewards; T.dx0 = B.dx0; T.dbg = B.dbg;
+        ClusterParams &P = pl.tpre;
+        P.states = B.states; P.actions = B.actions; P.rewards = B.rewards;
+        P.g_states = B.g_states; P.g_actions = B.g_actions; P.g_rewards = B.g_rewards;
+        if (phases & 2) {
+            PMB_CUDA(launch_bwd_pre(P, st));
+            PMB_CUDA(launch_tc_bwd(T, st));
+        }
+    } else if (pl.cluster) {
         ClusterParams &CB = pl.cbwd;
         CB.states = B.states; CB.actions = B.actions; CB.rewards = B.rewards;
         CB.g_states = B.g_states; CB.g_actions = B.g_actions; CB.g_rewards = B.g_rewards; CB.dx0 = B.dx0; CB.dbg = B.dbg;

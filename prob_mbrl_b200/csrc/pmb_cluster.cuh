@@ -69,6 +69,7 @@ struct ClusterParams {
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
     float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
+    const float *s1pre;         // next states BEFORE moment matching [H][N][D] (the reward acts on them), nullptr = states[t+1]
     long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)
     int off_cst, off_xa, off_xb, off_act, off_red, off_inbox, off_misc;
     int smem_floats;
@@ -319,6 +320,7 @@ __device__ __forceinline__ float ct_exp_clamped_logstd(float l, float lmax, floa
 
 cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
 cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
+cudaError_t launch_bwd_pre(const ClusterParams &prm, cudaStream_t stream);   // the adjoint-factor pre-pass alone
 int cluster_max_active(int C, int smem_bytes, bool fwd);
 
 }  // namespace pmb

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) cluster_bwd_pre_kernel(const __grid_const
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i / N), n = (int)(i - (long long)t * N);
         float *out = prm.pre + i * PW;
-        const float *s1 = prm.states + ((size_t)(t + 1) * N + n) * D;
+        // the reward sees the next state BEFORE moment matching (models/core.py:293 runs inside dynamics())
+        const float *s1 = prm.s1pre ? prm.s1pre + (size_t)i * D : prm.states + ((size_t)(t + 1) * N + n) * D;
         const float *a = prm.actions + ((size_t)t * N + n) * U;
         const float r = __ldg(prm.rewards + i);
         const float gr = prm.g_rewards ? __ldg(prm.g_rewards + i) : 0.f;
@@ -402,13 +403,17 @@ static cudaError_t cluster_launch_cfg_b(const void *fn, int C, int smem_bytes) {
     return e;
 }
 
+cudaError_t launch_bwd_pre(const ClusterParams &prm, cudaStream_t stream) {
+    const long long total = (long long)prm.H * prm.N;
+    const int blocks = (int)min((total + 255) / 256, (long long)148 * 8);
+    cluster_bwd_pre_kernel<<<blocks, 256, 0, stream>>>(prm);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream) {
     const int smem_bytes = prm.smem_floats * 4;
     {
-        const long long total = (long long)prm.H * prm.N;
-        const int blocks = (int)min((total + 255) / 256, (long long)148 * 8);
-        cluster_bwd_pre_kernel<<<blocks, 256, 0, stream>>>(prm);
-        cudaError_t e0 = cudaGetLastError();
+        cudaError_t e0 = launch_bwd_pre(prm, stream);
         if (e0 != cudaSuccess) return e0;
     }
     cudaLaunchConfig_t cfg = {};
