@@ -25,6 +25,7 @@ namespace pmb {
 
 constexpr int TC_NT = 256;         // threads per CTA: 8 warps; thread (warp w, lane) owns particle 32 (w%4) + lane and
                                    // the column half w/4 of the CTA's slice
+constexpr int TC_C = 16;           // CTAs per cluster
 constexpr int TC_M = 128;          // particles per tile (UMMA M)
 constexpr int TC_MAXNS = 64;       // widest column slice per CTA
 constexpr int TC_NOUT = 32;        // raw outputs of a net (max)
@@ -249,6 +250,36 @@ __device__ __forceinline__ void tc_store_hilo(float *img_hi, long long lo_off, i
     float *p = img_hi + (size_t)kb * 1024 + (m >> 3) * 64 + khalf * 32 + (m & 7) * 4;
     *reinterpret_cast<float4 *>(p) = h;
     *reinterpret_cast<float4 *>(p + lo_off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+// per-warp arrival marks of one step (profiling aid, pmb_tuning.reserved[2..3]): dbg[i * 8 + warp]
+#define TC_MARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0) prm.dbg[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+
+// Sum of the C = 16 per-CTA partials of every (output o, particle) item, in rank order, for all items of the
+// exchange block [rank][o][128]: the loads of up to 4 items (64 L2 requests) are in flight before the first add.
+__device__ __forceinline__ void tc_reduce_partials(const float *opart, int nitems, int nop, const float *bias, float *out) {
+    const int tid = threadIdx.x;
+    const size_t rstride = (size_t)nop * TC_M;
+#pragma unroll 1
+    for (int i0 = tid; i0 < nitems; i0 += 4 * TC_NT) {
+        float v[4][TC_C];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * TC_NT;
+#pragma unroll
+            for (int r = 0; r < TC_C; ++r) v[q][r] = i < nitems ? __ldcg(opart + r * rstride + i) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * TC_NT;
+            if (i < nitems) {
+                float a = bias ? bias[i / TC_M] : 0.f;
+#pragma unroll
+                for (int r = 0; r < TC_C; ++r) a += v[q][r];
+                out[i] = a;
+            }
+        }
+    }
 }
 
 cudaError_t launch_tc_pack(const TcPackJobs &jobs, float *wpack, cudaStream_t stream);

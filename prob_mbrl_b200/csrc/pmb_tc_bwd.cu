@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_bwd_kernel(const __grid_constant_
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)tc_rank(), tile = (int)tc_cluster_id();
-    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, C = prm.C, ns = prm.ns;
+    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, ns = prm.ns;
+    constexpr int C = TC_C;
     const int n0 = tile * prm.TP;
     const int nval = min(prm.TP, N - n0);
     const int p = 32 * (warp & 3) + lane, half = warp >> 2;
@@ -213,11 +214,7 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_bwd_kernel(const __grid_constant_
             tc_fence_before();
             tc_cluster_sync();
             tc_fence_after();
-            for (int i = tid; i < net.nin * TC_M; i += TC_NT) {
-                float v = 0.f;
-                for (int r = 0; r < C; ++r) v += __ldcg(opart + (size_t)r * nop * TC_M + i);
-                aux[i] = v;
-            }
+            tc_reduce_partials(opart, net.nin * TC_M, nop, nullptr, aux);
             __syncthreads();
             if (which == 0) {
                 // ---- through the input scaler d[s;a] = dx * iSx, then (action dims) the tanh squash +

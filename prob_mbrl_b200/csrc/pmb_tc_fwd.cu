@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)tc_rank(), tile = (int)tc_cluster_id();
-    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, C = prm.C, ns = prm.ns;
+    const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, ns = prm.ns;
+    constexpr int C = TC_C;
     const int n0 = tile * prm.TP;
     const int nval = min(prm.TP, N - n0);
     const int p = 32 * (warp & 3) + lane, half = warp >> 2;      // particle row of the tile, column half of the slice
@@ -169,12 +170,14 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
 
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
+        const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
         int buf = 0;
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
             const TcNet &net = which ? prm.dyn : prm.pol;
             const int L = net.L;
             float h[HW], mk[HW];
+            TC_MARK(0 + 16 * which);
             // ---------------- first layer (K = nin <= 16) on the FP32 pipe, own columns ----------------
             tc_load_mask<HW>(prm, net, 0, n, c0, mk);
             {
@@ -197,16 +200,20 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
             for (int l = 0; l < L; ++l) {
                 if (l > 0) {
                     // ---------------- hidden x hidden layer on the tensor cores ----------------
+                    TC_MARK(1 + 16 * which);
                     tc_load_mask<HW>(prm, net, l, n, c0, mk);       // in flight while the operands stream in
                     tc_fence_proxy_async_all();                    // my image stores -> visible to the peers' TMA reads
+                    TC_MARK(2 + 16 * which);
                     tc_fence_before();
                     tc_cluster_sync();
                     tc_fence_after();
+                    TC_MARK(3 + 16 * which);
                     if (tid == 0) tc_fence_proxy_async_all();
                     const float *img = ximg + (size_t)buf * 2 * lo_off;
                     const float *wsl = prm.wpack + net.wp_off[l] + (size_t)rank * 2 * net.kb[l - 1] * ns * 8;
                     tc_wide_layer(prm, ring, &bars, rg, img, lo_off, wsl, net.kb[l - 1], tmem_d);
                     buf ^= 1;
+                    TC_MARK(4 + 16 * which);
                     tc_ld_acc<HW>(tmem_rd, h);
                 }
                 // ---------------- epilogue: bias, ReLU, dropout mask / keep (modules.py:61,160) ----------------
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                                       make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]));
                 }
             }
+            TC_MARK(5 + 16 * which);
             // ---------------- output projection: partial sums over my columns ----------------
             {
                 const float *wl = smem + net.s_wlast + half * HW;
@@ -256,16 +264,15 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
             // the two column halves meet; [rank][o][particle] rows of 128 floats, coalesced
             for (int i = tid; i < net.nout * TC_M; i += TC_NT)
                 opart[(size_t)rank * nop * TC_M + i] = aux[i] + aux[nop * TC_M + i];
+            TC_MARK(6 + 16 * which);
             tc_fence_before();
             tc_cluster_sync();
             tc_fence_after();
+            TC_MARK(8 + 16 * which);
             // every CTA adds the C partials in rank order: bit-identical outputs everywhere
-            for (int i = tid; i < net.nout * TC_M; i += TC_NT) {
-                float v = smem[net.s_bias + L * TC_MAXNS + i / TC_M];
-                for (int r = 0; r < C; ++r) v += __ldcg(opart + (size_t)r * nop * TC_M + i);
-                aux[i] = v;
-            }
+            tc_reduce_partials(opart, net.nout * TC_M, nop, smem + net.s_bias + L * TC_MAXNS, aux);
             __syncthreads();
+            TC_MARK(9 + 16 * which);
             if (which == 0) {
                 // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
                 //      dynamics input (core.py:269,177) ----
@@ -316,6 +323,7 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                 }
                 if (prm.mm_states) {
                     __syncthreads();
+                    TC_MARK(11 + 16 * which);
                     tc_mm_forward(prm, st, ring, t, n0, nval, rank);      // rollout.py:121-132 (ring memory is idle here)
                 }
                 if (tid < TC_M) {
@@ -327,6 +335,7 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                 }
             }
             __syncthreads();
+            TC_MARK(10 + 16 * which);
         }
     }
     // ---- rewards r_t = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset on (s_{t+1}, a_t) for every step
