@@ -254,7 +254,8 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
                          | ((0 if pp is None else int(pp) + 1) << 8))
     if t.stream_mode == 4:
         # tensor-core cluster sweeps required; tuning aid: k-blocks per ring stage (bits 0-7), ring stages (bits 8-11)
-        t.reserved[1] = int(os.environ.get("PMB_TC_KBS", "0")) | (int(os.environ.get("PMB_TC_STAGES", "0")) << 8)
+        t.reserved[1] = (int(os.environ.get("PMB_TC_KBS", "0")) | (int(os.environ.get("PMB_TC_STAGES", "0")) << 8)
+                         | (int(os.environ.get("PMB_TC_DBG", "0")) << 12))       # DBG: timing experiments, wrong results
     t.wgrad_splits = int(wgrad_splits or int(os.environ.get("PMB_WGRAD_SPLITS", "0")))
     return t
 

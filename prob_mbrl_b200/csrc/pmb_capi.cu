@@ -535,35 +535,32 @@ static int plan_tc(const pmb_problem *p, const pmb_tuning *tune, Plan &pl, Alloc
             TcNet &n = i ? T.dyn : T.pol;
             n.s_wfirst = take(16 * ns);
             n.s_wlast = take(TC_NOUT * ns);
-            n.s_bias = take((MAXL + 1) * TC_MAXNS);
+            n.s_bias = pass ? 0 : take((MAXL + 1) * TC_MAXNS);
         }
-        T.off_xin = take(TC_M * (TC_NOUT + 1));
-        T.off_st = take(2 * TC_M * TC_SDP);
+        const int PW = 2 * p->D + 3 * p->U;
+        T.off_xin = take(pass ? TC_M * (TC_NOUT + 1) : TC_M * TC_SDP);      // reverse: adjoint of the raw outputs
+        T.off_st = take((pass ? 2 : 1) * TC_M * TC_SDP);
         T.off_aux = take(2 * nop * TC_M);
+        T.off_z = take(pass ? TC_M * PW : 2 * TC_M * TC_SDP);             // forward: density noise; reverse: adjoint factors
+        T.off_mm = p->mm_states ? take(TCMM_FLOATS) : off;
         T.off_ring = off;
-        const int budget = SMEM_LIMIT_FLOATS - 256 - off;          // 1 KB of slack for the static barriers
-        const int per_kb = 2 * 1024 + 2 * ns * 8;
-        int nstage = 2, kbs = budget / nstage / per_kb;
+        const int budget = SMEM_LIMIT_FLOATS - 1024 - off;         // 4 KB of slack for the static barriers + schedule table
+        const int per_stage = 2 * TC_KC * ns * 8;
+        int nstage = min(TC_NSW, budget / per_stage);
         {
-            const int e = tune ? tune->reserved[1] : 0;           // tuning aid: bits 0-7 k-blocks per stage, 8-11 stages
-            if (mode == 4 && (e & 0xff)) kbs = min(kbs, e & 0xff);
-            if (mode == 4 && ((e >> 8) & 15) >= 2 && ((e >> 8) & 15) <= TC_MAXSTAGE) {
-                nstage = (e >> 8) & 15;
-                kbs = min((e & 0xff) ? (e & 0xff) : 64, budget / nstage / per_kb);
-            }
+            const int e = tune ? tune->reserved[1] : 0;            // tuning aid: bits 8-11 weight stages
+            if (mode == 4 && ((e >> 8) & 15) >= 1 && ((e >> 8) & 15) <= TC_NSW) nstage = min(nstage, (e >> 8) & 15);
         }
-        if (kbs > 16) kbs = 16;
-        if (kbs < 1) return mode == 4 ? fail(PMB_E_UNSUPPORTED, "tensor-core plan does not fit in shared memory") : PMB_OK;
-        T.kb_stage = kbs;
+        if (nstage < 1) return mode == 4 ? fail(PMB_E_UNSUPPORTED, "tensor-core plan does not fit in shared memory") : PMB_OK;
+        T.kb_stage = TC_KC;
         T.nstage = nstage;
-        T.stage_floats = kbs * per_kb;
-        off += nstage * T.stage_floats;
-        if (p->mm_states && nstage * T.stage_floats < TCMM_FLOATS)
-            return mode == 4 ? fail(PMB_E_UNSUPPORTED, "moment-matching scratch does not fit the operand ring") : PMB_OK;
+        T.dbg_flags = (tune && mode == 4) ? (tune->reserved[1] >> 12) & 15 : 0;
+        T.stage_floats = per_stage;
+        off += nstage * per_stage;
         T.smem_floats = off;
     }
     pl.tc_wpack_off = ws.take(wa.top);
-    pl.tc_xbuf_off = ws.take((long long)ntiles * 4 * (C * ns / 8) * 1024);
+    pl.tc_xbuf_off = ws.take((long long)ntiles * 2 * (C * ns / 8) * 1024);
     pl.tc_opart_off = ws.take((long long)ntiles * 2 * C * nop * TC_M);
     // the workspace-resident small operands (padded biases, masks): the streaming weight images are not needed
     pl.sjobs.n = 0;

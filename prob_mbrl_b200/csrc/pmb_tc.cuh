@@ -7,24 +7,36 @@
 // forms the ns = W/C (padded to 16/32/64) output columns [r ns, (r+1) ns) with tcgen05.mma.kind::tf32, fp32
 // accumulation in TMEM.  fp32 parity on the tensor pipe needs the 3-term split the weight-gradient kernel
 // validated (pmb_wgrad.cu): x = hi + lo, hi = tf32(x);  C += A_hi B_hi + A_hi B_lo + A_lo B_hi.
-//   * weights: split once per call by tc_pack_kernel into per-CTA hi/lo slices in the K-major no-swizzle
-//     canonical layout (8 rows x 16 B core matrices, LBO 128 B, SBO 256 B; profiles/r01_umma_layout_probe.txt);
-//   * activations: every CTA's epilogue (TMEM -> registers: bias, ReLU, dropout mask, keep) writes its columns,
-//     split into hi/lo and already in the canonical layout, to a small exchange image in global memory (L2
-//     resident, 2 x 512 KB per tile for 512-wide nets); after ONE cluster barrier every CTA streams the whole
-//     image + its weight slice through a TMA (cp.async.bulk) + mbarrier ring, chunk by chunk, while one elected
-//     thread issues the MMAs -- the tensor core reads shared memory, nothing is staged through registers.
+//   * weights (B operand): split once per call by tc_pack_kernel into per-CTA hi/lo slices in the K-major
+//     no-swizzle canonical layout (8 rows x 16 B core matrices, LBO 128 B, SBO 256 B;
+//     profiles/r01_umma_layout_probe.txt) and streamed by TMA (cp.async.bulk + mbarrier) through a shared-memory
+//     ring that runs ahead across layer boundaries (weights do not depend on the step's data);
+//   * activations (A operand): every CTA's epilogue (TMEM -> registers: bias, ReLU, dropout mask, keep) writes its
+//     columns as plain fp32 to a small exchange image in global memory (L2 resident, [k-block][k half][row][4]:
+//     coalesced both ways); after ONE cluster barrier the 8 compute warps of every CTA read the whole image back
+//     with 128-bit loads (3 chunks in flight), split it into TF32 hi/lo IN REGISTERS and park it in TENSOR MEMORY
+//     with tcgen05.st -- the MMAs take A from TMEM (profiles/r02_umma_tmem_a_probe.txt), so the activations never
+//     touch shared memory: the first version of these sweeps staged hi/lo images through shared memory and was
+//     bound by its bandwidth (1.6 MB per layer per SM, profiles/r02_tc_v1_timeline.txt).
+//   * a ninth warp drives the pipeline: one thread issues the weight TMA copies and the MMAs
+//     (A stage full / weight stage full -> 3 MMAs per k-block -> tcgen05.commit frees both).
 // The skinny first / last layers (K <= 16 inputs, <= 32 outputs) stay on the FP32 pipe: the first layer is formed
 // per CTA for its own columns, the output projection as per-CTA partial sums that meet in global memory
-// ([rank][particle][output], fixed-order sum => bit-identical state copies on every CTA, deterministic).
+// ([rank][output][particle], fixed-order sum => bit-identical state copies on every CTA, deterministic).
 // Moment matching of the states needs no communication at all: every CTA holds the full state tile.
 #pragma once
 #include "pmb_internal.cuh"
 
 namespace pmb {
 
-constexpr int TC_NT = 256;         // threads per CTA: 8 warps; thread (warp w, lane) owns particle 32 (w%4) + lane and
-                                   // the column half w/4 of the CTA's slice
+constexpr int TC_NT = 256;         // COMPUTE threads per CTA: 8 warps; thread (warp w, lane) owns particle 32 (w%4) + lane
+                                   // and the column half w/4 of the CTA's slice
+constexpr int TC_NTL = TC_NT + 32; // + the driver warp (weight TMA + MMA issue)
+constexpr int TC_KC = 8;           // k-blocks (of 8) per pipeline chunk
+constexpr int TC_NSA = 3;          // A stages in tensor memory (2 x 64 columns each: hi | lo)
+constexpr int TC_NSW = 4;          // weight stages in shared memory (max)
+constexpr int TC_COL_A = 64;       // TMEM columns: accumulator at 0 .. ns-1, A stages from 64
+constexpr int TC_MAXITEMS = 2 * (MAXL - 1) * 16;   // weight chunks per step (schedule table)
 constexpr int TC_C = 16;           // CTAs per cluster
 constexpr int TC_M = 128;          // particles per tile (UMMA M)
 constexpr int TC_MAXNS = 64;       // widest column slice per CTA
@@ -64,13 +76,13 @@ struct TcParams {
     int TP;                         // particles per tile (<= 128)
     int ntiles;
     int ns;                         // columns per CTA (16, 32 or 64)
-    int kb_stage, nstage;           // k-blocks per ring stage, ring stages
+    int kb_stage, nstage;           // k-blocks per weight stage (= TC_KC), weight stages
     int kbmax;                      // k-blocks of an exchange image (= C * ns / 8: every CTA writes all its columns)
     int nop;                        // rows of the partial-sum exchange: max(inputs, raw outputs) over both nets
     TcNet pol, dyn;
     float *ws;                      // workspace base
     const float *wpack;             // tc weight area (hi/lo slices)
-    float *xbuf;                    // [ntiles][2][hi | lo][kbmax][128 x 8] activation exchange images
+    float *xbuf;                    // [ntiles][2][kbmax][k half][128][4] fp32 activation exchange images
     float *opart;                   // [ntiles][2][C][nop][128] partial sums of the skinny projections (2 = pass parity)
     const float *act_scale, *act_bias, *mx, *iSx, *my, *Sy;
     int KR;
@@ -88,8 +100,10 @@ struct TcParams {
     float *s1pre;                   // [H][N][D] particles before matching
     float *mmstat;                  // [H][G][3*SD + SD*SD] mean, z mean, 1/z std, Cholesky factor
     long long *dbg;
+    int dbg_flags;                  // timing experiments only (results are wrong): 1 = skip the MMAs, 2 = skip the image
+                                    // loads, 4 = skip the tcgen05.st, 8 = skip the hi/lo split
     // shared-memory carve-up (float offsets)
-    int off_cst, off_res, off_xin, off_st, off_aux, off_ring;
+    int off_cst, off_res, off_xin, off_st, off_aux, off_z, off_mm, off_ring;
     int stage_floats;
     int smem_floats;
 };
@@ -163,102 +177,217 @@ __device__ __forceinline__ void tc_ld_acc(uint32_t taddr, float (&v)[HW]) {
     for (int c = 0; c < HW; ++c) v[c] = __uint_as_float(r[c]);
 }
 
-// ----------------------------------------------------------------------------------------
-// The operand ring of one CTA: stages of [A_hi | A_lo | W_hi | W_lo] k-block groups filled by TMA bulk copies
-// (thread 0 = producer) and consumed by the MMAs (thread 32 = issuer).  tcgen05.commit hands a stage back.
-// ----------------------------------------------------------------------------------------
-constexpr int TC_MAXSTAGE = 4;
-struct TcBars {
-    uint64_t full[TC_MAXSTAGE];
-    uint64_t empty[TC_MAXSTAGE];
-    uint64_t done;
-};
-struct TcRing {
-    int stage;            // producer / issuer: next stage
-    uint32_t parity;      // issuer: parity of the next full wait; producer: of the next empty wait
-    uint32_t issued;      // producer: chunks issued so far
-    uint32_t done_parity; // all threads
-    __device__ __forceinline__ void init() { stage = 0; parity = 0; issued = 0; done_parity = 0; }
-};
-
-// One hidden x hidden layer of this CTA: D[128 x ns] = A[128 x 8 KB] . B[ns x 8 KB]^T over KB k-blocks.
-//   a_img : exchange image of the layer input in global memory: hi at a_img, lo at a_img + lo_off (floats)
-//   w_sl  : this CTA's weight slices: hi at w_sl, lo at w_sl + KB * ns * 8
-// Called by all 256 threads; returns when the accumulator is complete and visible to tcgen05.ld.
-__device__ __forceinline__ void tc_wide_layer(const TcParams &prm, float *ring_base, TcBars *bars, TcRing &rg,
-                                              const float *a_img, long long lo_off, const float *w_sl, int KB,
-                                              uint32_t tmem_d) {
-    const int tid = threadIdx.x;
-    const int ns = prm.ns, KBS = prm.kb_stage;
-    const int nchunks = (KB + KBS - 1) / KBS;
-    const int a_st = KBS * 1024, w_st = KBS * ns * 8;      // floats of one operand half in a stage
-    if (tid == 0) {
-        // ---- producer ----
-        for (int c = 0; c < nchunks; ++c) {
-            const int nkb = min(KBS, KB - c * KBS);
-            if (rg.issued >= (uint32_t)prm.nstage) mbar_wait(&bars->empty[rg.stage], rg.parity);
-            float *st = ring_base + (size_t)rg.stage * prm.stage_floats;
-            const uint32_t ab = (uint32_t)nkb * 4096u, wb = (uint32_t)(nkb * ns * 32);
-            mbar_expect_tx(&bars->full[rg.stage], 2u * ab + 2u * wb);
-            const float *ag = a_img + (size_t)c * a_st;
-            const float *wg = w_sl + (size_t)c * w_st;
-            tma_bulk_g2s(st, ag, ab, &bars->full[rg.stage]);
-            tma_bulk_g2s(st + a_st, ag + lo_off, ab, &bars->full[rg.stage]);
-            tma_bulk_g2s(st + 2 * a_st, wg, wb, &bars->full[rg.stage]);
-            tma_bulk_g2s(st + 2 * a_st + w_st, wg + (size_t)KB * ns * 8, wb, &bars->full[rg.stage]);
-            ++rg.issued;
-            if (++rg.stage == prm.nstage) {
-                rg.stage = 0;
-                if (rg.issued > (uint32_t)prm.nstage) rg.parity ^= 1u;
-            }
-        }
-    } else if (tid == 32) {
-        // ---- MMA issuer ----
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ns >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        for (int c = 0; c < nchunks; ++c) {
-            const int nkb = min(KBS, KB - c * KBS);
-            mbar_wait(&bars->full[rg.stage], rg.parity);
-            tc_fence_after();
-            const uint32_t s0 = smem_u32(ring_base + (size_t)rg.stage * prm.stage_floats);
-            for (int k = 0; k < nkb; ++k) {
-                const uint64_t dAh = tc_desc(s0 + (uint32_t)k * 4096u);
-                const uint64_t dAl = tc_desc(s0 + (uint32_t)(a_st * 4) + (uint32_t)k * 4096u);
-                const uint64_t dBh = tc_desc(s0 + (uint32_t)(2 * a_st * 4) + (uint32_t)(k * ns * 32));
-                const uint64_t dBl = tc_desc(s0 + (uint32_t)((2 * a_st + w_st) * 4) + (uint32_t)(k * ns * 32));
-                tc_mma_tf32(tmem_d, dAh, dBh, idesc, (c | k) ? 1u : 0u);
-                tc_mma_tf32(tmem_d, dAh, dBl, idesc, 1u);
-                tc_mma_tf32(tmem_d, dAl, dBh, idesc, 1u);
-            }
-            tc_commit(&bars->empty[rg.stage]);       // the stage is free once these MMAs retired
-            if (++rg.stage == prm.nstage) {
-                rg.stage = 0;
-                rg.parity ^= 1u;
-            }
-        }
-        tc_commit(&bars->done);
-    }
-    __syncwarp();
-    mbar_wait(&bars->done, rg.done_parity);
-    rg.done_parity ^= 1u;
-    tc_fence_after();
+// MMA with the A operand in tensor memory (lane = row, one 32-bit column per tf32 element)
+__device__ __forceinline__ void tc_mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// 32 consecutive TMEM columns of this warp's 32 lanes <- registers
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+          "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+          "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+          "f"(v[30]), "f"(v[31])
+        : "memory");
 }
 
-// hi/lo split of 4 consecutive k values of one particle row -> the exchange image (canonical K-major layout):
-// element (row m, k) of k-block kb sits at kb*1024 + (m/8)*64 + ((k%8)/4)*32 + (m%8)*4 + (k%4)
-__device__ __forceinline__ void tc_store_hilo(float *img_hi, long long lo_off, int kb, int khalf, int m, float4 v) {
-    const float4 h = make_float4(tc_tf32_hi(v.x), tc_tf32_hi(v.y), tc_tf32_hi(v.z), tc_tf32_hi(v.w));
-    float *p = img_hi + (size_t)kb * 1024 + (m >> 3) * 64 + khalf * 32 + (m & 7) * 4;
-    *reinterpret_cast<float4 *>(p) = h;
-    *reinterpret_cast<float4 *>(p + lo_off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+// ----------------------------------------------------------------------------------------
+// The layer pipeline of one CTA.
+//   weight stages (shared memory, TMA):  w_full  <- complete_tx,        w_empty <- tcgen05.commit
+//   A stages (tensor memory, tcgen05.st): a_full <- 8 compute warps,     a_empty <- tcgen05.commit
+//   done: the layer's accumulator is complete
+// ----------------------------------------------------------------------------------------
+struct TcBars {
+    uint64_t w_full[TC_NSW];
+    uint64_t w_empty[TC_NSW];
+    uint64_t a_full[TC_NSA];
+    uint64_t a_empty[TC_NSA];
+    uint64_t done;
+};
+struct TcWItem {            // one weight chunk of the per-step schedule (this CTA's slice)
+    const float *hi;        // lo at hi + lo_off
+    uint32_t lo_off;        // floats
+    uint32_t nkb;
+};
+struct TcPipe {
+    // driver thread
+    uint32_t w_issued, w_consumed, w_total, w_items;   // weight chunks issued / consumed so far, of the whole kernel, per step
+    uint32_t w_next;                                    // next schedule item to issue
+    // both sides: A chunks so far
+    uint32_t a_count;
+    uint32_t done_parity;
+    __device__ __forceinline__ void init(uint32_t items, uint32_t total) {
+        w_issued = w_consumed = 0; w_total = total; w_items = items; w_next = 0; a_count = 0; done_parity = 0;
+    }
+};
+
+// exchange image: element (row m, column k) at (k/8)*1024 + ((k%8)/4)*512 + m*4 + (k%4)
+__device__ __forceinline__ void tc_store_img(float *img, int kb, int khalf, int m, float4 v) {
+    *reinterpret_cast<float4 *>(img + (size_t)kb * 1024 + khalf * 512 + m * 4) = v;
+}
+
+// driver thread: keep the weight ring full (it runs ahead across layers), issue the MMAs of one layer
+__device__ __forceinline__ void tc_drive_layer(const TcParams &prm, float *ring, TcBars *bars, TcPipe &pp, const TcWItem *sched,
+                                               int KB, uint32_t tmem_base) {
+    const int ns = prm.ns, nsw = prm.nstage;
+    const int nch = (KB + TC_KC - 1) / TC_KC;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ns >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t wlo = (uint32_t)(TC_KC * ns * 8);       // floats: lo half of a weight stage
+    for (int c = 0; c < nch; ++c) {
+        while (pp.w_issued < pp.w_total && pp.w_issued < pp.w_consumed + (uint32_t)nsw) {
+            const uint32_t s = pp.w_issued % nsw;
+            if (pp.w_issued >= (uint32_t)nsw) mbar_wait(&bars->w_empty[s], ((pp.w_issued / nsw) - 1u) & 1u);
+            const TcWItem it = sched[pp.w_next];
+            const uint32_t bytes = it.nkb * (uint32_t)(ns * 32);
+            float *dst = ring + (size_t)s * prm.stage_floats;
+            mbar_expect_tx(&bars->w_full[s], 2u * bytes);
+            tma_bulk_g2s(dst, it.hi, bytes, &bars->w_full[s]);
+            tma_bulk_g2s(dst + wlo, it.hi + it.lo_off, bytes, &bars->w_full[s]);
+            ++pp.w_issued;
+            if (++pp.w_next == pp.w_items) pp.w_next = 0;
+        }
+        const int nkb = min(TC_KC, KB - c * TC_KC);
+        const uint32_t sw = pp.w_consumed % nsw, sa = pp.a_count % TC_NSA;
+        mbar_wait(&bars->w_full[sw], (pp.w_consumed / nsw) & 1u);
+        mbar_wait(&bars->a_full[sa], (pp.a_count / TC_NSA) & 1u);
+        tc_fence_after();
+        const uint32_t wb = smem_u32(ring + (size_t)sw * prm.stage_floats);
+        const uint32_t ta = tmem_base + (uint32_t)TC_COL_A + sa * 128u;
+        for (int k = 0; k < nkb && !(prm.dbg_flags & 1); ++k) {
+            const uint64_t dBh = tc_desc(wb + (uint32_t)(k * ns * 32));
+            const uint64_t dBl = tc_desc(wb + wlo * 4u + (uint32_t)(k * ns * 32));
+            tc_mma_tf32_ta(tmem_base, ta + 8u * k, dBh, idesc, (c | k) ? 1u : 0u);
+            tc_mma_tf32_ta(tmem_base, ta + 8u * k, dBl, idesc, 1u);
+            tc_mma_tf32_ta(tmem_base, ta + 64u + 8u * k, dBh, idesc, 1u);
+        }
+        tc_commit(&bars->a_empty[sa]);
+        tc_commit(&bars->w_empty[sw]);
+        ++pp.w_consumed;
+        ++pp.a_count;
+    }
+    tc_commit(&bars->done);
+}
+
+// compute warps: this thread's share of chunk c of the image (row m, k-blocks 4*half .. 4*half+3) -> registers
+__device__ __forceinline__ void tc_img_issue(float (&b)[32], const float *img, int c, int KB, int m, int half, int flags = 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int kb = c * TC_KC + 4 * half + j;
+        float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
+        if (kb < KB && !(flags & 2)) {
+            const float *q = img + (size_t)kb * 1024 + m * 4;
+            lo4 = __ldcg(reinterpret_cast<const float4 *>(q));
+            hi4 = __ldcg(reinterpret_cast<const float4 *>(q + 512));
+        }
+        b[8 * j] = lo4.x; b[8 * j + 1] = lo4.y; b[8 * j + 2] = lo4.z; b[8 * j + 3] = lo4.w;
+        b[8 * j + 4] = hi4.x; b[8 * j + 5] = hi4.y; b[8 * j + 6] = hi4.z; b[8 * j + 7] = hi4.w;
+    }
+}
+// ... split into TF32 hi / lo and parked in the chunk's A stage of tensor memory (lo overwrites the buffer registers)
+__device__ __forceinline__ void tc_img_produce(float (&x)[32], TcBars *bars, TcPipe &pp, uint32_t tmem_lane_base, int half,
+                                               int flags = 0) {
+    const uint32_t sa = pp.a_count % TC_NSA;
+    if (pp.a_count >= (uint32_t)TC_NSA) {
+        mbar_wait(&bars->a_empty[sa], ((pp.a_count / TC_NSA) - 1u) & 1u);
+        tc_fence_after();
+    }
+    const uint32_t ta = tmem_lane_base + (uint32_t)TC_COL_A + sa * 128u + 32u * (uint32_t)half;
+    {
+        float hi[32];
+        if (!(flags & 8)) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                hi[e] = tc_tf32_hi(x[e]);
+                x[e] -= hi[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) hi[e] = x[e];
+        }
+        if (!(flags & 4)) tc_st32(ta, hi);
+    }
+    if (!(flags & 4)) tc_st32(ta + 64u, x);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->a_full[sa]);
+    ++pp.a_count;
+}
+
+// One hidden x hidden layer of this CTA: D[128 x ns] = A[128 x 8 KB] . B[ns x 8 KB]^T over KB k-blocks, A from the
+// fp32 exchange image `img`.  Called by all 288 threads; returns when the accumulator is complete.
+__device__ __forceinline__ void tc_wide_layer(const TcParams &prm, float *ring, TcBars *bars, TcPipe &pp, const TcWItem *sched,
+                                              const float *img, int KB, uint32_t tmem_base, int m, int half,
+                                              long long *dbgp = nullptr) {
+    const int warp = threadIdx.x >> 5;
+    const int nch = (KB + TC_KC - 1) / TC_KC;
+    const int fl = prm.dbg_flags;
+    int dbi = 0;
+#define TC_WMARK() do { if (dbgp && (threadIdx.x & 31) == 0 && dbi < 24) dbgp[(threadIdx.x >> 5) * 24 + dbi++] = clock64(); } while (0)
+    if (warp == 8) {
+        if ((threadIdx.x & 31) == 0) tc_drive_layer(prm, ring, bars, pp, sched, KB, tmem_base);
+        __syncwarp();
+    } else {
+        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        float b0[32], b1[32];          // two chunks of image loads in flight per thread (64 KB per CTA)
+        TC_WMARK();
+        tc_img_issue(b0, img, 0, KB, m, half, fl);
+        if (nch > 1) tc_img_issue(b1, img, 1, KB, m, half, fl);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+            tc_img_produce(b0, bars, pp, lane_base, half, fl);
+            TC_WMARK();
+            if (c + 2 < nch) tc_img_issue(b0, img, c + 2, KB, m, half, fl);
+            if (c + 1 < nch) {
+                tc_img_produce(b1, bars, pp, lane_base, half, fl);
+                TC_WMARK();
+                if (c + 3 < nch) tc_img_issue(b1, img, c + 3, KB, m, half, fl);
+            }
+        }
+    }
+    mbar_wait(&bars->done, pp.done_parity);
+    pp.done_parity ^= 1u;
+    tc_fence_after();
+    TC_WMARK();
+#undef TC_WMARK
+}
+
+// this CTA's weight-chunk schedule of one step, in consumption order (built once by the driver thread)
+__device__ __forceinline__ uint32_t tc_build_schedule(const TcParams &prm, const TcNet *const (&order)[2], bool reverse, int rank,
+                                                      TcWItem *sched) {
+    uint32_t n = 0;
+    const int ns = prm.ns;
+    for (int w = 0; w < 2; ++w) {
+        const TcNet &net = *order[w];
+        for (int i = 1; i < net.L; ++i) {
+            const int l = reverse ? net.L - i : i;                         // reverse sweep walks l = L-1 .. 1
+            const int KB = reverse ? net.kb[l] : net.kb[l - 1];
+            const float *base = prm.wpack + net.wp_off[l] + (size_t)rank * 2 * KB * ns * 8;
+            for (int c = 0; c * TC_KC < KB; ++c) {
+                sched[n].hi = base + (size_t)c * TC_KC * ns * 8;
+                sched[n].lo_off = (uint32_t)(KB * ns * 8);
+                sched[n].nkb = (uint32_t)min(TC_KC, KB - c * TC_KC);
+                ++n;
+            }
+        }
+    }
+    return n;
 }
 
 // per-warp arrival marks of one step (profiling aid, pmb_tuning.reserved[2..3]): dbg[i * 8 + warp]
-#define TC_MARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0) prm.dbg[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+#define TC_MARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0 && threadIdx.x < TC_NT) prm.dbg[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
 
 // Sum of the C = 16 per-CTA partials of every (output o, particle) item, in rank order, for all items of the
 // exchange block [rank][o][128]: the loads of up to 4 items (64 L2 requests) are in flight before the first add.
 __device__ __forceinline__ void tc_reduce_partials(const float *opart, int nitems, int nop, const float *bias, float *out) {
     const int tid = threadIdx.x;
+    if (tid >= TC_NT) return;
     const size_t rstride = (size_t)nop * TC_M;
 #pragma unroll 1
     for (int i0 = tid; i0 < nitems; i0 += 4 * TC_NT) {

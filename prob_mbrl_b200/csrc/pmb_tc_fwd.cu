@@ -105,34 +105,63 @@ __device__ __forceinline__ void tc_load_mask(const TcParams &prm, const TcNet &n
     }
 }
 
+// raw dropout-mask values of (particle n, columns c0 .. c0+HW) of hidden layer l: issued early, consumed by the
+// layer's epilogue (tc_mask_apply) so that the L2 latency hides behind the layer
 template <int HW>
-__global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant__ TcParams prm) {
+__device__ __forceinline__ void tc_mask_issue(const TcParams &prm, const TcNet &n, int l, int nld, int c0, float (&mk)[HW]) {
+    const int npad = n.npad[l];
+    if (n.mask_off[l] >= 0) {
+        const float *src = prm.ws + n.mask_off[l] + (long long)nld * npad + c0;
+#pragma unroll
+        for (int j = 0; j < HW; j += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + j < npad) v = __ldg(reinterpret_cast<const float4 *>(src + j));
+            mk[j] = v.x; mk[j + 1] = v.y; mk[j + 2] = v.z; mk[j + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < HW; ++j) mk[j] = 1.f;
+    }
+}
+
+template <int HW>
+__global__ void __launch_bounds__(TC_NTL, 1) tc_fwd_kernel(const __grid_constant__ TcParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) TcBars bars;
-    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) TcWItem sched[TC_MAXITEMS];
+    __shared__ uint32_t tmem_base_s, sched_n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool compute = tid < TC_NT;
     const int rank = (int)tc_rank(), tile = (int)tc_cluster_id();
     const int N = prm.N, D = prm.D, U = prm.U, H = prm.H, ns = prm.ns;
     constexpr int C = TC_C;
     const int n0 = tile * prm.TP;
     const int nval = min(prm.TP, N - n0);
-    const int p = 32 * (warp & 3) + lane, half = warp >> 2;      // particle row of the tile, column half of the slice
-    const bool valid = p < nval;
+    const int p = 32 * (warp & 3) + lane, half = (warp >> 2) & 1;   // particle row of the tile, column half of the slice
+    const bool valid = compute && p < nval;
     const int n = n0 + min(p, nval - 1);                          // clamped: safe address for loads
     const int c0 = rank * ns + half * HW;                         // first column this thread owns
     const bool owner = valid && (p % C) == rank;                  // this CTA writes particle p's trajectory
 
-    for (int i = tid; i < prm.smem_floats; i += TC_NT) smem[i] = 0.f;
+    for (int i = tid; i < prm.smem_floats; i += TC_NTL) smem[i] = 0.f;
     if (tid == 0) {
-        for (int s = 0; s < prm.nstage; ++s) {
-            mbar_init(&bars.full[s], 1);
-            mbar_init(&bars.empty[s], 1);
+        for (int s = 0; s < TC_NSW; ++s) {
+            mbar_init(&bars.w_full[s], 1);
+            mbar_init(&bars.w_empty[s], 1);
+        }
+        for (int s = 0; s < TC_NSA; ++s) {
+            mbar_init(&bars.a_full[s], TC_NT / 32);
+            mbar_init(&bars.a_empty[s], 1);
         }
         mbar_init(&bars.done, 1);
         fence_mbar_init();
     }
+    if (tid == TC_NT) {
+        const TcNet *const order[2] = {&prm.pol, &prm.dyn};
+        sched_n = tc_build_schedule(prm, order, false, rank, sched);
+    }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -144,43 +173,60 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
     float *cst = smem + prm.off_cst;
     float *xin = smem + prm.off_xin;          // [128][TC_SDP] input rows of the net being evaluated
     float *st = smem + prm.off_st;            // [128][TC_SDP] current state
-    float *aux = smem + prm.off_aux;          // [2][TC_NOUT][128] partial sums of the column halves / reduced outputs
+    float *aux = smem + prm.off_aux;          // [2][nop][128] partial sums of the column halves / reduced outputs
+    float *zt = smem + prm.off_z;             // [2][128][TC_SDP] density noise of the tile: policy, dynamics
+    float *mmscr = smem + prm.off_mm;
     float *ring = smem + prm.off_ring;
-    load_constants(prm, cst);
-    tc_load_resident(prm, prm.pol, smem, rank, true);
-    tc_load_resident(prm, prm.dyn, smem, rank, true);
-    if (tid < TC_M) {
-        for (int d = 0; d < D; ++d) {
-            const float v = valid ? prm.x0[(size_t)n * D + d] : 0.f;
-            st[p * TC_SDP + d] = v;
-            xin[p * TC_SDP + d] = v;
-            if (owner) prm.states[(size_t)n * D + d] = v;
+    if (compute) {
+        load_constants(prm, cst);
+        tc_load_resident(prm, prm.pol, smem, rank, true);
+        tc_load_resident(prm, prm.dyn, smem, rank, true);
+        if (tid < TC_M) {
+            for (int d = 0; d < D; ++d) {
+                const float v = valid ? prm.x0[(size_t)n * D + d] : 0.f;
+                st[p * TC_SDP + d] = v;
+                xin[p * TC_SDP + d] = v;
+                if (owner) prm.states[(size_t)n * D + d] = v;
+            }
+            // PEGASUS: the density noise is constant over the horizon (per-step tables are re-read every step)
+            if (prm.pol.has_density) for (int u = 0; u < U; ++u) zt[p * TC_SDP + u] = __ldg(prm.pol.z + (size_t)n * U + u);
+            if (prm.dyn.has_density) for (int d = 0; d < D; ++d) zt[(TC_M + p) * TC_SDP + d] = __ldg(prm.dyn.z + (size_t)n * D + d);
         }
+        if (prm.mm_states) tc_mm_load_table(prm, mmscr);
     }
     const float elmax_pol = expf(prm.pol.lmax), elmax_dyn = expf(prm.dyn.lmax);
-    const long long lo_off = (long long)prm.kbmax * 1024;
-    float *ximg = prm.xbuf + (size_t)tile * 4 * lo_off;            // two images of [hi | lo]
+    const long long img_floats = (long long)prm.kbmax * 1024;
+    float *ximg = prm.xbuf + (size_t)tile * 2 * img_floats;        // two fp32 images
     float *opart2 = prm.opart + (size_t)tile * 2 * C * prm.nop * TC_M;   // [pass parity][rank][o][128]
     const int nop = prm.nop;
     int pass = 0;
-    TcRing rg;
-    rg.init();
     __syncthreads();
+    TcPipe pp;
+    pp.init(sched_n, sched_n * (uint32_t)H);
     tc_cluster_sync();
+
+    float mk[HW];                  // raw dropout mask of the next layer to finish (prefetched)
+    if (compute) tc_mask_issue<HW>(prm, prm.pol, 0, n, c0, mk);
 
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
         int buf = 0;
+        if (compute && tid < TC_M) {     // per-step noise tables (only when the caller pre-drew [H, N, .] noise)
+            if (prm.pol.has_density && prm.pol.zstride != 0)
+                for (int u = 0; u < U; ++u) zt[p * TC_SDP + u] = __ldg(prm.pol.z + (size_t)t * prm.pol.zstride + (size_t)n * U + u);
+            if (prm.dyn.has_density && prm.dyn.zstride != 0)
+                for (int d = 0; d < D; ++d)
+                    zt[(TC_M + p) * TC_SDP + d] = __ldg(prm.dyn.z + (size_t)t * prm.dyn.zstride + (size_t)n * D + d);
+        }
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
             const TcNet &net = which ? prm.dyn : prm.pol;
             const int L = net.L;
-            float h[HW], mk[HW];
+            float h[HW];
             TC_MARK(0 + 16 * which);
             // ---------------- first layer (K = nin <= 16) on the FP32 pipe, own columns ----------------
-            tc_load_mask<HW>(prm, net, 0, n, c0, mk);
-            {
+            if (compute) {
                 const float *xr = xin + p * TC_SDP;
                 const float *wf = smem + net.s_wfirst + half * HW;
 #pragma unroll
@@ -198,52 +244,51 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
             }
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
-                if (l > 0) {
-                    // ---------------- hidden x hidden layer on the tensor cores ----------------
-                    TC_MARK(1 + 16 * which);
-                    tc_load_mask<HW>(prm, net, l, n, c0, mk);       // in flight while the operands stream in
-                    tc_fence_proxy_async_all();                    // my image stores -> visible to the peers' TMA reads
-                    TC_MARK(2 + 16 * which);
-                    tc_fence_before();
-                    tc_cluster_sync();
-                    tc_fence_after();
-                    TC_MARK(3 + 16 * which);
-                    if (tid == 0) tc_fence_proxy_async_all();
-                    const float *img = ximg + (size_t)buf * 2 * lo_off;
-                    const float *wsl = prm.wpack + net.wp_off[l] + (size_t)rank * 2 * net.kb[l - 1] * ns * 8;
-                    tc_wide_layer(prm, ring, &bars, rg, img, lo_off, wsl, net.kb[l - 1], tmem_d);
-                    buf ^= 1;
-                    TC_MARK(4 + 16 * which);
-                    tc_ld_acc<HW>(tmem_rd, h);
-                }
                 // ---------------- epilogue: bias, ReLU, dropout mask / keep (modules.py:61,160) ----------------
-                {
+                if (compute) {
                     const float *bs = smem + net.s_bias + l * TC_MAXNS + half * HW;
-                    const int npad = net.npad[l];
-                    float *sv = prm.ws + net.saved_off[l] + ((size_t)t * N + n) * npad + c0;
+                    const float ki = net.keep_inv[l];
 #pragma unroll
                     for (int j = 0; j < HW; j += 4) {
                         const float4 b = *reinterpret_cast<const float4 *>(bs + j);
-                        h[j] = fmaxf(h[j] + b.x, 0.f) * mk[j];
-                        h[j + 1] = fmaxf(h[j + 1] + b.y, 0.f) * mk[j + 1];
-                        h[j + 2] = fmaxf(h[j + 2] + b.z, 0.f) * mk[j + 2];
-                        h[j + 3] = fmaxf(h[j + 3] + b.w, 0.f) * mk[j + 3];
-                        if (valid && c0 + j < npad)
-                            *reinterpret_cast<float4 *>(sv + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+                        h[j] = fmaxf(h[j] + b.x, 0.f) * mk[j] * ki;
+                        h[j + 1] = fmaxf(h[j + 1] + b.y, 0.f) * mk[j + 1] * ki;
+                        h[j + 2] = fmaxf(h[j + 2] + b.z, 0.f) * mk[j + 2] * ki;
+                        h[j + 3] = fmaxf(h[j + 3] + b.w, 0.f) * mk[j + 3] * ki;
                     }
                 }
-                if (l + 1 < L) {
-                    // next layer's A operand: my columns, split into hi/lo, into the exchange image
-                    float *img = ximg + (size_t)buf * 2 * lo_off;
+                if (l + 1 == L) break;
+                // next layer's A operand: my columns, plain fp32, into the exchange image
+                if (compute) {
+                    float *img = ximg + (size_t)buf * img_floats;
 #pragma unroll
                     for (int j = 0; j < HW; j += 4)
-                        tc_store_hilo(img, lo_off, (c0 + j) >> 3, ((c0 + j) >> 2) & 1, p,
-                                      make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]));
+                        tc_store_img(img, (c0 + j) >> 3, ((c0 + j) >> 2) & 1, p, make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]));
                 }
+                TC_MARK(1 + 16 * which);
+                tc_fence_before();
+                tc_cluster_sync();
+                tc_fence_after();
+                TC_MARK(3 + 16 * which);
+                if (compute) {
+                    // kept for the reverse sweep / weight gradient (after the barrier: off the exchange's critical path)
+                    const int npad = net.npad[l];
+                    float *sv = prm.ws + net.saved_off[l] + ((size_t)t * N + n) * npad + c0;
+#pragma unroll
+                    for (int j = 0; j < HW; j += 4)
+                        if (valid && c0 + j < npad) *reinterpret_cast<float4 *>(sv + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+                    tc_mask_issue<HW>(prm, net, l + 1, n, c0, mk);      // in flight while the layer runs
+                }
+                // ---------------- hidden x hidden layer on the tensor cores ----------------
+                tc_wide_layer(prm, ring, &bars, pp, sched, ximg + (size_t)buf * img_floats, net.kb[l], tmem_d, p, half,
+                              (dbg_step && which == 1) ? prm.dbg + 512 : nullptr);
+                buf ^= 1;
+                TC_MARK(4 + 16 * which);
+                if (compute) tc_ld_acc<HW>(tmem_rd, h);
             }
             TC_MARK(5 + 16 * which);
             // ---------------- output projection: partial sums over my columns ----------------
-            {
+            if (compute) {
                 const float *wl = smem + net.s_wlast + half * HW;
                 float *mine = aux + half * (nop * TC_M) + p;
 #pragma unroll 1
@@ -257,33 +302,44 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                     }
                     mine[o * TC_M] = s0 + s1;
                 }
+                CTA_SYNC();
             }
-            __syncthreads();
             float *opart = opart2 + (size_t)pass * C * nop * TC_M;      // double-buffered by pass parity
             pass ^= 1;
-            // the two column halves meet; [rank][o][particle] rows of 128 floats, coalesced
-            for (int i = tid; i < net.nout * TC_M; i += TC_NT)
-                opart[(size_t)rank * nop * TC_M + i] = aux[i] + aux[nop * TC_M + i];
+            if (compute) {
+                // the two column halves meet; [rank][o][particle] rows of 128 floats, coalesced
+                for (int i = tid; i < net.nout * TC_M; i += TC_NT)
+                    opart[(size_t)rank * nop * TC_M + i] = aux[i] + aux[nop * TC_M + i];
+            }
             TC_MARK(6 + 16 * which);
             tc_fence_before();
             tc_cluster_sync();
             tc_fence_after();
             TC_MARK(8 + 16 * which);
-            // every CTA adds the C partials in rank order: bit-identical outputs everywhere
-            tc_reduce_partials(opart, net.nout * TC_M, nop, smem + net.s_bias + L * TC_MAXNS, aux);
-            __syncthreads();
+            if (compute) {
+                {   // last hidden layer, kept for the reverse sweep / weight gradient
+                    const int npad = net.npad[L - 1];
+                    float *sv = prm.ws + net.saved_off[L - 1] + ((size_t)t * N + n) * npad + c0;
+#pragma unroll
+                    for (int j = 0; j < HW; j += 4)
+                        if (valid && c0 + j < npad) *reinterpret_cast<float4 *>(sv + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+                }
+                tc_mask_issue<HW>(prm, which ? prm.pol : prm.dyn, 0, n, c0, mk);     // first layer of the next pass
+                // every CTA adds the C partials in rank order: bit-identical outputs everywhere
+                tc_reduce_partials(opart, net.nout * TC_M, nop, smem + net.s_bias + L * TC_MAXNS, aux);
+                CTA_SYNC();
+            }
             TC_MARK(9 + 16 * which);
-            if (which == 0) {
-                // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
-                //      dynamics input (core.py:269,177) ----
-                if (tid < TC_M) {
-                    for (int u = 0; u < U; ++u) {
+            if (compute) {
+                if (which == 0) {
+                    // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243);
+                    //      dynamics input (core.py:269,177): thread (particle, half) takes every second dim ----
+                    for (int u = half; u < U; u += 2) {
                         const float mu = aux[u * TC_M + p];
                         float uu = mu, ls = 0.f;
                         if (net.has_density) {
                             ls = aux[(U + u) * TC_M + p];
-                            const float z = __ldg(net.z + (size_t)t * net.zstride + (size_t)n * U + u);
-                            uu += z * exp_clamped_logstd(ls, net.lmax, elmax_pol);
+                            uu += zt[p * TC_SDP + u] * exp_clamped_logstd(ls, net.lmax, elmax_pol);
                         }
                         const float a = cst[C_SCALE + u] * tanhf(uu) + cst[C_BIAS + u];
                         xin[p * TC_SDP + D + u] = (a - cst[C_MX + D + u]) * cst[C_ISX + D + u];
@@ -294,20 +350,17 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                             if (net.has_density) raw[U + u] = ls;
                         }
                     }
-                    for (int d = 0; d < D; ++d) xin[p * TC_SDP + d] = (st[p * TC_SDP + d] - cst[C_MX + d]) * cst[C_ISX + d];
-                }
-            } else {
-                // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
-                if (tid < TC_M) {
-                    for (int d = 0; d < D; ++d) {
+                    for (int d = half; d < D; d += 2) xin[p * TC_SDP + d] = (st[p * TC_SDP + d] - cst[C_MX + d]) * cst[C_ISX + d];
+                } else {
+                    // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
+                    for (int d = half; d < D; d += 2) {
                         const float sy = cst[C_SY + d], my = cst[C_MY + d];
                         const float mu = aux[d * TC_M + p];
                         float delta, ls = 0.f;
                         if (net.has_density) {
                             ls = aux[(D + d) * TC_M + p];
-                            const float z = __ldg(net.z + (size_t)t * net.zstride + (size_t)n * D + d);
                             // exp(clamped log-std + log Sy) = Sy * exp(clamped log-std)   (densities.py:105)
-                            delta = (mu * sy + my) + z * (sy * exp_clamped_logstd(ls, net.lmax, elmax_dyn));
+                            delta = (mu * sy + my) + zt[(TC_M + p) * TC_SDP + d] * (sy * exp_clamped_logstd(ls, net.lmax, elmax_dyn));
                         } else {
                             delta = mu * sy + my;
                         }
@@ -320,57 +373,57 @@ __global__ void __launch_bounds__(TC_NT, 1) tc_fwd_kernel(const __grid_constant_
                             if (prm.mm_states) prm.s1pre[((size_t)t * N + n) * D + d] = s1;
                         }
                     }
-                }
-                if (prm.mm_states) {
-                    __syncthreads();
-                    TC_MARK(11 + 16 * which);
-                    tc_mm_forward(prm, st, ring, t, n0, nval, rank);      // rollout.py:121-132 (ring memory is idle here)
-                }
-                if (tid < TC_M) {
-                    for (int d = 0; d < D; ++d) {
+                    if (prm.mm_states) {
+                        CTA_SYNC();
+                        TC_MARK(11 + 16 * which);
+                        tc_mm_forward(prm, st, mmscr, t, n0, nval, rank);      // rollout.py:121-132
+                    }
+                    for (int d = half; d < D; d += 2) {
                         const float s1 = st[p * TC_SDP + d];
                         xin[p * TC_SDP + d] = s1;
                         if (owner) prm.states[((size_t)(t + 1) * N + n) * D + d] = s1;
                     }
                 }
+                CTA_SYNC();
             }
-            __syncthreads();
             TC_MARK(10 + 16 * which);
         }
     }
     // ---- rewards r_t = scale*exp(-0.5*(d^T Q d + a^T R a)) + offset on (s_{t+1}, a_t) for every step
     //      (envs/cartpole/env.py:62-86).  Nothing in the recurrence consumes them: evaluated here, off the serial
     //      chain, for the particles whose trajectory THIS CTA wrote. ----
-    for (int i = tid; i < H * TC_M; i += TC_NT) {
-        const int tt = i / TC_M, q = i - tt * TC_M;
-        if (q >= nval || (q % C) != rank) continue;
-        // the reward sees the next state BEFORE moment matching (models/core.py:293 runs inside dynamics())
-        const float *s1 = prm.mm_states ? prm.s1pre + ((size_t)tt * N + n0 + q) * D
-                                        : prm.states + ((size_t)(tt + 1) * N + n0 + q) * D;
-        const float *a = prm.actions + ((size_t)tt * N + n0 + q) * U;
-        float dl[PMB_MAX_REWARD_ROWS];
-        for (int r = 0; r < prm.KR; ++r) {
-            float acc = cst[C_C0 + r];
-            for (int d = 0; d < D; ++d) acc = fmaf(cst[C_C + r * SD + d], s1[d], acc);
-            dl[r] = acc;
+    if (compute) {
+        for (int i = tid; i < H * TC_M; i += TC_NT) {
+            const int tt = i / TC_M, q = i - tt * TC_M;
+            if (q >= nval || (q % C) != rank) continue;
+            // the reward sees the next state BEFORE moment matching (models/core.py:293 runs inside dynamics())
+            const float *s1 = prm.mm_states ? prm.s1pre + ((size_t)tt * N + n0 + q) * D
+                                            : prm.states + ((size_t)(tt + 1) * N + n0 + q) * D;
+            const float *a = prm.actions + ((size_t)tt * N + n0 + q) * U;
+            float dl[PMB_MAX_REWARD_ROWS];
+            for (int r = 0; r < prm.KR; ++r) {
+                float acc = cst[C_C0 + r];
+                for (int d = 0; d < D; ++d) acc = fmaf(cst[C_C + r * SD + d], s1[d], acc);
+                dl[r] = acc;
+            }
+            float cost = 0.f;
+            for (int r = 0; r < prm.KR; ++r) {
+                float qq = 0.f;
+                for (int j = 0; j < prm.KR; ++j) qq = fmaf(dl[j], cst[C_Q + j * 4 + r], qq);
+                cost = fmaf(qq, dl[r], cost);
+            }
+            for (int u = 0; u < U; ++u) {
+                float qq = 0.f;
+                for (int v = 0; v < U; ++v) qq = fmaf(a[v], cst[C_R + v * SD + u], qq);
+                cost = fmaf(qq, a[u], cost);
+            }
+            prm.rewards[(size_t)tt * N + n0 + q] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
         }
-        float cost = 0.f;
-        for (int r = 0; r < prm.KR; ++r) {
-            float qq = 0.f;
-            for (int j = 0; j < prm.KR; ++j) qq = fmaf(dl[j], cst[C_Q + j * 4 + r], qq);
-            cost = fmaf(qq, dl[r], cost);
-        }
-        for (int u = 0; u < U; ++u) {
-            float qq = 0.f;
-            for (int v = 0; v < U; ++v) qq = fmaf(a[v], cst[C_R + v * SD + u], qq);
-            cost = fmaf(qq, a[u], cost);
-        }
-        prm.rewards[(size_t)tt * N + n0 + q] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
     }
     tc_fence_before();
     __syncthreads();
     tc_cluster_sync();          // peers may still read my partial sums / image until here
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_d) : "memory");
 }
 
 static cudaError_t tc_launch_cfg(const void *fn, int C, int smem_bytes) {
@@ -389,7 +442,7 @@ cudaError_t launch_tc_fwd(const TcParams &prm, cudaStream_t stream) {
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(prm.ntiles * prm.C);
-    cfg.blockDim = dim3(TC_NT);
+    cfg.blockDim = dim3(TC_NTL);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cfg.attrs = attr;
@@ -417,7 +470,7 @@ int tc_max_active_clusters(int C, int smem_bytes) {
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(C * 16);
-    cfg.blockDim = dim3(TC_NT);
+    cfg.blockDim = dim3(TC_NTL);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.attrs = attr;
     cfg.numAttrs = 1;

@@ -3,32 +3,43 @@
 //   zhat = (z - mean z) / std_unbiased(z) per column, z = z_mm[(t + n) mod N] (rollout.py:53-59).
 // Every CTA of the cluster holds the state of ALL particles of the tile (and the tile holds every matching group
 // completely), so each CTA evaluates the group statistics redundantly from its own shared memory: no exchange, no
-// barrier beyond __syncthreads, and -- fixed summation order -- bit-identical results on every CTA.  Same
+// barrier beyond the CTA's own, and -- fixed summation order -- bit-identical results on every CTA.  Same
 // arithmetic as the streaming variant (pmb_mm.cuh): fp64 sums, the 1e-12-jittered Cholesky in fp32 like the
 // reference's, a non-positive pivot reported through the status word (reference: cholesky() raises,
 // rollout.py:25,154-157).  The reverse step is the hand-derived adjoint of oracle/rollout_oracle.py::mm_backward.
+// Called by the 256 compute threads only (CTA_SYNC = their named barrier).
 #pragma once
 #include "pmb_tc.cuh"
 
 namespace pmb {
 
-// scratch layout (floats; lives in the idle operand ring)
-constexpr int TCMM_ZS = 0;                                   // [128][TC_SDP] z rows of the tile
+// scratch layout (floats)
+constexpr int TCMM_ZT = 0;                                   // [128][TC_SDP] the z_mm table (rows 0..N-1), loaded once
+constexpr int TCMM_ZS = TCMM_ZT + TC_M * TC_SDP;             // [128][TC_SDP] z rows of the tile at this step (rotated)
 constexpr int TCMM_XS = TCMM_ZS + TC_M * TC_SDP;             // [128][TC_SDP] pre-matching particles (reverse)
 constexpr int TCMM_DBL = TCMM_XS + TC_M * TC_SDP;            // doubles: per group 2*SD means
-constexpr int TCMM_MAXG = 16;                                // groups per tile
+constexpr int TCMM_MAXG = 4;                                 // groups per tile
 constexpr int TCMM_GST = TCMM_DBL + 2 * (TCMM_MAXG * 2 * SD);   // per group: m[SD], zm[SD], zistd[SD], L[SD*SD], A, X, Sb, dm[SD]
 constexpr int TCMM_GSTRIDE = 3 * SD + 4 * SD * SD + SD;
 constexpr int TCMM_FLOATS = TCMM_GST + TCMM_MAXG * TCMM_GSTRIDE;
 
-// sum over the particles of group g of f(particle) in fp64 by 4 neighbouring lanes (fixed order)
+// sum over the particles of group g of f(particle) in fp64 by `nl` neighbouring lanes (power of two; fixed order)
 template <typename F>
-__device__ __forceinline__ double tcmm_group_sum(int sub, int base, int Ng, F f) {
+__device__ __forceinline__ double tcmm_group_sum(int sub, int nl, int base, int Ng, F f) {
     double a = 0.0;
-    for (int i = sub; i < Ng; i += 4) a += f(base + i);
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    for (int i = sub; i < Ng; i += nl) a += f(base + i);
+    for (int o = 1; o < nl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     return a;
+}
+// lanes per reduction item: as many as keep all items in one pass over the 256 compute threads
+__device__ __forceinline__ int tcmm_lanes(int items) { return items <= 8 ? 32 : items <= 16 ? 16 : items <= 32 ? 8 : 4; }
+
+// the z_mm rows 0..N-1 (rollout.py:53-59 only ever reads those), once per kernel
+__device__ __forceinline__ void tc_mm_load_table(const TcParams &prm, float *scr) {
+    for (int i = threadIdx.x; i < prm.N * prm.D; i += TC_NT) {
+        const int r = i / prm.D, d = i - r * prm.D;
+        scr[TCMM_ZT + r * TC_SDP + d] = __ldg(prm.z_mm + i);
+    }
 }
 
 // forward: st[p][d] (pre-matching particles of the tile) -> moment-matched particles, in place
@@ -36,22 +47,27 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
     const int tid = threadIdx.x, D = prm.D, N = prm.N, G = max(prm.mm_G, 1), Ng = prm.mm_Ng;
     float *zs = scr + TCMM_ZS;
     double *mean = reinterpret_cast<double *>(scr + TCMM_DBL);
-    if (tid < nval)
-        for (int d = 0; d < D; ++d) zs[tid * TC_SDP + d] = __ldg(prm.z_mm + (size_t)((t + n0 + tid) % N) * D + d);
-    __syncthreads();
-    const int sub = tid & 3, slot = tid >> 2, nslot = TC_NT >> 2;
+    if (tid < nval) {
+        const float *zr = scr + TCMM_ZT + ((t + n0 + tid) % N) * TC_SDP;
+        for (int d = 0; d < D; ++d) zs[tid * TC_SDP + d] = zr[d];
+    }
+    CTA_SYNC();
+    int nl = tcmm_lanes(G * 2 * D);
+    int sub = tid & (nl - 1), slot = tid / nl, nslot = TC_NT / nl;
     // ---- means of x and z per group (whole warps walk the loop: the shuffles are convergent) ----
     for (int it0 = 0; it0 < G * 2 * D; it0 += nslot) {
         const int it = it0 + slot;
         const bool on = it < G * 2 * D;
         const int g = on ? it / (2 * D) : 0, q = on ? it - g * 2 * D : 0;
         const float *src = q < D ? st + q : zs + (q - D);
-        const double s = tcmm_group_sum(sub, g * Ng, on ? Ng : 0, [&](int i) { return (double)src[i * TC_SDP]; });
+        const double s = tcmm_group_sum(sub, nl, g * Ng, on ? Ng : 0, [&](int i) { return (double)src[i * TC_SDP]; });
         if (on && sub == 0) mean[g * 2 * SD + (q < D ? q : SD + q - D)] = s / Ng;
     }
-    __syncthreads();
+    CTA_SYNC();
     // ---- unbiased covariance (lower triangle) + jitter, z variance ----
     const int nq = D * D + D;
+    nl = tcmm_lanes(G * nq);
+    sub = tid & (nl - 1); slot = tid / nl; nslot = TC_NT / nl;
     for (int it0 = 0; it0 < G * nq; it0 += nslot) {
         const int it = it0 + slot;
         const bool on = it < G * nq;
@@ -62,7 +78,7 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
             const int i = q / D, j = q - i * D;
             const bool low = on && j <= i;
             const double mi = mg[i], mj = mg[j];
-            const double s = tcmm_group_sum(sub, g * Ng, low ? Ng : 0, [&](int k) {
+            const double s = tcmm_group_sum(sub, nl, g * Ng, low ? Ng : 0, [&](int k) {
                 return ((double)st[k * TC_SDP + i] - mi) * ((double)st[k * TC_SDP + j] - mj);
             });
             // rollout.py:24; handed to the fp32 Cholesky (A = 3*SD + SD*SD floats into the group block)
@@ -70,7 +86,7 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
         } else {
             const int d = q - D * D;
             const double mz = mg[SD + d];
-            const double s = tcmm_group_sum(sub, g * Ng, on ? Ng : 0, [&](int k) {
+            const double s = tcmm_group_sum(sub, nl, g * Ng, on ? Ng : 0, [&](int k) {
                 const double dz = (double)zs[k * TC_SDP + d] - mz;
                 return dz * dz;
             });
@@ -81,7 +97,7 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
             }
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     // ---- fp32 Cholesky, one thread per group ----
     if (tid < G) {
         float *gs_ = scr + TCMM_GST + tid * TCMM_GSTRIDE;
@@ -103,7 +119,7 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
         }
         if (!ok && prm.status && rank == 0) atomicCAS(prm.status, 0, 1 + t);
     }
-    __syncthreads();
+    CTA_SYNC();
     // keep (m, z statistics, L) of this step for the reverse sweep
     if (rank == 0) {
         for (int i = tid; i < G * (3 * SD + SD * SD); i += TC_NT) {
@@ -123,7 +139,7 @@ __device__ __forceinline__ void tc_mm_forward(const TcParams &prm, float *st, fl
         }
         for (int d = 0; d < D; ++d) st[tid * TC_SDP + d] = xo[d];
     }
-    __syncthreads();
+    CTA_SYNC();
 }
 
 // reverse: gs[p][d] holds the cotangent of the moment-matched particles x'; on return the cotangent of the
@@ -137,14 +153,16 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
         const int g = i / GS, k = i - g * GS;
         scr[TCMM_GST + g * TCMM_GSTRIDE + k] = __ldcg(prm.mmstat + ((size_t)t * G + g) * GS + k);
     }
-    if (tid < nval)
-        for (int d = 0; d < D; ++d) {
-            zs[tid * TC_SDP + d] = __ldg(prm.z_mm + (size_t)((t + n0 + tid) % N) * D + d);
-            xs[tid * TC_SDP + d] = __ldcg(prm.s1pre + ((size_t)t * N + n0 + tid) * D + d);
-        }
-    __syncthreads();
-    const int sub = tid & 3, slot = tid >> 2, nslot = TC_NT >> 2;
+    if (tid < nval) {
+        const float *zr = scr + TCMM_ZT + ((t + n0 + tid) % N) * TC_SDP;
+        for (int d = 0; d < D; ++d) zs[tid * TC_SDP + d] = zr[d];
+    }
+    for (int i = tid; i < nval * D; i += TC_NT)       // pre-matching particles of the step: one coalesced block
+        xs[(i / D) * TC_SDP + (i % D)] = __ldcg(prm.s1pre + ((size_t)t * N + n0) * D + i);
+    CTA_SYNC();
     const int nq = D * D + D;
+    const int nl = tcmm_lanes(G * nq);
+    const int sub = tid & (nl - 1), slot = tid / nl, nslot = TC_NT / nl;
     for (int it0 = 0; it0 < G * nq; it0 += nslot) {
         const int it = it0 + slot;
         const bool on = it < G * nq;
@@ -155,17 +173,17 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
             const int i = q / D, j = q - i * D;
             const bool low = on && j <= i;
             const float zm = gs_[SD + j], zi = gs_[2 * SD + j];
-            const double s = tcmm_group_sum(sub, g * Ng, low ? Ng : 0, [&](int k) {
+            const double s = tcmm_group_sum(sub, nl, g * Ng, low ? Ng : 0, [&](int k) {
                 return (double)gs[k * TC_SDP + i] * (double)((zs[k * TC_SDP + j] - zm) * zi);
             });
             if (on && sub == 0) X[i * SD + j] = low ? (float)s : 0.f;          // dL (lower triangle), staged in X
         } else {
             const int d = q - D * D;
-            const double s = tcmm_group_sum(sub, g * Ng, on ? Ng : 0, [&](int k) { return (double)gs[k * TC_SDP + d]; });
+            const double s = tcmm_group_sum(sub, nl, g * Ng, on ? Ng : 0, [&](int k) { return (double)gs[k * TC_SDP + d]; });
             if (on && sub == 0) dm[d] = (float)s;
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     // A = Phi(L^T dL): lower triangle, diagonal halved
     for (int it = tid; it < G * D * D; it += TC_NT) {
         const int g = it / (D * D), q = it - g * D * D, i = q / D, j = q - i * D;
@@ -179,7 +197,7 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
         }
         A[i * SD + j] = a;
     }
-    __syncthreads();
+    CTA_SYNC();
     // X = L^-T A  (back substitution, one column per thread)
     for (int it = tid; it < G * D; it += TC_NT) {
         const int g = it / D, j = it - g * D;
@@ -192,7 +210,7 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
             X[r * SD + j] = s / Lm[r * SD + r];
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     // Sb = X L^-1  (one row per thread)
     for (int it = tid; it < G * D; it += TC_NT) {
         const int g = it / D, i = it - g * D;
@@ -205,7 +223,7 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
             Sb[i * SD + c] = s / Lm[c * SD + c];
         }
     }
-    __syncthreads();
+    CTA_SYNC();
     if (tid < nval) {
         const int g = tid / Ng;
         const float *gs_ = scr + TCMM_GST + g * TCMM_GSTRIDE;
@@ -219,7 +237,7 @@ __device__ __forceinline__ void tc_mm_backward(const TcParams &prm, float *gs, f
         }
         for (int d = 0; d < D; ++d) gs[tid * TC_SDP + d] = out[d];
     }
-    __syncthreads();
+    CTA_SYNC();
 }
 
 }  // namespace pmb

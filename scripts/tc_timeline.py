@@ -19,8 +19,8 @@ eng.tune.reserved[2] = ptr & 0xffffffff if (ptr & 0xffffffff) < 2**31 else (ptr 
 eng.tune.reserved[3] = ptr >> 32
 eng.step(x0.cuda()); torch.cuda.synchronize()
 d = dbg.cpu().tolist()
-names = {0: "pass top", 1: "first layer + epilogue + image stores issued", 2: "fence.proxy.async done", 3: "cluster barrier passed",
-         4: "operands streamed + MMAs done", 5: "tcgen05.ld + epilogue done", 6: "projection partials -> global",
+names = {0: "pass top", 1: "first layer + epilogue + image stores issued", 3: "cluster barrier passed",
+         4: "image -> TMEM + MMAs done (last wide layer)", 5: "tcgen05.ld + epilogue done", 6: "projection partials -> global",
          8: "cluster barrier passed", 9: "partials reduced", 11: "(mm start)", 10: "per-particle stage done"}
 order = [0, 1, 2, 3, 4, 5, 6, 8, 9, 11, 10]
 t0 = min(x for x in d[0:8] if x)
@@ -32,3 +32,9 @@ for which, nm in ((0, "policy"), (1, "dynamics")):
             continue
         v = [x - t0 if x else -1 for x in row]
         print("  %-9s %-46s | %s" % (nm, names[k], " ".join("%6d" % x for x in v)))
+
+print("dynamics wide layer, per compute warp: cycles from entry to [loads issued, chunk 0 parked, chunk 1, ..., accumulator done]")
+for w in range(8):
+    v = [x for x in d[512 + 24 * w: 512 + 24 * w + 24] if x]
+    if v:
+        print("   warp %d: %s" % (w, " ".join("%6d" % (x - v[0]) for x in v)))
