@@ -87,13 +87,13 @@ typedef struct pmb_problem {
 typedef struct pmb_tuning {
     int particles_per_cta;   /* 1, 2, 4 or 8 */
     int stream_mode;         /* sweep variant: 0 = auto (FFMA2 cluster-resident sweeps for two-hidden-layer nets <= 256
-                                wide with <= 128 particles and no moment matching of the states; otherwise the
-                                tensor-core cluster sweeps when eligible; otherwise 2),
+                                wide without moment matching of the states; otherwise 2),
                                 1/2 = streaming sweeps (hidden x hidden weights through a TMA + mbarrier ring),
                                 3 = cluster-resident sweeps required (all weights in the shared memory of a
                                 thread-block cluster; PMB_E_UNSUPPORTED when the problem is outside them),
                                 4 = tensor-core cluster sweeps required (tcgen05 3xTF32 hidden x hidden layers,
-                                16-CTA cluster per 128-particle tile; PMB_E_UNSUPPORTED when outside them) */
+                                16-CTA cluster per 128-particle tile; PMB_E_UNSUPPORTED when outside them; opt-in:
+                                measured slower than the FFMA2 variants at every BASELINE shape) */
     int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
                                 4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default; with

@@ -484,11 +484,11 @@ static int plan_tc(const pmb_problem *p, const pmb_tuning *tune, Plan &pl, Alloc
         if (mode == 4) return fail(PMB_E_UNSUPPORTED, "problem is outside the tensor-core cluster sweeps");
         return PMB_OK;
     }
-    if (mode == 0) {
-        // auto: the FFMA2 cluster-resident sweeps keep the shapes they were built for (two hidden layers <= 256 wide,
-        // few particles: BASELINE c1 / c2); everything else that is eligible runs here
-        if (!p->mm_states && cluster_eligible(p, 8) && p->N <= TC_M) return PMB_OK;
-    }
+    // Opt-in only (stream_mode 4).  Measured on B200 (profiles/r02_tc_timelines_v1_v2.txt): a tcgen05.mma costs ~100
+    // cycles to issue whatever its size, a column slice of a 128-particle tile is only N = 16..64 wide and K = 8 per
+    // tf32 instruction, so one 512x512 layer is 192 instructions = ~25 k cycles per CTA -- slower than the FFMA2
+    // streaming sweeps at every BASELINE shape.  The auto planner therefore never picks this variant.
+    if (mode != 4) return PMB_OK;
     int maxw = 0, nop = 1;
     const pmb_net *nets[2] = {&p->pol, &p->dyn};
     for (int i = 0; i < 2; ++i) {
@@ -544,19 +544,29 @@ static int plan_tc(const pmb_problem *p, const pmb_tuning *tune, Plan &pl, Alloc
         T.off_z = take(pass ? TC_M * PW : 2 * TC_M * TC_SDP);             // forward: density noise; reverse: adjoint factors
         T.off_mm = p->mm_states ? take(TCMM_FLOATS) : off;
         T.off_ring = off;
-        const int budget = SMEM_LIMIT_FLOATS - 1024 - off;         // 4 KB of slack for the static barriers + schedule table
-        const int per_stage = 2 * TC_KC * ns * 8;
-        int nstage = min(TC_NSW, budget / per_stage);
-        {
-            const int e = tune ? tune->reserved[1] : 0;            // tuning aid: bits 8-11 weight stages
-            if (mode == 4 && ((e >> 8) & 15) >= 1 && ((e >> 8) & 15) <= TC_NSW) nstage = min(nstage, (e >> 8) & 15);
+        const int budget = SMEM_LIMIT_FLOATS - 1280 - off;         // 5 KB of slack for the static barriers + schedule table
+        const int per_stage = 2 * TC_KC * ns * 8;                  // weights: hi | lo of TC_KC k-blocks
+        const int per_x = TC_KC * 1024;                            // image: fp32 [TC_KC][2][128][4]
+        int nsx = TC_NSX, nstage = TC_NSW;
+        while (nsx * per_x + nstage * per_stage > budget && (nstage > 2 || nsx > 2)) {
+            if (nstage > 2 && (nstage >= nsx + 1 || nsx <= 2)) --nstage; else --nsx;
         }
-        if (nstage < 1) return mode == 4 ? fail(PMB_E_UNSUPPORTED, "tensor-core plan does not fit in shared memory") : PMB_OK;
+        {
+            const int e = tune ? tune->reserved[1] : 0;            // tuning aid: bits 0-3 image stages, 8-11 weight stages
+            if (mode == 4 && ((e >> 8) & 15) >= 1 && ((e >> 8) & 15) <= TC_NSW) nstage = min(nstage, (e >> 8) & 15);
+            if (mode == 4 && (e & 15) >= 1 && (e & 15) <= TC_NSX) nsx = min(nsx, e & 15);
+        }
+        if (nsx * per_x + nstage * per_stage > budget)
+            return mode == 4 ? fail(PMB_E_UNSUPPORTED, "tensor-core plan does not fit in shared memory") : PMB_OK;
         T.kb_stage = TC_KC;
         T.nstage = nstage;
+        T.nsx = nsx;
+        T.nsa = min(TC_NSA, (512 - TC_NDRV * ns) / 128);
         T.dbg_flags = (tune && mode == 4) ? (tune->reserved[1] >> 12) & 15 : 0;
         T.stage_floats = per_stage;
         off += nstage * per_stage;
+        T.off_xring = off;
+        off += nsx * per_x;
         T.smem_floats = off;
     }
     pl.tc_wpack_off = ws.take(wa.top);
@@ -770,7 +780,7 @@ int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_inf
     if (pl.tc) {
         info->variant = 2;
         info->ctas = pl.tfwd.ntiles * pl.tc;
-        info->threads_per_cta = TC_NT;
+        info->threads_per_cta = TC_NTL;
         info->cluster_size = pl.tc;
         info->particles_per_group = pl.tfwd.TP;
         info->smem_fwd_bytes = pl.tfwd.smem_floats * 4;

@@ -13,12 +13,13 @@
 //     ring that runs ahead across layer boundaries (weights do not depend on the step's data);
 //   * activations (A operand): every CTA's epilogue (TMEM -> registers: bias, ReLU, dropout mask, keep) writes its
 //     columns as plain fp32 to a small exchange image in global memory (L2 resident, [k-block][k half][row][4]:
-//     coalesced both ways); after ONE cluster barrier the 8 compute warps of every CTA read the whole image back
-//     with 128-bit loads (3 chunks in flight), split it into TF32 hi/lo IN REGISTERS and park it in TENSOR MEMORY
-//     with tcgen05.st -- the MMAs take A from TMEM (profiles/r02_umma_tmem_a_probe.txt), so the activations never
-//     touch shared memory: the first version of these sweeps staged hi/lo images through shared memory and was
-//     bound by its bandwidth (1.6 MB per layer per SM, profiles/r02_tc_v1_timeline.txt).
-//   * a ninth warp drives the pipeline: one thread issues the weight TMA copies and the MMAs
+//     coalesced both ways); after ONE cluster barrier TMA streams the whole image through a shared-memory ring, the
+//     8 compute warps of every CTA pick their rows up with 128-bit shared loads, split them into TF32 hi/lo IN
+//     REGISTERS and park them in TENSOR MEMORY with tcgen05.st -- the MMAs take A from TMEM
+//     (tests/csrc/umma_tmem_a_probe.cu), so shared memory sees every activation twice (TMA write, one read) instead
+//     of the five times of the first version, which staged hi/lo images and read them per MMA
+//     (profiles/r02_tc_timelines_v1_v2.txt).
+//   * four more warps drive the pipeline: TMA producers and MMA issuers, each issuer with its own accumulator
 //     (A stage full / weight stage full -> 3 MMAs per k-block -> tcgen05.commit frees both).
 // The skinny first / last layers (K <= 16 inputs, <= 32 outputs) stay on the FP32 pipe: the first layer is formed
 // per CTA for its own columns, the output projection as per-CTA partial sums that meet in global memory
@@ -31,11 +32,10 @@ namespace pmb {
 
 constexpr int TC_NT = 256;         // COMPUTE threads per CTA: 8 warps; thread (warp w, lane) owns particle 32 (w%4) + lane
                                    // and the column half w/4 of the CTA's slice
-constexpr int TC_NTL = TC_NT + 32; // + the driver warp (weight TMA + MMA issue)
+constexpr int TC_NTL = TC_NT + 128; // + four driver warps (TMA producers + MMA issue)
 constexpr int TC_KC = 8;           // k-blocks (of 8) per pipeline chunk
-constexpr int TC_NSA = 3;          // A stages in tensor memory (2 x 64 columns each: hi | lo)
+constexpr int TC_NSA = 3;          // A stages in tensor memory (max; 2 x 64 columns each: hi | lo)
 constexpr int TC_NSW = 4;          // weight stages in shared memory (max)
-constexpr int TC_COL_A = 64;       // TMEM columns: accumulator at 0 .. ns-1, A stages from 64
 constexpr int TC_MAXITEMS = 2 * (MAXL - 1) * 16;   // weight chunks per step (schedule table)
 constexpr int TC_C = 16;           // CTAs per cluster
 constexpr int TC_M = 128;          // particles per tile (UMMA M)
@@ -77,6 +77,7 @@ struct TcParams {
     int ntiles;
     int ns;                         // columns per CTA (16, 32 or 64)
     int kb_stage, nstage;           // k-blocks per weight stage (= TC_KC), weight stages
+    int nsx, nsa;                   // image stages (shared memory), A stages (tensor memory; 4 ns + 128 nsa <= 512)
     int kbmax;                      // k-blocks of an exchange image (= C * ns / 8: every CTA writes all its columns)
     int nop;                        // rows of the partial-sum exchange: max(inputs, raw outputs) over both nets
     TcNet pol, dyn;
@@ -103,7 +104,7 @@ struct TcParams {
     int dbg_flags;                  // timing experiments only (results are wrong): 1 = skip the MMAs, 2 = skip the image
                                     // loads, 4 = skip the tcgen05.st, 8 = skip the hi/lo split
     // shared-memory carve-up (float offsets)
-    int off_cst, off_res, off_xin, off_st, off_aux, off_z, off_mm, off_ring;
+    int off_cst, off_res, off_xin, off_st, off_aux, off_z, off_mm, off_ring, off_xring;
     int stage_floats;
     int smem_floats;
 };
@@ -198,14 +199,24 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
 }
 
 // ----------------------------------------------------------------------------------------
-// The layer pipeline of one CTA.
-//   weight stages (shared memory, TMA):  w_full  <- complete_tx,        w_empty <- tcgen05.commit
-//   A stages (tensor memory, tcgen05.st): a_full <- 8 compute warps,     a_empty <- tcgen05.commit
-//   done: the layer's accumulator is complete
+// The layer pipeline of one CTA (12 warps).
+//   driver warp 0 (thread 256): TMA producer of the weight ring (runs ahead across layers) and of the image ring
+//   image stages  (shared memory, fp32 [k-block][k half][row][4]):  x_full <- complete_tx,  x_empty <- 8 compute warps
+//   compute warps: LDS own row share -> TF32 hi/lo split -> tcgen05.st into an A stage of tensor memory
+//   A stages      (tensor memory, hi | lo):                         a_full <- 8 compute warps, a_empty <- 4 drivers
+//   weight stages (shared memory, hi | lo, UMMA canonical):         w_full <- complete_tx,  w_empty <- 4 drivers
+//   driver warps 0..3: one thread each issues the MMAs of the k-blocks kb % 4 == j into ITS OWN accumulator
+//   (a single thread sustains one tcgen05.mma per ~100 cycles whatever its size, profiles/r02_tc_timelines_v1_v2.txt;
+//   the slices are only N = 16..64 wide, so four issuers keep the tensor pipe fed); the epilogue adds the four
+//   accumulators in a fixed order.   done <- 4 drivers: the layer's accumulators are complete.
 // ----------------------------------------------------------------------------------------
+constexpr int TC_NDRV = 4;         // MMA-issuing driver warps = independent accumulators
+constexpr int TC_NSX = 3;          // image stages in shared memory (max)
 struct TcBars {
     uint64_t w_full[TC_NSW];
     uint64_t w_empty[TC_NSW];
+    uint64_t x_full[TC_NSX];
+    uint64_t x_empty[TC_NSX];
     uint64_t a_full[TC_NSA];
     uint64_t a_empty[TC_NSA];
     uint64_t done;
@@ -216,14 +227,13 @@ struct TcWItem {            // one weight chunk of the per-step schedule (this C
     uint32_t nkb;
 };
 struct TcPipe {
-    // driver thread
-    uint32_t w_issued, w_consumed, w_total, w_items;   // weight chunks issued / consumed so far, of the whole kernel, per step
-    uint32_t w_next;                                    // next schedule item to issue
-    // both sides: A chunks so far
-    uint32_t a_count;
+    // driver 0: weight chunks issued so far, of the whole kernel, per step; next schedule item; image chunks issued
+    uint32_t w_issued, w_total, w_items, w_next, x_issued;
+    // every thread: chunks consumed so far (weights by the drivers, image / A stages by everybody)
+    uint32_t count;
     uint32_t done_parity;
     __device__ __forceinline__ void init(uint32_t items, uint32_t total) {
-        w_issued = w_consumed = 0; w_total = total; w_items = items; w_next = 0; a_count = 0; done_parity = 0;
+        w_issued = 0; w_total = total; w_items = items; w_next = 0; x_issued = 0; count = 0; done_parity = 0;
     }
 };
 
@@ -232,123 +242,128 @@ __device__ __forceinline__ void tc_store_img(float *img, int kb, int khalf, int 
     *reinterpret_cast<float4 *>(img + (size_t)kb * 1024 + khalf * 512 + m * 4) = v;
 }
 
-// driver thread: keep the weight ring full (it runs ahead across layers), issue the MMAs of one layer
-__device__ __forceinline__ void tc_drive_layer(const TcParams &prm, float *ring, TcBars *bars, TcPipe &pp, const TcWItem *sched,
-                                               int KB, uint32_t tmem_base) {
-    const int ns = prm.ns, nsw = prm.nstage;
+// driver thread j of one layer
+__device__ __forceinline__ void tc_drive_layer(const TcParams &prm, float *wring, float *xring, TcBars *bars, TcPipe &pp,
+                                               const TcWItem *sched, const float *img, int KB, uint32_t tmem_base, int j) {
+    const int ns = prm.ns, nsw = prm.nstage, nsx = prm.nsx, nsa = prm.nsa;
     const int nch = (KB + TC_KC - 1) / TC_KC;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ns >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const uint32_t wlo = (uint32_t)(TC_KC * ns * 8);       // floats: lo half of a weight stage
+    const uint32_t tmem_dj = tmem_base + (uint32_t)(j * ns);
+    const uint32_t col_a = (uint32_t)(TC_NDRV * ns);
+    const uint32_t x_base = pp.count;                       // chunk counter at layer entry
+    uint32_t first = 1u;
     for (int c = 0; c < nch; ++c) {
-        while (pp.w_issued < pp.w_total && pp.w_issued < pp.w_consumed + (uint32_t)nsw) {
-            const uint32_t s = pp.w_issued % nsw;
-            if (pp.w_issued >= (uint32_t)nsw) mbar_wait(&bars->w_empty[s], ((pp.w_issued / nsw) - 1u) & 1u);
-            const TcWItem it = sched[pp.w_next];
-            const uint32_t bytes = it.nkb * (uint32_t)(ns * 32);
-            float *dst = ring + (size_t)s * prm.stage_floats;
-            mbar_expect_tx(&bars->w_full[s], 2u * bytes);
-            tma_bulk_g2s(dst, it.hi, bytes, &bars->w_full[s]);
-            tma_bulk_g2s(dst + wlo, it.hi + it.lo_off, bytes, &bars->w_full[s]);
-            ++pp.w_issued;
-            if (++pp.w_next == pp.w_items) pp.w_next = 0;
+        if (j == 0) {
+            // weights: keep nsw chunks in flight, across layer boundaries
+            while (pp.w_issued < pp.w_total && pp.w_issued < pp.count + (uint32_t)nsw) {
+                const uint32_t s = pp.w_issued % nsw;
+                if (pp.w_issued >= (uint32_t)nsw) mbar_wait(&bars->w_empty[s], ((pp.w_issued / nsw) - 1u) & 1u);
+                const TcWItem it = sched[pp.w_next];
+                const uint32_t bytes = it.nkb * (uint32_t)(ns * 32);
+                float *dst = wring + (size_t)s * prm.stage_floats;
+                mbar_expect_tx(&bars->w_full[s], 2u * bytes);
+                tma_bulk_g2s(dst, it.hi, bytes, &bars->w_full[s]);
+                tma_bulk_g2s(dst + wlo, it.hi + it.lo_off, bytes, &bars->w_full[s]);
+                ++pp.w_issued;
+                if (++pp.w_next == pp.w_items) pp.w_next = 0;
+            }
+            // image of THIS layer: keep nsx chunks in flight
+            while (pp.x_issued < x_base + (uint32_t)nch && pp.x_issued < pp.count + (uint32_t)nsx) {
+                const uint32_t s = pp.x_issued % nsx;
+                if (pp.x_issued >= (uint32_t)nsx) mbar_wait(&bars->x_empty[s], ((pp.x_issued / nsx) - 1u) & 1u);
+                const int cc = (int)(pp.x_issued - x_base);
+                const uint32_t bytes = (uint32_t)min(TC_KC, KB - cc * TC_KC) * 4096u;
+                mbar_expect_tx(&bars->x_full[s], bytes);
+                tma_bulk_g2s(xring + (size_t)s * (TC_KC * 1024), img + (size_t)cc * TC_KC * 1024, bytes, &bars->x_full[s]);
+                ++pp.x_issued;
+            }
         }
         const int nkb = min(TC_KC, KB - c * TC_KC);
-        const uint32_t sw = pp.w_consumed % nsw, sa = pp.a_count % TC_NSA;
-        mbar_wait(&bars->w_full[sw], (pp.w_consumed / nsw) & 1u);
-        mbar_wait(&bars->a_full[sa], (pp.a_count / TC_NSA) & 1u);
+        const uint32_t sw = pp.count % nsw, sa = pp.count % nsa;
+        mbar_wait(&bars->w_full[sw], (pp.count / nsw) & 1u);
+        mbar_wait(&bars->a_full[sa], (pp.count / nsa) & 1u);
         tc_fence_after();
-        const uint32_t wb = smem_u32(ring + (size_t)sw * prm.stage_floats);
-        const uint32_t ta = tmem_base + (uint32_t)TC_COL_A + sa * 128u;
-        for (int k = 0; k < nkb && !(prm.dbg_flags & 1); ++k) {
+        const uint32_t wb = smem_u32(wring + (size_t)sw * prm.stage_floats);
+        const uint32_t ta = tmem_base + col_a + sa * 128u;
+        for (int k = j; k < nkb; k += TC_NDRV) {
+            if (prm.dbg_flags & 1) break;
             const uint64_t dBh = tc_desc(wb + (uint32_t)(k * ns * 32));
             const uint64_t dBl = tc_desc(wb + wlo * 4u + (uint32_t)(k * ns * 32));
-            tc_mma_tf32_ta(tmem_base, ta + 8u * k, dBh, idesc, (c | k) ? 1u : 0u);
-            tc_mma_tf32_ta(tmem_base, ta + 8u * k, dBl, idesc, 1u);
-            tc_mma_tf32_ta(tmem_base, ta + 64u + 8u * k, dBh, idesc, 1u);
+            tc_mma_tf32_ta(tmem_dj, ta + 8u * k, dBh, idesc, first ? 0u : 1u);
+            tc_mma_tf32_ta(tmem_dj, ta + 8u * k, dBl, idesc, 1u);
+            tc_mma_tf32_ta(tmem_dj, ta + 64u + 8u * k, dBh, idesc, 1u);
+            first = 0u;
         }
         tc_commit(&bars->a_empty[sa]);
         tc_commit(&bars->w_empty[sw]);
-        ++pp.w_consumed;
-        ++pp.a_count;
+        ++pp.count;
     }
     tc_commit(&bars->done);
 }
 
-// compute warps: this thread's share of chunk c of the image (row m, k-blocks 4*half .. 4*half+3) -> registers
-__device__ __forceinline__ void tc_img_issue(float (&b)[32], const float *img, int c, int KB, int m, int half, int flags = 0) {
+// compute warps: chunk -> this thread's share (row m, k-blocks 4*half .. 4*half+3) of an image stage -> TF32 hi / lo
+// -> the chunk's A stage of tensor memory
+__device__ __forceinline__ void tc_img_produce(const TcParams &prm, const float *xring, TcBars *bars, TcPipe &pp,
+                                               uint32_t tmem_lane_base, int m, int half) {
+    const int nsx = prm.nsx, nsa = prm.nsa;
+    const uint32_t sx = pp.count % nsx, sa = pp.count % nsa;
+    float x[32];
+    mbar_wait(&bars->x_full[sx], (pp.count / nsx) & 1u);
+    {
+        const float *q = xring + (size_t)sx * (TC_KC * 1024) + (size_t)(4 * half) * 1024 + m * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int kb = c * TC_KC + 4 * half + j;
-        float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
-        if (kb < KB && !(flags & 2)) {
-            const float *q = img + (size_t)kb * 1024 + m * 4;
-            lo4 = __ldcg(reinterpret_cast<const float4 *>(q));
-            hi4 = __ldcg(reinterpret_cast<const float4 *>(q + 512));
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = *reinterpret_cast<const float4 *>(q + j * 1024);
+            const float4 b = *reinterpret_cast<const float4 *>(q + j * 1024 + 512);
+            x[8 * j] = a.x; x[8 * j + 1] = a.y; x[8 * j + 2] = a.z; x[8 * j + 3] = a.w;
+            x[8 * j + 4] = b.x; x[8 * j + 5] = b.y; x[8 * j + 6] = b.z; x[8 * j + 7] = b.w;
         }
-        b[8 * j] = lo4.x; b[8 * j + 1] = lo4.y; b[8 * j + 2] = lo4.z; b[8 * j + 3] = lo4.w;
-        b[8 * j + 4] = hi4.x; b[8 * j + 5] = hi4.y; b[8 * j + 6] = hi4.z; b[8 * j + 7] = hi4.w;
     }
-}
-// ... split into TF32 hi / lo and parked in the chunk's A stage of tensor memory (lo overwrites the buffer registers)
-__device__ __forceinline__ void tc_img_produce(float (&x)[32], TcBars *bars, TcPipe &pp, uint32_t tmem_lane_base, int half,
-                                               int flags = 0) {
-    const uint32_t sa = pp.a_count % TC_NSA;
-    if (pp.a_count >= (uint32_t)TC_NSA) {
-        mbar_wait(&bars->a_empty[sa], ((pp.a_count / TC_NSA) - 1u) & 1u);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->x_empty[sx]);      // the stage may be refilled
+    if (pp.count >= (uint32_t)nsa) {
+        mbar_wait(&bars->a_empty[sa], ((pp.count / nsa) - 1u) & 1u);
         tc_fence_after();
     }
-    const uint32_t ta = tmem_lane_base + (uint32_t)TC_COL_A + sa * 128u + 32u * (uint32_t)half;
+    const uint32_t ta = tmem_lane_base + (uint32_t)(TC_NDRV * prm.ns) + sa * 128u + 32u * (uint32_t)half;
     {
         float hi[32];
-        if (!(flags & 8)) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                hi[e] = tc_tf32_hi(x[e]);
-                x[e] -= hi[e];
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) hi[e] = x[e];
+        for (int e = 0; e < 32; ++e) {
+            hi[e] = tc_tf32_hi(x[e]);
+            x[e] -= hi[e];
         }
-        if (!(flags & 4)) tc_st32(ta, hi);
+        tc_st32(ta, hi);
     }
-    if (!(flags & 4)) tc_st32(ta + 64u, x);
+    tc_st32(ta + 64u, x);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->a_full[sa]);
-    ++pp.a_count;
+    ++pp.count;
 }
 
 // One hidden x hidden layer of this CTA: D[128 x ns] = A[128 x 8 KB] . B[ns x 8 KB]^T over KB k-blocks, A from the
-// fp32 exchange image `img`.  Called by all 288 threads; returns when the accumulator is complete.
-__device__ __forceinline__ void tc_wide_layer(const TcParams &prm, float *ring, TcBars *bars, TcPipe &pp, const TcWItem *sched,
-                                              const float *img, int KB, uint32_t tmem_base, int m, int half,
-                                              long long *dbgp = nullptr) {
+// fp32 exchange image `img`.  Called by all 384 threads; returns when the accumulators are complete.
+__device__ __forceinline__ void tc_wide_layer(const TcParams &prm, float *wring, float *xring, TcBars *bars, TcPipe &pp,
+                                              const TcWItem *sched, const float *img, int KB, uint32_t tmem_base, int m,
+                                              int half, long long *dbgp = nullptr) {
     const int warp = threadIdx.x >> 5;
     const int nch = (KB + TC_KC - 1) / TC_KC;
-    const int fl = prm.dbg_flags;
     int dbi = 0;
 #define TC_WMARK() do { if (dbgp && (threadIdx.x & 31) == 0 && dbi < 24) dbgp[(threadIdx.x >> 5) * 24 + dbi++] = clock64(); } while (0)
-    if (warp == 8) {
-        if ((threadIdx.x & 31) == 0) tc_drive_layer(prm, ring, bars, pp, sched, KB, tmem_base);
+    TC_WMARK();
+    if (warp >= 8) {
+        if ((threadIdx.x & 31) == 0) tc_drive_layer(prm, wring, xring, bars, pp, sched, img, KB, tmem_base, warp - 8);
+        else pp.count += (uint32_t)nch;
         __syncwarp();
     } else {
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-        float b0[32], b1[32];          // two chunks of image loads in flight per thread (64 KB per CTA)
-        TC_WMARK();
-        tc_img_issue(b0, img, 0, KB, m, half, fl);
-        if (nch > 1) tc_img_issue(b1, img, 1, KB, m, half, fl);
 #pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-            tc_img_produce(b0, bars, pp, lane_base, half, fl);
+        for (int c = 0; c < nch; ++c) {
+            tc_img_produce(prm, xring, bars, pp, lane_base, m, half);
             TC_WMARK();
-            if (c + 2 < nch) tc_img_issue(b0, img, c + 2, KB, m, half, fl);
-            if (c + 1 < nch) {
-                tc_img_produce(b1, bars, pp, lane_base, half, fl);
-                TC_WMARK();
-                if (c + 3 < nch) tc_img_issue(b1, img, c + 3, KB, m, half, fl);
-            }
         }
     }
     mbar_wait(&bars->done, pp.done_parity);
@@ -356,6 +371,18 @@ __device__ __forceinline__ void tc_wide_layer(const TcParams &prm, float *ring, 
     tc_fence_after();
     TC_WMARK();
 #undef TC_WMARK
+}
+
+// sum of the drivers' accumulators, columns [col0, col0 + HW) of this warp's 32 TMEM lanes (fixed order)
+template <int HW>
+__device__ __forceinline__ void tc_ld_acc_sum(uint32_t taddr, int ns, int nacc, float (&v)[HW]) {
+    tc_ld_acc<HW>(taddr, v);
+    for (int j = 1; j < nacc; ++j) {
+        float w[HW];
+        tc_ld_acc<HW>(taddr + (uint32_t)(j * ns), w);
+#pragma unroll
+        for (int c = 0; c < HW; ++c) v[c] += w[c];
+    }
 }
 
 // this CTA's weight-chunk schedule of one step, in consumption order (built once by the driver thread)

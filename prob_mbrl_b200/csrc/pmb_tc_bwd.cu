@@ -68,13 +68,17 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_bwd_kernel(const __grid_constant
     if (tid == 0) {
         for (int s = 0; s < TC_NSW; ++s) {
             mbar_init(&bars.w_full[s], 1);
-            mbar_init(&bars.w_empty[s], 1);
+            mbar_init(&bars.w_empty[s], TC_NDRV);
+        }
+        for (int s = 0; s < TC_NSX; ++s) {
+            mbar_init(&bars.x_full[s], 1);
+            mbar_init(&bars.x_empty[s], TC_NT / 32);
         }
         for (int s = 0; s < TC_NSA; ++s) {
             mbar_init(&bars.a_full[s], TC_NT / 32);
-            mbar_init(&bars.a_empty[s], 1);
+            mbar_init(&bars.a_empty[s], TC_NDRV);
         }
-        mbar_init(&bars.done, 1);
+        mbar_init(&bars.done, TC_NDRV);
         fence_mbar_init();
     }
     if (tid == TC_NT) {
@@ -98,7 +102,8 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_bwd_kernel(const __grid_constant
     float *aux = smem + prm.off_aux;          // [2][nop][128]
     float *pre = smem + prm.off_z;            // [128][PW] step-local adjoint factors of the tile (cluster_bwd_pre_kernel)
     float *mmscr = smem + prm.off_mm;
-    float *ring = smem + prm.off_ring;
+    float *ring = smem + prm.off_ring;        // weight stages
+    float *xring = smem + prm.off_xring;      // image stages
     const int PW = 2 * D + 3 * U;
     if (compute) {
         load_constants(prm, cst);
@@ -206,9 +211,9 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_bwd_kernel(const __grid_constant
                     }
                     tc_gate_issue<HW>(prm, net, l - 1, t, n, c0, sv, mk);      // in flight while the layer runs
                 }
-                tc_wide_layer(prm, ring, &bars, pp, sched, ximg + (size_t)buf * img_floats, net.kb[l], tmem_d, p, half);
+                tc_wide_layer(prm, ring, xring, &bars, pp, sched, ximg + (size_t)buf * img_floats, net.kb[l], tmem_d, p, half);
                 buf ^= 1;
-                if (compute) tc_ld_acc<HW>(tmem_rd, h);
+                if (compute) tc_ld_acc_sum<HW>(tmem_rd, ns, min(TC_NDRV, net.kb[l]), h);
             }
             // ---------------- adjoint of the first layer: partial sums of d(input) over my columns ----------------
             if (compute) {

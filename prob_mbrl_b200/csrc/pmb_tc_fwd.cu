@@ -147,13 +147,17 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_fwd_kernel(const __grid_constant
     if (tid == 0) {
         for (int s = 0; s < TC_NSW; ++s) {
             mbar_init(&bars.w_full[s], 1);
-            mbar_init(&bars.w_empty[s], 1);
+            mbar_init(&bars.w_empty[s], TC_NDRV);
+        }
+        for (int s = 0; s < TC_NSX; ++s) {
+            mbar_init(&bars.x_full[s], 1);
+            mbar_init(&bars.x_empty[s], TC_NT / 32);
         }
         for (int s = 0; s < TC_NSA; ++s) {
             mbar_init(&bars.a_full[s], TC_NT / 32);
-            mbar_init(&bars.a_empty[s], 1);
+            mbar_init(&bars.a_empty[s], TC_NDRV);
         }
-        mbar_init(&bars.done, 1);
+        mbar_init(&bars.done, TC_NDRV);
         fence_mbar_init();
     }
     if (tid == TC_NT) {
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_fwd_kernel(const __grid_constant
     float *aux = smem + prm.off_aux;          // [2][nop][128] partial sums of the column halves / reduced outputs
     float *zt = smem + prm.off_z;             // [2][128][TC_SDP] density noise of the tile: policy, dynamics
     float *mmscr = smem + prm.off_mm;
-    float *ring = smem + prm.off_ring;
+    float *ring = smem + prm.off_ring;        // weight stages
+    float *xring = smem + prm.off_xring;      // image stages
     if (compute) {
         load_constants(prm, cst);
         tc_load_resident(prm, prm.pol, smem, rank, true);
@@ -280,11 +285,11 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_fwd_kernel(const __grid_constant
                     tc_mask_issue<HW>(prm, net, l + 1, n, c0, mk);      // in flight while the layer runs
                 }
                 // ---------------- hidden x hidden layer on the tensor cores ----------------
-                tc_wide_layer(prm, ring, &bars, pp, sched, ximg + (size_t)buf * img_floats, net.kb[l], tmem_d, p, half,
+                tc_wide_layer(prm, ring, xring, &bars, pp, sched, ximg + (size_t)buf * img_floats, net.kb[l], tmem_d, p, half,
                               (dbg_step && which == 1) ? prm.dbg + 512 : nullptr);
                 buf ^= 1;
                 TC_MARK(4 + 16 * which);
-                if (compute) tc_ld_acc<HW>(tmem_rd, h);
+                if (compute) tc_ld_acc_sum<HW>(tmem_rd, ns, min(TC_NDRV, net.kb[l]), h);
             }
             TC_MARK(5 + 16 * which);
             // ---------------- output projection: partial sums over my columns ----------------

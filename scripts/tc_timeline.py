@@ -34,7 +34,7 @@ for which, nm in ((0, "policy"), (1, "dynamics")):
         print("  %-9s %-46s | %s" % (nm, names[k], " ".join("%6d" % x for x in v)))
 
 print("dynamics wide layer, per compute warp: cycles from entry to [loads issued, chunk 0 parked, chunk 1, ..., accumulator done]")
-for w in range(8):
+for w in range(12):
     v = [x for x in d[512 + 24 * w: 512 + 24 * w + 24] if x]
     if v:
         print("   warp %d: %s" % (w, " ".join("%6d" % (x - v[0]) for x in v)))

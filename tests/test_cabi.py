@@ -114,10 +114,10 @@ def test_planner_accepts_the_baseline_configs(lib):
 
 
 def test_planner_picks_the_sweep_variant(lib, monkeypatch):
-    """Two hidden layers of <= 256 units, <= 128 particles, no state moment matching: FFMA2 cluster-resident sweeps
-    (weights in the shared memory of an 8-CTA cluster, two 4-slot particle tiles per CTA).  Moment matching of the
-    states, wider / deeper nets, more particles: tensor-core cluster sweeps (16-CTA cluster per 128-particle tile).
-    stream_mode 2 forces the streaming sweeps, 3 requires cluster-resident, 4 requires tensor-core."""
+    """Two hidden layers of <= 256 units without state moment matching: FFMA2 cluster-resident sweeps (weights in the
+    shared memory of an 8-CTA cluster, two 4-slot particle tiles per CTA); everything else: streaming sweeps.
+    stream_mode 2 forces the streaming sweeps, 3 requires cluster-resident, 4 requires the tensor-core cluster
+    sweeps (16-CTA cluster per 128-particle tile; opt-in: measured slower than the FFMA2 variants)."""
     from prob_mbrl_b200 import _lib
     from prob_mbrl_b200.operands import NotEligible
     monkeypatch.delenv("PMB_STREAM_MODE", raising=False)
@@ -128,11 +128,13 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     assert c2["ctas"] // 8 * c2["particles_per_group"] >= 100
     assert c2["smem_fwd_bytes"] <= 232448 and c2["smem_bwd_bytes"] <= 232448
     assert c2["launches_fwd"] == 2 and c2["launches_bwd"] == 1 + 1 + 3 + 1
+    tc = _lib.make_tuning(stream_mode=4)
     for kw, tiles, tp in ((dict(N=100, H=400, mm=True), 1, 100), (dict(N=125, H=600, D=8, hid=(400, 400, 400)), 1, 125),
                           (dict(N=250, H=1000, hid=(512, 512)), 2, 125), (dict(N=1000, H=40), 8, 125)):
-        info = _lib.describe_plan(_fake_problem(**kw), auto)
+        assert _lib.describe_plan(_fake_problem(**kw), auto)["variant"] == 0, kw      # auto: streaming sweeps
+        info = _lib.describe_plan(_fake_problem(**kw), tc)
         assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16 * tiles, kw
-        assert info["particles_per_group"] == tp and info["threads_per_cta"] == 256
+        assert info["particles_per_group"] == tp and info["threads_per_cta"] == 384
         assert info["smem_fwd_bytes"] <= 232448 - 1024 and info["smem_bwd_bytes"] <= 232448 - 1024
         forced = _lib.describe_plan(_fake_problem(**kw), _lib.make_tuning(stream_mode=2))
         assert forced["variant"] == 0 and forced["cluster_size"] == 1, kw
@@ -140,8 +142,6 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     assert tc2["variant"] == 2 and tc2["launches_fwd"] == 3 and tc2["launches_bwd"] == 1 + 1 + 3 + 1
     with pytest.raises(NotEligible):
         _lib.describe_plan(_fake_problem(N=300, H=40, mm=True), _lib.make_tuning(stream_mode=4))   # group > one tile
-    big_mm = _lib.describe_plan(_fake_problem(N=144, H=40, mm=True), auto)           # ... falls to the grid-barrier sweeps
-    assert big_mm["variant"] == 0
     ring = _lib.describe_plan(_fake_problem(), _lib.make_tuning(stream_mode=2))
     assert ring["variant"] == 0 and ring["launches_bwd"] == 1 + 3 + 1
     with pytest.raises(NotEligible):

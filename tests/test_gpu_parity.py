@@ -184,7 +184,8 @@ def test_planner_runs_the_bench_workload_on_the_cluster_resident_sweeps(monkeypa
     assert info["variant"] == 1 and info["cluster_size"] == 8
     assert info["ctas"] <= 148 and info["ctas"] // 8 * info["particles_per_group"] >= 100
     mm = _lib.make_problem(o, 100, int(g["H"]), mm_states=True, z_mm=torch.zeros(500, o.D, device="cuda"))[0]
-    info = _lib.describe_plan(mm, _lib.make_tuning())       # moment matching of the states: tensor-core cluster sweeps
+    assert _lib.describe_plan(mm, _lib.make_tuning())["variant"] == 0      # moment matching: streaming sweeps
+    info = _lib.describe_plan(mm, _lib.make_tuning(stream_mode=4))          # ... or, opt-in, the tensor-core cluster sweeps
     assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16
 
 
