@@ -131,7 +131,7 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     tc = _lib.make_tuning(stream_mode=4)
     for kw, tiles, tp in ((dict(N=100, H=400, mm=True), 1, 100), (dict(N=125, H=600, D=8, hid=(400, 400, 400)), 1, 125),
                           (dict(N=250, H=1000, hid=(512, 512)), 2, 125), (dict(N=1000, H=40), 8, 125)):
-        assert _lib.describe_plan(_fake_problem(**kw), auto)["variant"] == 0, kw      # auto: streaming sweeps
+        assert _lib.describe_plan(_fake_problem(**kw), auto)["variant"] == (1 if kw["N"] == 1000 else 0), kw
         info = _lib.describe_plan(_fake_problem(**kw), tc)
         assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16 * tiles, kw
         assert info["particles_per_group"] == tp and info["threads_per_cta"] == 384
