@@ -615,7 +615,11 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     memset(&pl, 0, sizeof(pl));
     pl.mm_G = G;
     int P = tune && tune->particles_per_cta ? tune->particles_per_cta : 0;
+    const bool autoP = P == 0;
     if (P == 0) P = (p->N > 8 * 148) ? 8 : (p->N > 2 * 148) ? 4 : (p->N > 148) ? 2 : 1;   // few particles: spread over more SMs
+    // moment matching: every step ends in a grid barrier whose cost grows with the CTA count (c3, 100 particles:
+    // 22.1 / 17.4 / 16.3 / 19.7 ms per iteration at P = 1 / 2 / 4 / 8, profiles/r02_tc_timelines_v1_v2.txt)
+    if (autoP && p->mm_states && P < 4 && p->N >= 16) P = 4;
     if (P != 1 && P != 2 && P != 4 && P != 8) return fail(PMB_E_INVALID, "particles_per_cta must be 1, 2, 4 or 8");
     if (p->mm_states) {
         // every CTA of the grid takes part in a per-step barrier: CTAs must not straddle groups and the
