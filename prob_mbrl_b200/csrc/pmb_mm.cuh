@@ -26,6 +26,7 @@ struct MMSmem {
     float *L;            // [SD*SD]
     float *A, *X, *Sb;   // [SD*SD] each (reverse step)
     float *dm;           // [SD]
+    double *stage;       // [MM_STAGE] the group's per-CTA records, fetched with ONE round of parallel loads per step
     template <int P>
     __device__ __forceinline__ void carve(float *base) {
         xs = base;
@@ -37,9 +38,13 @@ struct MMSmem {
         X = A + SD * SD;
         Sb = X + SD * SD;
         dm = Sb + SD * SD;
+        stage = reinterpret_cast<double *>(dm + SD + (((2 * P * SD) & 1) ? 1 : 0));     // 8-byte aligned (offsets are even)
     }
 };
-constexpr int mm_smem_floats(int P) { return 2 * P * SD + 8 * SD + 3 * SD + 4 * SD * SD + SD + 32; }
+// The combine after the grid barrier used to walk the group's records with dependent L2 loads (one round trip per
+// CTA and quantity: ~17 k cycles per step at 25 CTAs); the records are now staged in shared memory first.
+constexpr int MM_STAGE = 1280;   // doubles: e.g. 31 CTAs x 41 doubles (D = 5); larger groups fall back to direct loads
+constexpr int mm_smem_floats(int P) { return 2 * P * SD + 8 * SD + 3 * SD + 4 * SD * SD + SD + 34 + 2 * MM_STAGE; }
 
 // All CTAs of the (cooperatively launched) grid meet here.  `epoch` counts arrivals expected so far.
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &epoch) {
@@ -121,15 +126,29 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
     }
     if (tid == 0) rec[0] = (double)grp.Pv;
     grid_barrier(prm.mmctr, epoch);
-    const double *recs = prm.mmrec + (size_t)(t & 1) * gridDim.x * MMREC;
+    // the records of this group: staged in shared memory when they fit (one round of parallel loads), else read in place
+    const int ncta = grp.c1 - grp.c0, nrec = 1 + 3 * D + D * D;
+    const bool staged = ncta * nrec <= MM_STAGE;
+    const double *recs = prm.mmrec + ((size_t)(t & 1) * gridDim.x + grp.c0) * MMREC;
+    int rstride = MMREC;
+    if (staged) {
+        for (int i = tid; i < ncta * nrec; i += NT) {
+            const int c = i / nrec, k = i - c * nrec;
+            M.stage[i] = __ldcg(recs + (size_t)c * MMREC + k);
+        }
+        CTA_SYNC();
+        recs = M.stage;
+        rstride = nrec;
+    }
+    auto rd = [&](const double *q) { return staged ? *q : __ldcg(q); };
     if (tid < D) {
         double n = 0.0, a = 0.0, b = 0.0;
-        for (int c = grp.c0; c < grp.c1; ++c) {
-            const double *r = recs + (size_t)c * MMREC;
-            const double nc = __ldcg(r);
+        for (int c = 0; c < ncta; ++c) {
+            const double *r = recs + (size_t)c * rstride;
+            const double nc = rd(r);
             n += nc;
-            a += nc * __ldcg(r + 1 + tid);
-            b += nc * __ldcg(r + 1 + D + D * D + tid);
+            a += nc * rd(r + 1 + tid);
+            b += nc * rd(r + 1 + D + D * D + tid);
         }
         gm[tid] = a / n;
         gzm[tid] = b / n;
@@ -139,10 +158,10 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
         const int i = idx / D, j = idx - i * D;
         if (j <= i) {
             double a = 0.0;
-            for (int c = grp.c0; c < grp.c1; ++c) {
-                const double *r = recs + (size_t)c * MMREC;
-                const double nc = __ldcg(r);
-                a += __ldcg(r + 1 + D + idx) + nc * (__ldcg(r + 1 + i) - gm[i]) * (__ldcg(r + 1 + j) - gm[j]);
+            for (int c = 0; c < ncta; ++c) {
+                const double *r = recs + (size_t)c * rstride;
+                const double nc = rd(r);
+                a += rd(r + 1 + D + idx) + nc * (rd(r + 1 + i) - gm[i]) * (rd(r + 1 + j) - gm[j]);
             }
             // unbiased covariance + jitter (rollout.py:24), handed to the fp32 Cholesky
             M.A[i * SD + j] = (float)(a / (double)(grp.Ng - 1)) + (i == j ? 1e-12f : 0.f);
@@ -150,11 +169,11 @@ __device__ __forceinline__ void mm_states_forward(const SweepParams &prm, const 
     }
     if (tid < D) {
         double a = 0.0;
-        for (int c = grp.c0; c < grp.c1; ++c) {
-            const double *r = recs + (size_t)c * MMREC;
-            const double nc = __ldcg(r);
-            const double dz = __ldcg(r + 1 + D + D * D + tid) - gzm[tid];
-            a += __ldcg(r + 1 + D + D * D + D + tid) + nc * dz * dz;
+        for (int c = 0; c < ncta; ++c) {
+            const double *r = recs + (size_t)c * rstride;
+            const double nc = rd(r);
+            const double dz = rd(r + 1 + D + D * D + tid) - gzm[tid];
+            a += rd(r + 1 + D + D * D + D + tid) + nc * dz * dz;
         }
         M.st[tid] = (float)gm[tid];
         M.st[SD + tid] = (float)gzm[tid];
@@ -220,10 +239,22 @@ __device__ __forceinline__ void mm_states_backward(const SweepParams &prm, const
         rec[idx] = a;
     }
     grid_barrier(prm.mmctr, epoch);
-    const double *recs = prm.mmrec + (size_t)(t & 1) * gridDim.x * MMREC;
+    const int ncta = grp.c1 - grp.c0, nrec = D * D + D;
+    const bool staged = ncta * nrec <= MM_STAGE;
+    const double *recs = prm.mmrec + ((size_t)(t & 1) * gridDim.x + grp.c0) * MMREC;
+    int rstride = MMREC;
+    if (staged) {
+        for (int i = tid; i < ncta * nrec; i += NT) {
+            const int c = i / nrec, k = i - c * nrec;
+            M.stage[i] = __ldcg(recs + (size_t)c * MMREC + k);
+        }
+        CTA_SYNC();
+        recs = M.stage;
+        rstride = nrec;
+    }
     for (int idx = tid; idx < D * D + D; idx += NT) {
         double a = 0.0;
-        for (int c = grp.c0; c < grp.c1; ++c) a += __ldcg(recs + (size_t)c * MMREC + idx);
+        for (int c = 0; c < ncta; ++c) a += staged ? recs[(size_t)c * rstride + idx] : __ldcg(recs + (size_t)c * rstride + idx);
         if (idx < D * D) M.X[(idx / D) * SD + (idx % D)] = (float)a;     // dL (lower triangle), staged in X
         else M.dm[idx - D * D] = (float)a;
     }
