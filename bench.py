@@ -390,7 +390,7 @@ class Harness:
             tune = _lib.make_tuning(phases=ph)
             return lambda: _lib.check(lib.pmb_rollout_backward(
                 pb, C.byref(tune), eng.states.data_ptr(), eng.actions.data_ptr(), eng.rewards.data_ptr(), None,
-                None, eng.g_rewards.data_ptr(), eng.grad_flat.data_ptr(), eng.dx0.data_ptr(), eng.ws.data_ptr(),
+                None, eng.g_rewards.data_ptr(), eng.grad_flat.data_ptr(), eng.dx0.data_ptr(), None, eng.ws.data_ptr(),
                 eng.nbytes, st))
 
         fwd(7)()

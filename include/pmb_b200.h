@@ -27,10 +27,10 @@
 extern "C" {
 #endif
 
-#define PMB_ABI_VERSION 2
+#define PMB_ABI_VERSION 3
 #define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
 #define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
-#define PMB_MAX_REWARD_ROWS 4 /* rows of the tip map C */
+#define PMB_MAX_REWARD_ROWS 16 /* rows of the distance map C (2 for the env tip rewards, D for losses.quadratic_*) */
 #define PMB_MAX_STATE 16      /* D + U <= 16 */
 
 enum {
@@ -70,7 +70,8 @@ typedef struct pmb_problem {
     const float *act_bias;        /* [U] Policy.bias  */
     const float *mx, *iSx;        /* [D+U] Regressor input scaler (models/core.py:177) */
     const float *my, *Sy;         /* [D]   Regressor output scaler (densities.py:100-107) */
-    int rew_rows;                 /* rows of C (2 for all reference rewards) */
+    int rew_rows;                 /* rows of C (2 for the env *Reward modules; D with C = I for a full quadratic form
+                                     on the state, reference losses.py:67-75) */
     const float *rew_C;           /* [rew_rows][D]   delta = C s' + c0 (envs/cartpole/env.py:54-75) */
     const float *rew_c0;          /* [rew_rows] */
     const float *rew_Q;           /* [rew_rows][rew_rows] */
@@ -152,11 +153,14 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
  *   g_states [H+1][N][D], g_actions [H][N][U], g_rewards [H][N]   (each may be NULL = zeros)
  *   grad_flat [pmb_policy_param_count]   OVERWRITTEN with dL/dtheta_policy (parameters() order)
  *   dx0       [N][D] or NULL             dL/dx0
+ *   da_total  [H][N][U] or NULL          TOTAL dL/da_t of every step (direct cotangent + reward + through the
+ *                                        dynamics): what a hook on actions[t] sees in the reference; prioritized
+ *                                        replay scores initial states by its norm (algorithms/mc_pilco.py:160-188)
  * Must follow a pmb_rollout_forward on the same problem/workspace. */
 int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune,
                          const float *states, const float *actions, const float *rewards,
                          const float *g_states, const float *g_actions, const float *g_rewards,
-                         float *grad_flat, float *dx0,
+                         float *grad_flat, float *dx0, float *da_total,
                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* One tensor of the optimiser step (all device pointers, `n` floats each). */

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libpmb_b200.so")
 PMB_MAX_LINEAR = 6
 PMB_MAX_WIDTH = 1024
 PMB_MAX_STATE = 16
-ABI_VERSION = 2
+PMB_MAX_REWARD_ROWS = 16
+ABI_VERSION = 3
 
 _fp = C.POINTER(C.c_float)
 
@@ -117,7 +118,7 @@ def load():
     lib.pmb_rollout_forward.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.pmb_rollout_backward.restype = C.c_int
-    lib.pmb_rollout_backward.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)] + [C.c_void_p] * 9 + \
+    lib.pmb_rollout_backward.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning)] + [C.c_void_p] * 10 + \
                                         [C.c_size_t, C.c_void_p]
     lib.pmb_clip_adam_step.restype = C.c_int
     lib.pmb_clip_adam_step.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -28,7 +28,8 @@ static int fail(int code, const char *fmt, ...) {
 static inline int round4(int x) { return (x + 3) & ~3; }
 static inline long long round32(long long x) { return (x + 31) & ~31LL; }
 
-constexpr int SMEM_LIMIT_FLOATS = 232448 / 4;   // 227 KB opt-in dynamic shared memory per CTA
+constexpr int SMEM_LIMIT_FLOATS = (232448 - 2048) / 4;   // 227 KB opt-in shared memory per CTA minus the kernels' static part
+                                                        // (ring barriers, chunk table)
 
 struct WGrad {
     long long delta_off;   // workspace floats
@@ -870,7 +871,7 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
 
 int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const float *states, const float *actions,
                          const float *rewards, const float *g_states, const float *g_actions,
-                         const float *g_rewards, float *grad_flat, float *dx0, void *workspace,
+                         const float *g_rewards, float *grad_flat, float *dx0, float *da_total, void *workspace,
                          size_t workspace_bytes, void *stream) {
     Plan pl;
     int rc = build_plan(p, tune, pl);
@@ -884,7 +885,7 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     SweepParams &B = pl.bwd;
     B.states = const_cast<float *>(states); B.actions = const_cast<float *>(actions);
     B.rewards = const_cast<float *>(rewards);
-    B.g_states = g_states; B.g_actions = g_actions; B.g_rewards = g_rewards; B.dx0 = dx0;
+    B.g_states = g_states; B.g_actions = g_actions; B.g_rewards = g_rewards; B.dx0 = dx0; B.da_total = da_total;
     if (p->mm_rewards) {
         // adjoint of the reward matching runs first, off the serial chain; the sweep then sees the
         // pre-matching rewards and their cotangent
@@ -902,6 +903,7 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
         TcParams &T = pl.tbwd;
         T.states = B.states; T.actions = B.actions; T.rewards = B.rewards;
         T.g_states = B.g_states; T.g_actions = B.g_actions; T.g_rewards = B.g_rewards; T.dx0 = B.dx0; T.dbg = B.dbg;
+        T.da_total = da_total;
         ClusterParams &P = pl.tpre;
         P.states = B.states; P.actions = B.actions; P.rewards = B.rewards;
         P.g_states = B.g_states; P.g_actions = B.g_actions; P.g_rewards = B.g_rewards;
@@ -913,6 +915,7 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
         ClusterParams &CB = pl.cbwd;
         CB.states = B.states; CB.actions = B.actions; CB.rewards = B.rewards;
         CB.g_states = B.g_states; CB.g_actions = B.g_actions; CB.g_rewards = B.g_rewards; CB.dx0 = B.dx0; CB.dbg = B.dbg;
+        CB.da_total = da_total;
         if (phases & 2) PMB_CUDA(launch_cluster_bwd(CB, pl.cl_nclusters, st));
     } else if (phases & 2) {
         PMB_CUDA(launch_rollout_bwd(B, pl.P, pl.smem_bwd_bytes, st));

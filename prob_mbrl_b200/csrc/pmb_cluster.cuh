@@ -68,6 +68,7 @@ struct ClusterParams {
     float *states, *actions, *rewards;
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
+    float *da_total;            // backward: total dL/da_t [H][N][U] (nullable)
     float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
     const float *s1pre;         // next states BEFORE moment matching [H][N][D] (the reward acts on them), nullptr = states[t+1]
     long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)

@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             } else {
                 const int u = x_k - D;
                 const float du = (c_ra + v) * c_tp;
+                if (x_own && prm.da_total) prm.da_total[((size_t)t * N + x_n) * U + u] = c_ra + v;
                 xp[u * CL_TS + x_p] = du;
                 float dls = 0.f;
                 if (pol.has_density) {

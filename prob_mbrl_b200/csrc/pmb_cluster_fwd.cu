@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         float cost = 0.f;
         for (int r = 0; r < prm.KR; ++r) {
             float q = 0.f;
-            for (int j = 0; j < prm.KR; ++j) q = fmaf(dl[j], cst[C_Q + j * 4 + r], q);
+            for (int j = 0; j < prm.KR; ++j) q = fmaf(dl[j], cst[C_Q + j * SD + r], q);
             cost = fmaf(q, dl[r], cost);
         }
         for (int u = 0; u < U; ++u) {

@@ -67,8 +67,10 @@ struct StreamItem {
 };
 
 // layout of the constants block in shared memory (floats)
+// (reward matrices C [KR][D], Q [KR][KR], R [U][U] and the symmetrised Q + Q^T, R + R^T: rows of SD floats)
 constexpr int C_MX = 0, C_ISX = 16, C_MY = 32, C_SY = 48, C_LSY = 64, C_SCALE = 80, C_BIAS = 96, C_C0 = 112,
-              C_C = 128, C_Q = 192, C_QS = 208, C_R = 224, C_RS = 480, C_TOTAL = 736;
+              C_C = 128, C_Q = 384, C_QS = 640, C_R = 896, C_RS = 1152, C_TOTAL = 1408;
+static_assert(PMB_MAX_REWARD_ROWS <= SD, "reward rows are stored with the per-particle row stride");
 
 struct SweepParams {
     int N, H, D, U;
@@ -87,6 +89,7 @@ struct SweepParams {
     // cotangents (backward)
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
+    float *da_total;            // backward: total dL/da_t [H][N][U] (nullable)
     int *status;
     // moment matching (pmb_mm.cuh)
     int mm_states, mm_rewards, mm_G, mm_Ng;
@@ -576,8 +579,8 @@ __device__ __forceinline__ void load_constants(const PRM &prm, float *cst) {
     for (int i = threadIdx.x; i < KR * D; i += NT) cst[C_C + (i / D) * SD + (i % D)] = prm.rew_C[i];
     for (int i = threadIdx.x; i < KR * KR; i += NT) {
         int a = i / KR, b = i % KR;
-        cst[C_Q + a * 4 + b] = prm.rew_Q[a * KR + b];
-        cst[C_QS + a * 4 + b] = prm.rew_Q[a * KR + b] + prm.rew_Q[b * KR + a];
+        cst[C_Q + a * SD + b] = prm.rew_Q[a * KR + b];
+        cst[C_QS + a * SD + b] = prm.rew_Q[a * KR + b] + prm.rew_Q[b * KR + a];
     }
     for (int i = threadIdx.x; i < U * U; i += NT) {
         int a = i / U, b = i % U;

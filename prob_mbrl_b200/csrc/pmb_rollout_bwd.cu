@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
             float acc = 0.f;
             for (int i = 0; i < KR; ++i) {
                 float qd = 0.f;
-                for (int j = 0; j < KR; ++j) qd = fmaf(cst[C_QS + i * 4 + j], dl[j], qd);
+                for (int j = 0; j < KR; ++j) qd = fmaf(cst[C_QS + i * SD + j], dl[j], qd);
                 acc = fmaf(qd, cst[C_C + i * SD + b_d], acc);
             }
             pre[PRE_RS * BL + b_p * SD + b_d] = stg_w[b_p] * acc;
@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(NT_LAUNCH, 1) rollout_bwd_kernel(const __grid_
                             out[(U + u) * P + x_p] = dls;
                         }
                         if (n0 + x_p < N) {
+                            if (prm.da_total) prm.da_total[((size_t)t * N + n0 + x_p) * U + u] = ga;
                             float *dd = prm.ws + pol.delta_off[pol.nlin - 1] + ((size_t)t * N + n0 + x_p) * pol.nout;
                             dd[u] = du;
                             if (pol.has_density) dd[U + u] = dls;

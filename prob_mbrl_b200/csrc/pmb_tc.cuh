@@ -93,6 +93,7 @@ struct TcParams {
     float *states, *actions, *rewards;
     const float *g_states, *g_actions, *g_rewards;
     float *dx0;
+    float *da_total;                // backward: total dL/da_t [H][N][U] (nullable)
     float *pre;                     // backward: [H][N][2D + 3U] step-local adjoint factors (cluster_bwd_pre_kernel)
     int *status;
     // moment matching of the states (reference utils/rollout.py:20-29,121-132); the whole group lives in the tile

@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_bwd_kernel(const __grid_constant
                             xo[p * TC_XO + U + u] = dls;
                         }
                         if (owner) {
+                            if (prm.da_total) prm.da_total[((size_t)t * N + n) * U + u] = ga;
                             float *dd = prm.ws + pol.delta_off[pol.L] + ((size_t)t * N + n) * pol.nout;
                             dd[u] = du;
                             if (pol.has_density) dd[U + u] = dls;

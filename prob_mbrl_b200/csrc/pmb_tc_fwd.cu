@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(TC_NTL, 1) tc_fwd_kernel(const __grid_constant
             float cost = 0.f;
             for (int r = 0; r < prm.KR; ++r) {
                 float qq = 0.f;
-                for (int j = 0; j < prm.KR; ++j) qq = fmaf(dl[j], cst[C_Q + j * 4 + r], qq);
+                for (int j = 0; j < prm.KR; ++j) qq = fmaf(dl[j], cst[C_Q + j * SD + r], qq);
                 cost = fmaf(qq, dl[r], cost);
             }
             for (int u = 0; u < U; ++u) {

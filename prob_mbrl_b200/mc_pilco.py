@@ -27,6 +27,8 @@ from .operands import NotEligible
 from .rollout import backend, fused_rollout_tensors, rollout
 
 policy_update_counter = defaultdict(lambda: 0)   # persists across calls like the reference's (mc_pilco.py:8)
+x0_tree = None          # prioritized replay: sum tree over every state seen so far (reference mc_pilco.py:9), made on first use
+episode_counter = 0     # episodes of `exp` already in the tree (reference mc_pilco.py:10)
 _ENGINES = {}   # fused-iteration engines survive across mc_pilco calls (the examples call it once per episode)
 
 
@@ -211,7 +213,7 @@ class FusedIteration:
                                            self.nbytes, self.status.data_ptr(), st))
         _lib.check(lib.pmb_rollout_backward(pb, tb, self.states.data_ptr(), self.actions.data_ptr(),
                                             self.rewards.data_ptr(), None, None, self.g_rewards.data_ptr(),
-                                            self.grad_flat.data_ptr(), self.dx0.data_ptr(), self.ws.data_ptr(),
+                                            self.grad_flat.data_ptr(), self.dx0.data_ptr(), None, self.ws.data_ptr(),
                                             self.nbytes, st))
         torch.mul(self.rewards, self.g_rewards, out=self.weighted)
         torch.sum(self.weighted.view(-1), 0, out=self.loss)
@@ -329,10 +331,10 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
              priority_alpha=0.6, priority_eps=1e-8, init_priority_beta=1.0, priority_beta_increase=0.0,
              debug=False, rollout_kwargs={}):
     """MC-PILCO policy search: ``opt_iters`` policy-gradient iterations on imagined particle rollouts."""
-    global policy_update_counter
-    if prioritized_replay:
-        raise NotEligible("prioritized_replay needs per-step action-gradient hooks (reference "
-                          "algorithms/mc_pilco.py:184-188); use the reference loop for it")
+    global policy_update_counter, x0_tree, episode_counter
+    if prioritized_replay and x0_tree is None:
+        from .replay import SumTree
+        x0_tree = SumTree(2 ** 20)
     dynamics.eval()
     policy.train()
     H = int(steps)
@@ -359,10 +361,16 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
     x0 = init_states
     N_particles = init_states.shape[0]
     n_opt_steps = policy_update_counter[policy]
+    if prioritized_replay:      # reference mc_pilco.py:79-83
+        x0_idxs = None
+        x0_weights = torch.ones_like(x0)
+        priority_beta = init_priority_beta
     mode = backend()
     rank, world = dist.world()
     sharder = None
     if world > 1:
+        if prioritized_replay:
+            raise NotEligible("prioritized replay keeps one host-side sum tree; not sharded across ranks")
         if mm_states or mm_rewards:
             raise NotEligible("moment matching across ranks needs a per-step reduction (SURVEY.md 8e/8f)")
         sharder = dist.ShardedNoise(dynamics, policy, N_particles, rank, world)
@@ -441,6 +449,8 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
             dynamics.zero_grad()
             opt.zero_grad()
             lists = None
+            want_prio = prioritized_replay and x0_idxs is not None
+            extras = {"want_action_grads": True} if want_prio else None
             try:
                 if mode == "eager":
                     lists = rollout(x0_, dynamics, policy, H, resample_state_noise=not pegasus,
@@ -452,7 +462,7 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
                 else:
                     S, A, R, status = fused_rollout_tensors(
                         x0_, dynamics, policy, H, mm_states, mm_rewards, z_mm if pegasus else None,
-                        z_rr if pegasus else None, mm_groups, not pegasus, not pegasus)
+                        z_rr if pegasus else None, mm_groups, not pegasus, not pegasus, extras)
                     if (mm_states or mm_rewards) and int(status.item()):
                         failed = ("moment matching: covariance not positive-definite at step %d"
                                   % (int(status.item()) - 1))
@@ -478,10 +488,28 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
                         returns = returns[torch.as_tensor(rd < np.quantile(rd, cvar_eps), device=returns.device)]
                     else:
                         returns = returns[torch.as_tensor(rd > np.quantile(rd, -cvar_eps), device=returns.device)]
+                step_norms = []
+                if want_prio:
+                    # importance-sampling weights (same broadcast as the reference, mc_pilco.py:158-160)
+                    returns = returns.reshape(-1, 1) * x0_weights
+                    if lists is not None:       # module loop: hooks on the per-step actions like the reference (:184-188)
+                        for a_t in lists[1]:
+                            a_t.register_hook(lambda g: step_norms.append(g.norm(dim=-1)))
                 loss = returns.mean()
                 if reg_weight > 0:
                     loss = loss + reg_weight * policy.regularization_loss()
                 loss.backward()
+                if want_prio:
+                    # score every initial state by the mean norm of dL/da_t over its particles' imagined steps and
+                    # refresh its priority (reference mc_pilco.py:165-182); the fused reverse sweep exports the
+                    # total dL/da_t of every step in one tensor
+                    m_norms = torch.stack(step_norms) if lists is not None else extras["action_grads"].norm(dim=-1)
+                    if mm_groups is not None:
+                        m_norms = m_norms.view(-1, mm_groups, int(N_particles / mm_groups)).mean(-1)
+                    scores = m_norms.mean(0).detach().cpu().numpy() / x0_tree.counts[x0_idxs - x0_tree.max_size + 1]
+                    for node, prio in zip(x0_idxs, (scores + priority_eps) ** priority_alpha):
+                        x0_tree.update(node, prio)
+                    x0_tree.renormalize()
                 if world > 1:
                     for p in policy.parameters():
                         if p.grad is not None:
@@ -523,7 +551,21 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
         if callable(on_iteration):
             lists = _as_lists(S, A, R)
             on_iteration(i, loss, lists[0], lists[1], lists[2], disc)
-        if exp is not None:
+        if exp is not None and prioritized_replay:
+            # reference mc_pilco.py:223-246: new episodes enter the tree with the largest priority seen so far, then
+            # the next batch of initial states is drawn from it together with its importance weights
+            if exp.n_samples() > x0_tree.size:
+                for ep in range(episode_counter, exp.n_episodes()):
+                    for x in torch.tensor(exp.states[ep]):
+                        x0_tree.append(x, x0_tree.max_p)
+                        x0_tree.renormalize()
+                episode_counter = exp.n_episodes()
+            nsamp = mm_groups if mm_groups is not None else N_particles
+            picked, x0_idxs, w_is = x0_tree.sample(nsamp, beta=priority_beta)
+            priority_beta = max(1.0, priority_beta + priority_beta_increase)
+            x0 = torch.stack(list(picked)).to(dev, dt)
+            x0_weights = torch.tensor(np.stack(w_is)).to(x0.device, x0.dtype)
+        elif exp is not None:
             nsamp = mm_groups if mm_groups is not None else N_particles
             x0 = exp.sample_states(nsamp, timestep=step_idx_to_sample).to(dev, dt, non_blocking=True)
             init_states = x0

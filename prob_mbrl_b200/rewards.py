@@ -101,3 +101,55 @@ class CartAcrobotReward(DoubleCartpoleReward):
     def __init__(self, pole1_length=0.6, pole2_length=0.6, target=torch.zeros(6), Q=8.0 * torch.eye(2),
                  R=1e-4 * torch.eye(1)):
         super().__init__(pole1_length, pole2_length, target, Q, R)
+
+
+# --------------------------------------------------------------------------------------------------
+# Generic quadratic costs (reference losses.py:67-75)
+# --------------------------------------------------------------------------------------------------
+def quadratic_loss(states, target, Q):
+    """(x - t)^T Q (x - t), shape [N, 1]  (reference losses.py:67-71)."""
+    target, Q = target.to(states.device), Q.to(states.device)
+    d = states - target
+    return (d.mm(Q) * d).sum(-1)[:, None]
+
+
+def quadratic_saturating_loss(states, target, Q):
+    """1 - exp(-0.5 (x - t)^T Q (x - t))  (reference losses.py:74-75)."""
+    return 1 - (-0.5 * quadratic_loss(states, target, Q)).exp()
+
+
+class QuadraticSaturatingCost(nn.Module):
+    """``reward_func`` built on the reference's ``losses.quadratic_saturating_loss``: a full D x D quadratic form on
+    the next state around ``target`` (plus an optional control penalty u^T R u inside the exponent), as a COST in
+    [0, 1) (``reward=False``, use with ``mc_pilco(..., maximize=False)``) or as the reward exp(-0.5 q) = 1 - cost.
+    It is the same function family as the env tip rewards with the distance map C = I, so the fused sweeps evaluate
+    it in-kernel: ``tip_quadratic_form()`` hands (I, -target, Q, R, scale, offset) to operands.read_reward."""
+
+    def __init__(self, target, Q, R=None, reward=False):
+        super().__init__()
+        target = torch.as_tensor(target, dtype=torch.float32).reshape(1, -1)
+        Q = torch.as_tensor(Q, dtype=torch.float32)
+        if Q.shape != (target.shape[1], target.shape[1]):
+            raise ValueError("Q must be [D, D] for a target of D entries")
+        self.target = nn.Parameter(target, requires_grad=False)
+        self.Q = nn.Parameter(Q, requires_grad=False)
+        self.R = None if R is None else nn.Parameter(torch.as_tensor(R, dtype=torch.float32), requires_grad=False)
+        self.reward = bool(reward)
+
+    def forward(self, x, u):
+        x = torch.as_tensor(x).to(device=self.Q.device, dtype=self.Q.dtype)
+        x = x.unsqueeze(0) if x.dim() == 1 else x
+        q = quadratic_loss(x, self.target, self.Q)
+        if self.R is not None:
+            u = torch.as_tensor(u).to(device=self.Q.device, dtype=self.Q.dtype)
+            u = u.unsqueeze(0) if u.dim() == 1 else u
+            q = q + (u.mm(self.R) * u).sum(-1, keepdim=True)
+        e = (-0.5 * q).exp()
+        return e if self.reward else 1 - e
+
+    def tip_quadratic_form(self):
+        D = self.target.shape[1]
+        U = 1 if self.R is None else self.R.shape[0]
+        R = torch.zeros(U, U) if self.R is None else self.R.detach().cpu()
+        scale, offset = (1.0, 0.0) if self.reward else (-1.0, 1.0)
+        return torch.eye(D), -self.target.detach().cpu().reshape(-1), self.Q.detach().cpu(), R, scale, offset

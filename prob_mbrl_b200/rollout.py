@@ -103,7 +103,10 @@ class FusedRolloutFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, problem_pack, *params):
-        ops, N, H, mm = problem_pack
+        ops, N, H, mm = problem_pack[:4]
+        # optional side channel: {"want_action_grads": True} -> backward leaves the TOTAL dL/da_t [H, N, U] of every
+        # step in extras["action_grads"] (what hooks on actions[t] see in the reference, mc_pilco.py:160-188)
+        ctx.extras = problem_pack[4] if len(problem_pack) > 4 else None
         lib = _lib.load()
         prob, keep = _lib.make_problem(ops, N, H, **mm)
         tune = _lib.make_tuning()
@@ -138,12 +141,17 @@ class FusedRolloutFunction(torch.autograd.Function):
         g_states, g_actions, g_rewards = cot(g_states), cot(g_actions), cot(g_rewards)
         grad_flat = torch.empty(ctx.nparam, device=states.device, dtype=torch.float32)
         dx0 = torch.empty_like(x0c)
+        da_total = None
+        if ctx.extras is not None and ctx.extras.get("want_action_grads"):
+            da_total = torch.empty_like(actions)
+            ctx.extras["action_grads"] = da_total
         _lib.check(lib.pmb_rollout_backward(
             C.byref(prob), C.byref(tune), states.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
             g_states.data_ptr() if g_states is not None else None,
             g_actions.data_ptr() if g_actions is not None else None,
             g_rewards.data_ptr() if g_rewards is not None else None,
-            grad_flat.data_ptr(), dx0.data_ptr(), ws.data_ptr(), nbytes, _lib.current_stream_ptr()))
+            grad_flat.data_ptr(), dx0.data_ptr(), da_total.data_ptr() if da_total is not None else None,
+            ws.data_ptr(), nbytes, _lib.current_stream_ptr()))
         grads, off = [], 0
         for shp in ctx.param_shapes:
             n = 1
@@ -155,7 +163,8 @@ class FusedRolloutFunction(torch.autograd.Function):
 
 
 def fused_rollout_tensors(states, dynamics, policy, steps, mm_states=False, mm_rewards=False, z_mm=None,
-                          z_rr=None, mm_groups=None, resample_state_noise=False, resample_action_noise=False):
+                          z_rr=None, mm_groups=None, resample_state_noise=False, resample_action_noise=False,
+                          extras=None):
     """Fused rollout returning stacked tensors (states [H+1,N,D], actions [H,N,U], rewards [H,N], status).
     Raises NotEligible for module graphs outside the fused scope."""
     if not (torch.is_tensor(states) and states.is_cuda):
@@ -197,7 +206,7 @@ def fused_rollout_tensors(states, dynamics, policy, steps, mm_states=False, mm_r
             dynamics.output_density.z.data = zd[-1]
     mm = dict(mm_states=mm_states, mm_rewards=mm_rewards, mm_groups=mm_groups, z_mm=z_mm, z_rr=z_rr)
     params = ops.policy_parameters()
-    return FusedRolloutFunction.apply(states, (ops, N, int(steps), mm), *params)
+    return FusedRolloutFunction.apply(states, (ops, N, int(steps), mm, extras), *params)
 
 
 _warned = set()

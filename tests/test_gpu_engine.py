@@ -93,3 +93,74 @@ def test_library_errors_are_not_swallowed_as_numerical_failures(monkeypatch):
     monkeypatch.setattr(sys.modules["prob_mbrl_b200.mc_pilco"], "fused_rollout_tensors", broken)
     with pytest.raises(_lib.LibraryError):
         pm.mc_pilco(g["x0"].cuda(), dyn, pol, int(g["H"]), opt, None, 2, pegasus=True, init_state_noise=0.0)
+
+
+def test_total_action_gradients_match_autograd_hooks(monkeypatch):
+    """pmb_rollout_backward(..., da_total): the TOTAL dL/da_t of every step -- what a hook on actions[t] sees in the
+    reference (algorithms/mc_pilco.py:160-188, prioritized replay) -- against hooks on the eager module loop (fp64)."""
+    import prob_mbrl_b200 as pm
+    from prob_mbrl_b200.rollout import fused_rollout_tensors
+    for name, mode in (("cartpole_37x2_n7_h12", "3"), ("cartpole_37x2_n7_h12", "2"), ("dcartpole_48x3_n24_h30", "2"),
+                       ("dcartpole_48x3_n24_h30", "4")):
+        monkeypatch.setenv("PMB_STREAM_MODE", mode)
+        ops, g = gu.load(name)
+        H = int(g["H"])
+        dyn, pol = gu.modules_from_ops(ops, "cuda")
+        extras = {"want_action_grads": True}
+        S, A, R, _ = fused_rollout_tensors(g["x0"].cuda(), dyn, pol, H, extras=extras)
+        (-(R.sum(0) / H).mean()).backward()
+        got = extras["action_grads"].cpu()
+        monkeypatch.setenv("PROB_MBRL_BACKEND", "eager")
+        dyn64, pol64 = gu.modules_from_ops(ops, "cpu")
+        dyn64, pol64 = dyn64.double(), pol64.double()
+        seen = {}
+        Sr, Ar, Rr = pm.rollout(g["x0"].double(), dyn64, pol64, H, resample_state_noise=False, resample_action_noise=False)
+        for t, a in enumerate(Ar):
+            a.register_hook(lambda gr, t=t: seen.__setitem__(t, gr.detach().clone()))
+        (-(torch.stack(Rr).sum(0) / H).mean()).backward()
+        want = torch.stack([seen[t] for t in range(H)])
+        monkeypatch.delenv("PROB_MBRL_BACKEND")
+        assert gu.rel_l2(got, want) < 2e-5, (name, mode)
+
+
+def test_prioritized_replay_runs_on_the_fused_rollout(monkeypatch):
+    """mc_pilco(prioritized_replay=True) on the GPU: same losses / parameters as the eager module loop on the CPU with
+    identical seeds (the sum tree lives on the host; priorities come from the fused reverse sweep's da_total)."""
+    import numpy as np
+    import prob_mbrl_b200 as pm
+    from prob_mbrl_b200.replay import SumTree
+
+    class Exp:
+        def __init__(self, eps):
+            self.states = eps
+
+        def n_samples(self):
+            return sum(len(e) for e in self.states)
+
+        def n_episodes(self):
+            return len(self.states)
+
+    monkeypatch.setenv("PMB_NO_PBAR", "1")
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    gen = torch.Generator().manual_seed(3)
+    episodes = [(0.1 * torch.randn(10, 5, generator=gen)).tolist() for _ in range(2)]
+    out = []
+    for dev, backend in (("cpu", "eager"), ("cuda", "fused")):
+        monkeypatch.setenv("PROB_MBRL_BACKEND", backend)
+        dyn, pol = gu.modules_from_ops(ops, dev)
+        dyn.resample = lambda *a, **k: None          # keep the fixture's noise on both devices
+        pol.resample = lambda *a, **k: None
+        opt = torch.optim.Adam(pol.parameters(), 1e-3)
+        mod = sys.modules["prob_mbrl_b200.mc_pilco"]
+        mod.x0_tree, mod.episode_counter = SumTree(32), 0
+        mod.policy_update_counter[pol] = 1
+        torch.manual_seed(2)
+        np.random.seed(2)
+        losses = []
+        pm.mc_pilco(g["x0"].to(dev), dyn, pol, int(g["H"]), opt, Exp(episodes), 4, pegasus=True, init_state_noise=0.0,
+                    prioritized_replay=True, on_iteration=lambda i, loss, *a: losses.append(float(loss)))
+        out.append((losses, torch.cat([p.detach().cpu().flatten() for p in pol.parameters()]), mod.x0_tree.sum_tree.copy()))
+    (la, pa, ta), (lb, pb, tb) = out
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-6
+    assert (pa - pb).abs().max() < 5e-6
+    assert np.allclose(ta, tb, rtol=2e-3, atol=1e-9)

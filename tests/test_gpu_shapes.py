@@ -177,3 +177,28 @@ def test_mc_pilco_generic_path_matches_eager_loop(variant, monkeypatch):
     assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-6
     assert (pa - pb).abs().max() < 5e-6
     assert (pa - torch.cat([ops[k].flatten() for k in orc.policy_param_keys(ops)])).abs().max() > 1e-4
+
+
+@pytest.mark.parametrize("mode", ["2", "3", "4"])
+@pytest.mark.parametrize("as_reward", [False, True])
+def test_quadratic_saturating_cost_is_fused(mode, as_reward, monkeypatch):
+    """north_star: "the quadratic/saturating cost in prob_mbrl.losses" -- a full D x D quadratic form on the state
+    (reference losses.py:67-75) as reward_func, evaluated inside every sweep variant; vs the fp64 oracle."""
+    from prob_mbrl_b200 import operands, rewards
+    monkeypatch.setenv("PMB_STREAM_MODE", mode)
+    ops, g = gu.load("cartpole_37x2_n7_h12")
+    dyn, pol = gu.modules_from_ops(ops, "cuda")
+    gen = torch.Generator().manual_seed(1)
+    A = torch.randn(5, 5, generator=gen)
+    dyn.reward_func = rewards.QuadraticSaturatingCost(torch.tensor([0.1, 0.0, 0.0, 0.2, -1.0]), A @ A.T + torch.eye(5),
+                                                      R=torch.tensor([[1e-2]]), reward=as_reward).cuda()
+    H = int(g["H"])
+    S, A_, R, grads, dx0, obj = _fused(dyn, pol, g["x0"], H)
+    flat = {k: (v.double().cpu() if torch.is_tensor(v) and v.is_floating_point() else v)
+            for k, v in operands.extract(dyn, pol, 7).to_flat().items()}
+    ref = orc.loss_and_grads(flat, g["x0"].double(), H)
+    keys = orc.policy_param_keys(flat)
+    assert (R.cpu().double() - torch.stack(ref["rewards"]).squeeze(-1)).abs().max() < 2e-6
+    assert abs(float(obj) - float(ref["loss"])) < 1e-6
+    assert gu.rel_l2([x.cpu() for x in grads], [ref["grads"][k] for k in keys]) < 2e-5
+    assert gu.rel_l2(dx0.cpu(), ref["dx0"]) < 2e-5

@@ -125,6 +125,77 @@ def test_mc_pilco_mirror_equals_reference_mc_pilco():
 
 
 @needs_reference
+def test_quadratic_saturating_cost_matches_reference_losses():
+    """rewards.quadratic_loss / quadratic_saturating_loss / QuadraticSaturatingCost against the reference's
+    losses.quadratic_loss / quadratic_saturating_loss (losses.py:67-75), and the (C, c0, Q, R, scale, offset) form the
+    fused kernel evaluates against the module's own forward."""
+    ref_shim.install()
+    import prob_mbrl as ref
+    from prob_mbrl_b200 import rewards
+    from oracle import rollout_oracle as orc
+    g = torch.Generator().manual_seed(4)
+    x, u = torch.randn(11, 5, generator=g), torch.randn(11, 1, generator=g)
+    A = torch.randn(5, 5, generator=g)
+    Q, t = A @ A.T + torch.eye(5), torch.randn(1, 5, generator=g)
+    assert torch.equal(rewards.quadratic_loss(x, t, Q), ref.losses.quadratic_loss(x, t, Q))
+    assert torch.equal(rewards.quadratic_saturating_loss(x, t, Q), ref.losses.quadratic_saturating_loss(x, t, Q))
+    cost = rewards.QuadraticSaturatingCost(t, Q)
+    assert torch.allclose(cost(x, u), ref.losses.quadratic_saturating_loss(x, t, Q), rtol=0, atol=1e-7)
+    for mod in (cost, rewards.QuadraticSaturatingCost(t, Q, R=torch.tensor([[0.05]]), reward=True)):
+        C, c0, Qk, R, scale, offset = mod.tip_quadratic_form()
+        flat = {"rew_C": C, "rew_c0": c0, "rew_Q": Qk, "rew_R": R, "rew_scale": scale, "rew_offset": offset, "D": 5, "U": 1}
+        assert torch.allclose(orc.reward(flat, x, u), mod(x, u), rtol=0, atol=2e-7)
+
+
+class _FakeExperience:
+    """The three members mc_pilco's prioritized-replay branch touches (reference mc_pilco.py:223-231)."""
+
+    def __init__(self, episodes):
+        self.states = episodes
+
+    def n_samples(self):
+        return sum(len(e) for e in self.states)
+
+    def n_episodes(self):
+        return len(self.states)
+
+
+@needs_reference
+def test_prioritized_replay_mirror_equals_reference():
+    """prioritized_replay=True: initial states drawn from the sum tree, importance weights on the returns, priorities
+    from the per-step norms of dL/da_t -- this package's mc_pilco + SumTree (eager backend) against the reference's
+    mc_pilco + utils.SumTree on identical torch / numpy seeds: same losses, same parameters, same tree."""
+    ref_shim.install()
+    import prob_mbrl as ref
+    import prob_mbrl_b200 as pm
+    from prob_mbrl_b200.replay import SumTree
+    import numpy as np
+    finals = []
+    for which, (models, algo, reward) in enumerate(((ref.models, ref.algorithms.mc_pilco, ref.envs.cartpole.env.CartpoleReward),
+                                                   (pm.models, pm.mc_pilco, pm.rewards.CartpoleReward))):
+        dyn, pol, g = _build(models, lambda: reward(pole_length=torch.tensor(0.5)), 5, 1, [16, 16], 10.0)
+        x0 = 0.1 * torch.randn(8, 5, generator=g)
+        episodes = [(0.1 * torch.randn(12, 5, generator=g)).tolist() for _ in range(3)]
+        opt = torch.optim.Adam(pol.parameters(), 1e-3)
+        mod = sys.modules["prob_mbrl.algorithms.mc_pilco" if which == 0 else "prob_mbrl_b200.mc_pilco"]
+        mod.x0_tree = (ref.utils.SumTree if which == 0 else SumTree)(64)
+        mod.episode_counter = 0
+        torch.manual_seed(5)
+        np.random.seed(5)
+        losses = []
+        algo(x0, dyn, pol, 6, opt, _FakeExperience(episodes), 5, pegasus=True, maximize=True, clip_grad=1.0,
+             resampling_period=3, init_state_noise=0.01, prioritized_replay=True, priority_alpha=0.6,
+             on_iteration=lambda i, loss, *a: losses.append(float(loss)))
+        finals.append(([p.detach().clone() for p in pol.parameters()], losses, mod.x0_tree))
+    (pa, la, ta), (pb, lb, tb) = finals
+    assert la == lb and len(la) == 5
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
+    assert ta.size == tb.size == 36 and np.array_equal(ta.counts, tb.counts)
+    assert np.allclose(ta.sum_tree, tb.sum_tree, rtol=0, atol=0) and ta.max_p == tb.max_p
+
+
+@needs_reference
 def test_install_rebinds_reference_call_sites():
     """install() patches utils.rollout / utils.core.rollout / algorithms.mc_pilco of the reference package,
     and the reference's own mc_pilco then runs through this package's rollout with identical results."""
