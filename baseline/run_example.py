@@ -1,7 +1,7 @@
 """Acceptance runner: execute one of the reference's own example scripts UNCHANGED
 (examples/deep_pilco_no_mm.py, examples/deep_pilco_mm.py) with prob_mbrl_b200.install() active, i.e. with
-`prob_mbrl.utils.rollout` / `prob_mbrl.algorithms.mc_pilco` re-bound to the fused sm_100a path while everything
-else (environments, apply_controller, train_regressor, the nn.Modules themselves) stays the reference's.
+`prob_mbrl.utils.rollout` / `prob_mbrl.algorithms.mc_pilco` / `prob_mbrl.utils.train_regressor` re-bound to the fused
+sm_100a paths while everything else (environments, apply_controller, the nn.Modules themselves) stays the reference's.
 
     python baseline/run_example.py deep_pilco_no_mm.py --use_cuda --ps_iters 2 --pol_opt_iters 20 ...
 
@@ -33,7 +33,15 @@ def main():
     else:
         raise SystemExit("example %s not found (run baseline/install_reference.sh)" % sys.argv[1])
     pm.install(ref)
-    stats = {"script": os.path.basename(script), "engine_steps": 0, "mc_pilco_calls": 0, "plans": [], "losses": []}
+    stats = {"script": os.path.basename(script), "engine_steps": 0, "mc_pilco_calls": 0, "fit_steps": 0, "plans": [],
+             "losses": []}
+    real_fit_step = pm.FusedFit.step
+
+    def counting_fit_step(self, idx, noise=None):
+        stats["fit_steps"] += 1
+        return real_fit_step(self, idx, noise)
+
+    pm.FusedFit.step = counting_fit_step
     real_step = pm.FusedIteration.step
 
     def counting_step(self, x0):

@@ -188,6 +188,39 @@ int pmb_clip_adam_step(const pmb_adam_tensor *table_dev, int n_tensors, float ma
                        float lr, float beta1, float beta2, float eps, long long step,
                        long long *step_dev, float *scratch_dev, const int *skip_if_nonzero, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dynamics-model fit: one minibatch iteration of utils.train_regressor
+ * (reference utils/train_regressor.py:58-165, default branch) for a Regressor = (Linear, ReLU, CDropout) x L,
+ * Linear + DiagGaussianDensity (models/core.py:121-187, models/modules.py:73-171, models/densities.py:87-144).
+ * The uniform noise and the hard Bernoulli samples of the concrete-dropout layers are inputs, drawn by the host in
+ * the reference's order (modules.py:102-118,135-139) so that the RNG stream is the reference's.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pmb_fit_problem {
+    int N;                                   /* rows of the whitened dataset */
+    int M;                                   /* minibatch rows */
+    pmb_net net;                             /* dims / W / b / max_log_std; mask, keep, z are unused */
+    const float *logit_p[PMB_MAX_LINEAR];    /* [h_l] CDropout.logit_p of hidden layer l */
+    const float *u[PMB_MAX_LINEAR];          /* [M][h_l] uniform noise (torch.rand_like, modules.py:137) */
+    const float *hard[PMB_MAX_LINEAR];       /* [M][h_l] Bernoulli(probs) sample (modules.py:115) */
+    float temp[PMB_MAX_LINEAR];              /* CDropout.temp */
+    float reg_scale[PMB_MAX_LINEAR];         /* CDropout.regularizer_scale (modules.py:21-22) */
+    float drop_reg[PMB_MAX_LINEAR];          /* CDropout.dropout_regularizer */
+    float reg_weight;                        /* train_regressor(reg_weight=) */
+    const float *Xw, *Yw;                    /* whitened dataset [N][dims[0]], [N][dims[last] / 2] (train_regressor.py:75-76) */
+    float *mask_out[PMB_MAX_LINEAR];         /* optional [M][h_l]: this iteration's concrete masks (CDropout.concrete_noise) */
+    float *p_out[PMB_MAX_LINEAR];            /* optional [h_l]: sigmoid(logit_p) as the forward pass saw it (CDropout.p, modules.py:118) */
+} pmb_fit_problem;
+
+size_t pmb_fit_workspace_bytes(const pmb_fit_problem *p);
+/* floats of the flat gradient, model.parameters() order: fc0.weight, fc0.bias, drop0.logit_p, fc1.weight, ... */
+size_t pmb_fit_param_count(const pmb_fit_problem *p);
+const char *pmb_fit_last_error(void);
+/* Gradient of  loss = -mean_b log N(y_b | mean_b, std_b) + reg_weight * regularization_loss() / N  (train_regressor.py:
+ * 122-131) w.r.t. every trainable tensor for the minibatch rows idx_dev[0..M) (int64), and the mean log-likelihood of
+ * the minibatch (the progress-bar value, :143).  Follow with pmb_clip_adam_step(max_norm = 0) for optimizer.step(). */
+int pmb_fit_gradient(const pmb_fit_problem *p, const long long *idx_dev, float *grad_flat, float *loglik_dev,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from . import models, operands, rewards  # noqa: F401
 from .mc_pilco import FusedIteration, mc_pilco  # noqa: F401
 from .operands import NotEligible  # noqa: F401
 from .rollout import fused_rollout_tensors, rollout  # noqa: F401
+from .train_regressor import FusedFit, train_regressor  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -25,8 +26,10 @@ def install(reference_package=None):
     if reference_package is None:
         import prob_mbrl as reference_package
     ref = reference_package
-    saved = {"rollout": ref.utils.rollout, "mc_pilco": ref.algorithms.mc_pilco}
+    saved = {"rollout": ref.utils.rollout, "mc_pilco": ref.algorithms.mc_pilco,
+             "train_regressor": ref.utils.train_regressor}
     ref.utils.rollout = rollout
+    ref.utils.train_regressor = train_regressor      # examples call utils.train_regressor(...) (deep_pilco_no_mm.py:216)
     core = sys.modules.get(ref.__name__ + ".utils.core")
     if core is not None and hasattr(core, "rollout"):
         core.rollout = rollout
@@ -44,3 +47,5 @@ def uninstall(saved, reference_package=None):
     if core is not None and hasattr(core, "rollout"):
         core.rollout = saved["rollout"]
     ref.algorithms.mc_pilco = saved["mc_pilco"]
+    if "train_regressor" in saved:
+        ref.utils.train_regressor = saved["train_regressor"]

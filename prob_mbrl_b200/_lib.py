@@ -64,6 +64,19 @@ class PmbAdamTensor(C.Structure):
                 ("exp_avg_sq", C.c_void_p), ("n", C.c_longlong)]
 
 
+class PmbFitProblem(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("M", C.c_int),
+        ("net", PmbNet),
+        ("logit_p", C.c_void_p * PMB_MAX_LINEAR), ("u", C.c_void_p * PMB_MAX_LINEAR), ("hard", C.c_void_p * PMB_MAX_LINEAR),
+        ("temp", C.c_float * PMB_MAX_LINEAR), ("reg_scale", C.c_float * PMB_MAX_LINEAR), ("drop_reg", C.c_float * PMB_MAX_LINEAR),
+        ("reg_weight", C.c_float),
+        ("Xw", C.c_void_p), ("Yw", C.c_void_p),
+        ("mask_out", C.c_void_p * PMB_MAX_LINEAR),
+        ("p_out", C.c_void_p * PMB_MAX_LINEAR),
+    ]
+
+
 class PmbPlanInfo(C.Structure):
     _fields_ = [("variant", C.c_int), ("ctas", C.c_int), ("threads_per_cta", C.c_int), ("cluster_size", C.c_int),
                 ("particles_per_group", C.c_int), ("smem_fwd_bytes", C.c_int), ("smem_bwd_bytes", C.c_int),
@@ -72,7 +85,8 @@ class PmbPlanInfo(C.Structure):
 
 EXPORTS = ("pmb_abi_version", "pmb_last_error", "pmb_check_problem", "pmb_workspace_bytes", "pmb_policy_param_count",
            "pmb_plan_describe",
-           "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step")
+           "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step",
+           "pmb_fit_workspace_bytes", "pmb_fit_param_count", "pmb_fit_last_error", "pmb_fit_gradient")
 
 _lib = None
 
@@ -123,6 +137,14 @@ def load():
     lib.pmb_clip_adam_step.restype = C.c_int
     lib.pmb_clip_adam_step.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pmb_fit_workspace_bytes.restype = C.c_size_t
+    lib.pmb_fit_workspace_bytes.argtypes = [C.POINTER(PmbFitProblem)]
+    lib.pmb_fit_param_count.restype = C.c_size_t
+    lib.pmb_fit_param_count.argtypes = [C.POINTER(PmbFitProblem)]
+    lib.pmb_fit_last_error.restype = C.c_char_p
+    lib.pmb_fit_gradient.restype = C.c_int
+    lib.pmb_fit_gradient.argtypes = [C.POINTER(PmbFitProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]
     if lib.pmb_abi_version() != ABI_VERSION:
         raise LibraryMissing("ABI version mismatch: library %d, binding %d" % (lib.pmb_abi_version(), ABI_VERSION))
     _lib = lib

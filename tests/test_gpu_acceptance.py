@@ -86,6 +86,7 @@ def test_reference_example_runs_unchanged_on_the_fused_backend(script, tmp_path)
     st = json.loads(line[len("ACCEPTANCE "):])
     assert st["cuda"] and st["backend"] == "fused"
     assert st["mc_pilco_calls"] == 2 and st["engine_steps"] == 40        # every iteration on the device engine
+    assert st["fit_steps"] == 2 * 51                                     # ... and every dynamics-fit iteration (iters + 1)
     assert st["plans"] and all("N=100 H=15" in p for p in st["plans"])
     assert all(np.isfinite(v) for v in st["losses"])
     assert "Traceback" not in out.stderr

@@ -147,6 +147,34 @@ def test_quadratic_saturating_cost_matches_reference_losses():
         assert torch.allclose(orc.reward(flat, x, u), mod(x, u), rtol=0, atol=2e-7)
 
 
+@needs_reference
+def test_train_regressor_mirror_equals_reference():
+    """utils.train_regressor: this package's module loop (eager backend) on the mirror modules == the reference's on
+    its own, parameter for parameter, on identical numpy / torch seeds (reference utils/train_regressor.py:58-165)."""
+    ref_shim.install()
+    import prob_mbrl as ref
+    import prob_mbrl_b200 as pm
+    import numpy as np
+    import tqdm
+    from functools import partial
+    finals = []
+    for models, fit in ((ref.models, ref.utils.train_regressor), (pm.models, pm.train_regressor)):
+        torch.manual_seed(11)
+        np.random.seed(11)
+        CD = models.modules.CDropout if hasattr(models, "modules") else models.CDropout
+        net = models.mlp(6, 10, [24, 20], dropout_layers=[CD(0.1 * np.ones(h)) for h in (24, 20)], nonlin=torch.nn.ReLU)
+        dyn = models.DynamicsModel(net, reward_func=None, output_density=models.DiagGaussianDensity(5)).float()
+        g = torch.Generator().manual_seed(5)
+        X = torch.randn(70, 6, generator=g)
+        Y = 0.1 * torch.randn(70, 5, generator=g)
+        dyn.set_dataset(X, Y)
+        opt = torch.optim.Adam(dyn.parameters(), 1e-3)
+        fit(dyn, 7, 32, True, opt, log_likelihood=dyn.output_density.log_prob, pbar_class=partial(tqdm.tqdm, disable=True))
+        finals.append([p.detach().clone() for p in dyn.parameters()])
+    for a, b in zip(*finals):
+        assert (a - b).abs().max() < 2e-7           # same draws, same minibatches; the regulariser sums in another order
+
+
 class _FakeExperience:
     """The three members mc_pilco's prioritized-replay branch touches (reference mc_pilco.py:223-231)."""
 
