@@ -14,7 +14,7 @@ n = bench.CONFIGS[cfg][5]
 dyn, pol, x0, H, mm = bench.build_workload(cfg, n, "cuda")
 opt = torch.optim.Adam(pol.parameters(), 1e-4)
 g_r = torch.full((H, n), -1.0 / (H * n), device="cuda")
-eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0)
+eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0, mm)
 for _ in range(iters):
     eng.step(x0.cuda())
 torch.cuda.synchronize()
