@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PMB_ABI_VERSION 3
+#define PMB_ABI_VERSION 4
 #define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
 #define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
 #define PMB_MAX_REWARD_ROWS 16 /* rows of the distance map C (2 for the env tip rewards, D for losses.quadratic_*) */
@@ -82,6 +82,10 @@ typedef struct pmb_problem {
     const float *z_mm;            /* [>= N][D]  rows 0..N-1 are used, rotated by the step index (rollout.py:53-59) */
     const float *z_rr;            /* [>= N][1] */
     int n_global;                 /* reserved for sharded moment matching; set to N */
+    int masks_binary;             /* 1 = every dropout mask value is exactly 0 or 1 (true for BDropout noise and for
+                                     CDropout's concrete_noise = (b - probs).detach() + probs, which rounds to b exactly
+                                     in fp32; reference models/modules.py:61,113-116).  Lets the planner keep the masks
+                                     as bit words (wide cluster-resident sweeps); 0 = unknown (those sweeps are not used) */
 } pmb_problem;
 
 /* Tunables (0 = library default). */
@@ -94,7 +98,10 @@ typedef struct pmb_tuning {
                                 thread-block cluster; PMB_E_UNSUPPORTED when the problem is outside them),
                                 4 = tensor-core cluster sweeps required (tcgen05 3xTF32 hidden x hidden layers,
                                 16-CTA cluster per 128-particle tile; PMB_E_UNSUPPORTED when outside them; opt-in:
-                                measured slower than the FFMA2 variants at every BASELINE shape) */
+                                measured slower than the FFMA2 variants at every BASELINE shape),
+                                5 = wide cluster-resident sweeps required (two-hidden-layer nets up to 512 wide in the
+                                shared memory of a 16-CTA cluster, up to 36 particles per cluster; needs
+                                pmb_problem.masks_binary; auto picks them when the nets are too wide for 3) */
     int wgrad_splits;        /* split-K slices of the batched policy weight gradient */
     int reserved[5];         /* reserved[0]: profiling aid, bit mask of phases to run (1 pack, 2 sweep,
                                 4 weight gradient); 0 = all.  reserved[1]: ring stages (2..4), 0 = default; with
@@ -121,7 +128,7 @@ size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune);
  * and with which geometry.  Used by hosts for reporting (bench.py's roofline) and by the tests. */
 typedef struct pmb_plan_info {
     int variant;             /* 0 = streaming sweeps (TMA weight ring), 1 = cluster-resident FFMA2 sweeps,
-                                2 = tensor-core cluster sweeps */
+                                2 = tensor-core cluster sweeps, 3 = wide cluster-resident FFMA2 sweeps (16-CTA cluster) */
     int ctas;                /* CTAs of one sweep launch */
     int threads_per_cta;
     int cluster_size;        /* CTAs per thread-block cluster (1 for the streaming sweeps) */

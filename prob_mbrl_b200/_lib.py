@@ -17,7 +17,7 @@ PMB_MAX_LINEAR = 6
 PMB_MAX_WIDTH = 1024
 PMB_MAX_STATE = 16
 PMB_MAX_REWARD_ROWS = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _fp = C.POINTER(C.c_float)
 
@@ -49,6 +49,7 @@ class PmbProblem(C.Structure):
         ("mm_states", C.c_int), ("mm_rewards", C.c_int), ("mm_groups", C.c_int),
         ("z_mm", C.c_void_p), ("z_rr", C.c_void_p),
         ("n_global", C.c_int),
+        ("masks_binary", C.c_int),
     ]
 
 
@@ -256,6 +257,7 @@ def make_problem(ops: RolloutOperands, N, H, mm_states=False, mm_rewards=False, 
         keep.append(z)
         p.z_rr = z.data_ptr()
     p.n_global = int(N)
+    p.masks_binary = int(bool(ops.pol.masks_binary and ops.dyn.masks_binary))
     return p, keep
 
 
@@ -266,7 +268,7 @@ def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t.reserved[4] = int(os.environ.get("PMB_WGRAD_UMMA", "0"))
     t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))
     # 0 = auto, 1/2 = streaming sweeps, 3 = cluster-resident FFMA2 sweeps (required), 4 = tensor-core cluster
-    # sweeps (required)
+    # sweeps (required), 5 = wide cluster-resident FFMA2 sweeps (required)
     t.stream_mode = int(stream_mode or int(os.environ.get("PMB_STREAM_MODE", "0")))
     if t.stream_mode == 3:
         # particles per cluster (1..8, 0 = auto) and CTAs per cluster (4 or 8, 0 = 8)

@@ -10,6 +10,7 @@
 #include "pmb_internal.cuh"
 #include "pmb_mm.cuh"
 #include "pmb_cluster.cuh"
+#include "pmb_cw.cuh"
 #include "pmb_tc.cuh"
 #include "pmb_tc_mm.cuh"
 
@@ -65,6 +66,11 @@ struct Plan {
     PackJobs sjobs;           // the workspace-resident small operands only (padded biases, masks)
     long long tc_wpack_off, tc_xbuf_off, tc_opart_off;
     ClusterParams tpre;       // arguments of the adjoint-factor pre-pass (cluster_bwd_pre_kernel)
+    // wide cluster-resident sweeps (pmb_cw.cuh): 16-CTA clusters, two-hidden-layer nets up to 512 wide
+    int cw;                   // 0 = off
+    int cw_nclusters;
+    long long cw_g1_off, cw_g2_off;
+    ClusterParams wfwd, wbwd;
 };
 
 struct Alloc {
@@ -423,6 +429,96 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Wide cluster-resident sweeps (pmb_cw.cuh).  Eligible: two hidden layers per net, hidden widths <= 512, D+U <= 16,
+// outputs <= 16, binary dropout masks (pmb_problem.masks_binary), no moment matching of the states.
+// ---------------------------------------------------------------------------------------------
+static bool cw_eligible(const pmb_problem *p) {
+    if (p->mm_states || !p->masks_binary) return false;
+    const pmb_net *nets[2] = {&p->pol, &p->dyn};
+    for (int i = 0; i < 2; ++i) {
+        const pmb_net &n = *nets[i];
+        if (n.n_linear != 3) return false;
+        if (round4(n.dims[1]) > CW_TW || round4(n.dims[2]) > CW_TW) return false;
+        if (n.dims[0] > CW_NO || n.dims[3] > CW_NO) return false;
+    }
+    return true;
+}
+
+static int cw_carve(ClusterParams &P, bool reverse) {
+    int off = 0;
+    auto take = [&](int nfl) { int o = off; off += (nfl + 31) & ~31; return o; };
+    P.off_cst = reverse ? 0 : take(C_TOTAL);
+    CNet *nets[2] = {&P.pol, &P.dyn};
+    int tw_max = 4;
+    for (int i = 0; i < 2; ++i) {
+        CNet &n = *nets[i];
+        n.s_ww = take(n.tW * CW_HS);
+        n.s_nwt = take(CW_NO * CW_HS);
+        n.s_wb = take(CW_HS);
+        n.s_nb = take(CW_NO);
+        tw_max = max(tw_max, n.tW);
+    }
+    P.off_xa = take(CW_XT);
+    P.off_xb = take(CW_XT);
+    P.off_act = take(max(tw_max, CW_NW * 32) * CW_PS);    // hidden tile [tW][36]; partial sums [16][36][32]
+    P.off_inbox = take(2 * CW_MB);
+    P.off_misc = take(reverse ? 2 * CW_G2 : 32);
+    P.smem_floats = off;
+    return off;
+}
+
+// fills pl.cw / pl.wfwd / pl.wbwd from the streaming plan's layer tables (same workspace layout + the gate words)
+static int plan_cw(const pmb_problem *p, const pmb_tuning *tune, Plan &pl, Alloc &ws) {
+    pl.cw = 0;
+    const int mode = tune ? tune->stream_mode : 0;
+    if (mode != 0 && mode != 5) return PMB_OK;
+    if (mode == 0 && cluster_eligible(p, 8)) return PMB_OK;      // narrower nets: the 8-CTA latency-oriented sweeps
+    if (!cw_eligible(p)) {
+        if (mode == 5) return fail(PMB_E_UNSUPPORTED, "problem is outside the wide cluster-resident sweeps%s",
+                                   p->masks_binary ? "" : " (masks_binary is not set)");
+        return PMB_OK;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const SweepParams &S = pass ? pl.bwd : pl.fwd;
+        ClusterParams &P = pass ? pl.wbwd : pl.wfwd;
+        memset(&P, 0, sizeof(P));
+        P.N = p->N; P.H = p->H; P.D = p->D; P.U = p->U; P.C = CW_C;
+        cluster_net(S.pol, pass == 1, true, CW_C, P.pol);
+        cluster_net(S.dyn, pass == 1, false, CW_C, P.dyn);
+        P.act_scale = p->act_scale; P.act_bias = p->act_bias; P.mx = p->mx; P.iSx = p->iSx; P.my = p->my; P.Sy = p->Sy;
+        P.KR = p->rew_rows; P.rew_C = p->rew_C; P.rew_c0 = p->rew_c0; P.rew_Q = p->rew_Q; P.rew_R = p->rew_R;
+        P.rew_scale = p->rew_scale; P.rew_offset = p->rew_offset;
+        if (P.pol.hs > CW_HS || P.dyn.hs > CW_HS || cw_carve(P, pass == 1) > SMEM_LIMIT_FLOATS) {
+            if (mode == 5) return fail(PMB_E_UNSUPPORTED, "wide cluster-resident plan does not fit in shared memory");
+            return PMB_OK;
+        }
+    }
+    // particles per cluster: spread the particles over every cluster the device can hold at once
+    int PG = (tune && mode == 5) ? tune->reserved[1] & 63 : 0;
+    if (PG < 0 || PG > CW_PS) return fail(PMB_E_INVALID, "particles per cluster must be 1..%d", CW_PS);
+    if (PG == 0) {
+        static int cached[32];
+        static bool cached_init = false;
+        if (!cached_init) { for (auto &c : cached) c = -1; cached_init = true; }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+        int &mc = cached[dev];
+        if (mc < 0) mc = cw_max_active();
+        const int maxc = mc > 0 ? mc : 7;
+        PG = (p->N + maxc - 1) / maxc;
+        if (PG > CW_PS) PG = CW_PS;
+        if (PG < 1) PG = 1;
+    }
+    pl.wfwd.PG = pl.wbwd.PG = PG;
+    pl.cw_nclusters = (p->N + PG - 1) / PG;
+    pl.wfwd.ncl = pl.wbwd.ncl = pl.cw_nclusters;
+    pl.cw_g1_off = ws.take((long long)p->H * pl.cw_nclusters * 2 * 2 * CW_TW);
+    pl.cw_g2_off = ws.take((long long)p->H * p->N * 2 * CW_C);
+    pl.cw = CW_C;
+    return PMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tensor-core cluster sweeps: eligibility, operand tables, shared-memory carve-up, workspace (pmb_tc.cuh).
 // Eligible: >= 1 hidden layer per net, hidden widths <= 1024, <= 32 raw outputs, D+U <= 16; with moment matching
 // of the states the whole particle set must fit one tile (N <= 128, <= 16 groups).
@@ -634,7 +730,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     pl.P = P;
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
-    if (pl.stream_mode < 1 || pl.stream_mode > 4) return fail(PMB_E_INVALID, "stream_mode must be 0..4");
+    if (pl.stream_mode < 1 || pl.stream_mode > 5) return fail(PMB_E_INVALID, "stream_mode must be 0..5");
     if (pl.stream_mode >= 3) pl.stream_mode = 2;
     pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : 64;
     if (pl.nsplit < 1 || pl.nsplit > 1024) return fail(PMB_E_INVALID, "wgrad_splits outside [1,1024]");
@@ -679,7 +775,9 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.geff_off = ws.take(HN);
     }
     if ((rc = plan_tc(p, tune, pl, ws)) != PMB_OK) return rc;
-    pl.ws_floats = ws.top;
+    const long long ws_before_cw = ws.top;
+    (void)ws_before_cw;
+    pl.cw = 0;
 
     for (int pass = 0; pass < 2; ++pass) {
         SweepParams &S = pass ? B : F;
@@ -693,7 +791,11 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     }
     const NetSweep *fo[2] = {&F.pol, &F.dyn};
     const NetSweep *bo[2] = {&B.dyn, &B.pol};
+    pl.ws_floats = ws.top;
     if (pl.tc) return PMB_OK;
+    if ((rc = plan_cw(p, tune, pl, ws)) != PMB_OK) return rc;
+    pl.ws_floats = ws.top;
+    if (pl.cw) { pl.cluster = 0; return PMB_OK; }
     if ((rc = plan_cluster(p, tune, pl)) != PMB_OK) return rc;
     if (pl.cluster) return PMB_OK;
     const int nst = tune ? tune->reserved[1] : 0;
@@ -733,6 +835,16 @@ static void resolve(Plan &pl, float *ws) {
         pl.tpre.s1pre = pl.tfwd.mm_states ? ws + pl.s1pre_off : nullptr;
         for (int i = 0, k = 0; i < pl.jobs.n; ++i)
             if ((pl.job_dst_off[i] >> 60) == 2) pl.sjobs.job[k++].dst = ws + (pl.job_dst_off[i] & ((1LL << 60) - 1));
+    }
+    if (pl.cw) {
+        for (int pass = 0; pass < 2; ++pass) {
+            ClusterParams &W = pass ? pl.wbwd : pl.wfwd;
+            W.ws = ws;
+            W.wpack = ws + (pass ? pl.wpack_bwd_off : pl.wpack_fwd_off);
+            W.pre = ws + pl.cl_pre_off;
+            W.g1 = reinterpret_cast<unsigned *>(ws + pl.cw_g1_off);
+            W.g2 = reinterpret_cast<unsigned *>(ws + pl.cw_g2_off);
+        }
     }
     pl.cfwd.ws = pl.cbwd.ws = ws;
     pl.cbwd.pre = ws + pl.cl_pre_off;
@@ -790,6 +902,14 @@ int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_inf
         info->particles_per_group = pl.tfwd.TP;
         info->smem_fwd_bytes = pl.tfwd.smem_floats * 4;
         info->smem_bwd_bytes = pl.tbwd.smem_floats * 4;
+    } else if (pl.cw) {
+        info->variant = 3;
+        info->ctas = pl.cw_nclusters * pl.cw;
+        info->threads_per_cta = CW_NT;
+        info->cluster_size = pl.cw;
+        info->particles_per_group = pl.wfwd.PG;
+        info->smem_fwd_bytes = pl.wfwd.smem_floats * 4;
+        info->smem_bwd_bytes = pl.wbwd.smem_floats * 4;
     } else if (pl.cluster) {
         info->variant = 1;
         info->ctas = pl.cl_nclusters * pl.cluster;
@@ -810,7 +930,7 @@ int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_inf
     // pack + sweep (+ reward matching); [reward matching adjoint] + [adjoint-factor pre-pass] + sweep +
     // one weight-gradient kernel per policy layer + partial reduction
     info->launches_fwd = 2 + (pl.tc ? 1 : 0) + (p->mm_rewards ? 1 : 0);
-    info->launches_bwd = (p->mm_rewards ? 1 : 0) + ((pl.cluster || pl.tc) ? 1 : 0) + 1 + pl.n_wg + 1;
+    info->launches_bwd = (p->mm_rewards ? 1 : 0) + ((pl.cluster || pl.tc || pl.cw) ? 1 : 0) + 1 + pl.n_wg + 1;
     return PMB_OK;
 }
 
@@ -856,6 +976,10 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
         TcParams &T = pl.tfwd;
         T.x0 = x0; T.states = states; T.actions = actions; T.rewards = F.rewards; T.status = status_dev; T.dbg = F.dbg;
         if (phases & 2) PMB_CUDA(launch_tc_fwd(T, st));
+    } else if (pl.cw) {
+        ClusterParams &CF = pl.wfwd;
+        CF.x0 = x0; CF.states = states; CF.actions = actions; CF.rewards = F.rewards; CF.dbg = F.dbg;
+        if (phases & 2) PMB_CUDA(launch_cw_fwd(CF, pl.cw_nclusters, st));
     } else if (pl.cluster) {
         ClusterParams &CF = pl.cfwd;
         CF.x0 = x0; CF.states = states; CF.actions = actions; CF.rewards = F.rewards; CF.dbg = F.dbg;
@@ -910,6 +1034,15 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
         if (phases & 2) {
             PMB_CUDA(launch_bwd_pre(P, st));
             PMB_CUDA(launch_tc_bwd(T, st));
+        }
+    } else if (pl.cw) {
+        ClusterParams &CB = pl.wbwd;
+        CB.states = B.states; CB.actions = B.actions; CB.rewards = B.rewards;
+        CB.g_states = B.g_states; CB.g_actions = B.g_actions; CB.g_rewards = B.g_rewards; CB.dx0 = B.dx0; CB.dbg = B.dbg;
+        CB.da_total = da_total;
+        if (phases & 2) {
+            PMB_CUDA(launch_bwd_pre(CB, st));
+            PMB_CUDA(launch_cw_bwd(CB, pl.cw_nclusters, st));
         }
     } else if (pl.cluster) {
         ClusterParams &CB = pl.cbwd;

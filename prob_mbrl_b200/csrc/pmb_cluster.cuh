@@ -72,6 +72,8 @@ struct ClusterParams {
     float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
     const float *s1pre;         // next states BEFORE moment matching [H][N][D] (the reward acts on them), nullptr = states[t+1]
     long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)
+    unsigned *g1, *g2;          // wide cluster-resident sweeps (pmb_cw.cuh): ReLU/dropout gate bit words of hidden 0 / 1
+    int ncl;                    // ... clusters of the launch
     int off_cst, off_xa, off_xb, off_act, off_red, off_inbox, off_misc;
     int smem_floats;
 };

@@ -44,6 +44,9 @@ class NetOperands:
     has_density: bool = True
     z: Optional[torch.Tensor] = None     # [N, out_dims] (constant over steps) or [H, N, out_dims]
     lmax: float = 0.0
+    # every mask value is exactly 0 or 1: true for BDropout.noise (Bernoulli draws) and for CDropout.concrete_noise,
+    # whose (b - probs) + probs rounds to b exactly in fp32 (reference models/modules.py:61,113-116)
+    masks_binary: bool = False
 
     @property
     def hidden(self):
@@ -114,7 +117,8 @@ class RolloutOperands:
             p = [float(d["%s_p%d" % (tag, i)]) for i in range(L)]
             nets[tag] = NetOperands(W, b, mask, p, bool(int(d[tag + "_has_density"])),
                                     t(d[tag + "_z"]) if (tag + "_z") in d else None,
-                                    float(d[tag + "_lmax"]))
+                                    float(d[tag + "_lmax"]),
+                                    masks_binary=all(bool(((m == 0) | (m == 1)).all()) for m in mask if m is not None))
         rew = RewardOperands(t(d["rew_C"]), t(d["rew_c0"]), t(d["rew_Q"]), t(d["rew_R"]),
                              float(d["rew_scale"]), float(d["rew_offset"]))
         return RolloutOperands(int(d["D"]), int(d["U"]), nets["pol"], nets["dyn"],
@@ -216,7 +220,7 @@ def read_net(seq, n_rows, what):
         raise NotEligible("%s: empty network" % what)
     if len(mask) != len(W) - 1:
         raise NotEligible("%s: output projection must not be followed by an activation" % what)
-    net = NetOperands(W, b, mask, p, has_density=density is not None)
+    net = NetOperands(W, b, mask, p, has_density=density is not None, masks_binary=True)
     return net, density
 
 

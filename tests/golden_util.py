@@ -117,3 +117,21 @@ def synthetic_ops(D=3, U=2, hid=(24, 20), N=9, seed=5, dtype=torch.float32, pol_
     ops["rew_offset"] = 0.0
     x0 = 0.3 * r(N, D)
     return {k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in ops.items()}, x0.to(dtype)
+
+
+def min_abs_preactivation(d, x0, H, per_particle=False):
+    """Smallest |ReLU input| over all unmasked hidden units, particles and steps of the (fp64) oracle rollout.  A value
+    near the fp32 rounding error of the layer sum means the ReLU gate of that unit depends on the summation order:
+    two correct fp32 implementations may then differ by O(1/width) in the gradients of that particle."""
+    from oracle import rollout_oracle as orc
+    S, A, _, _ = orc.forward_with_saved(d, x0, H)
+    best = torch.full((x0.shape[0],), float("inf"), dtype=torch.float64)
+    for t in range(H):
+        for tag, x in (("pol", S[t]), ("dyn", (torch.cat([S[t], A[t]], -1) - d["mx"]) * d["iSx"])):
+            h = x
+            for l in range(int(d[tag + "_L"])):
+                pre = h @ d["%s_W%d" % (tag, l)].T + d["%s_b%d" % (tag, l)]
+                m = d["%s_mask%d" % (tag, l)]
+                best = torch.minimum(best, (pre.abs() + (m == 0) * 1e9).min(1).values.double())
+                h = torch.relu(pre) * m / d["%s_p%d" % (tag, l)]
+    return best if per_particle else float(best.min())

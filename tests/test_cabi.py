@@ -48,9 +48,9 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(pmb_net), sizeof(pmb_problem), sizeof(pmb_tuning), sizeof(pmb_adam_tensor));
   printf("%zu %zu %zu %zu %zu\n", offsetof(pmb_net, W), offsetof(pmb_net, keep), offsetof(pmb_net, z),
          offsetof(pmb_net, z_step_stride), offsetof(pmb_net, max_log_std));
-  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(pmb_problem, pol), offsetof(pmb_problem, dyn),
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(pmb_problem, pol), offsetof(pmb_problem, dyn),
          offsetof(pmb_problem, act_scale), offsetof(pmb_problem, rew_rows), offsetof(pmb_problem, z_mm),
-         offsetof(pmb_problem, n_global));
+         offsetof(pmb_problem, n_global), offsetof(pmb_problem, masks_binary));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -66,10 +66,10 @@ int main(void) {
     assert net == [getattr(_lib.PmbNet, f).offset for f in ("W", "keep", "z", "z_step_stride", "max_log_std")]
     prob = [int(x) for x in out[2].split()]
     assert prob == [getattr(_lib.PmbProblem, f).offset for f in ("pol", "dyn", "act_scale", "rew_rows", "z_mm",
-                                                                 "n_global")]
+                                                                 "n_global", "masks_binary")]
 
 
-def _fake_problem(N=100, H=400, D=5, U=1, hid=(200, 200), mm=False, groups=0):
+def _fake_problem(N=100, H=400, D=5, U=1, hid=(200, 200), mm=False, groups=0, binary=False):
     """Descriptor with non-NULL fake pointers: enough for the host-side planner (never dereferenced)."""
     from prob_mbrl_b200 import _lib
     p = _lib.PmbProblem()
@@ -89,6 +89,7 @@ def _fake_problem(N=100, H=400, D=5, U=1, hid=(200, 200), mm=False, groups=0):
     for f in ("act_scale", "act_bias", "mx", "iSx", "my", "Sy", "rew_C", "rew_c0", "rew_Q", "rew_R"):
         setattr(p, f, 0x1000)
     p.rew_rows, p.rew_scale, p.n_global = 2, 1.0, N
+    p.masks_binary = int(binary)
     if mm:
         p.mm_states = p.mm_rewards = 1
         p.mm_groups = groups
@@ -149,6 +150,22 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     # ragged particle counts: the last cluster is partly filled
     small = _lib.describe_plan(_fake_problem(N=7, H=12, hid=(37, 37)), auto)
     assert small["variant"] == 1 and small["ctas"] // 8 * small["particles_per_group"] >= 7
+    # two hidden layers wider than 256 (c5) with masks declared binary: the wide cluster-resident sweeps (16-CTA
+    # cluster, <= 36 particles per cluster; 7 clusters are co-resident on a B200); narrower nets stay on the 8-CTA
+    # sweeps, three hidden layers / moment matching / undeclared masks on the streaming sweeps
+    c5 = _lib.describe_plan(_fake_problem(N=250, H=1000, hid=(512, 512), binary=True), auto)
+    assert c5["variant"] == 3 and c5["cluster_size"] == 16 and c5["threads_per_cta"] == 512
+    assert c5["particles_per_group"] == 36 and c5["ctas"] == 7 * 16
+    assert c5["smem_fwd_bytes"] <= 232448 - 1024 and c5["smem_bwd_bytes"] <= 232448 - 1024
+    assert c5["launches_fwd"] == 2 and c5["launches_bwd"] == 1 + 1 + 3 + 1
+    assert _lib.describe_plan(_fake_problem(binary=True), auto)["variant"] == 1
+    assert _lib.describe_plan(_fake_problem(N=125, H=600, D=8, hid=(400, 400, 400), binary=True), auto)["variant"] == 0
+    assert _lib.describe_plan(_fake_problem(N=100, H=100, hid=(300, 300), binary=True, mm=True), auto)["variant"] == 0
+    wide = _lib.make_tuning(stream_mode=5)
+    assert _lib.describe_plan(_fake_problem(binary=True), wide)["variant"] == 3          # c2 on request
+    for kw in (dict(hid=(512, 512)), dict(hid=(400, 400, 400), binary=True), dict(hid=(600, 600), binary=True)):
+        with pytest.raises(NotEligible):
+            _lib.describe_plan(_fake_problem(**kw), wide)
 
 
 def test_cluster_tunables_from_the_environment(lib, monkeypatch):

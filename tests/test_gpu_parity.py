@@ -19,7 +19,7 @@ def _ops_cuda(ops):
     return RolloutOperands.from_flat(ops, device="cuda")
 
 
-def _run(ops, x0, H, cot="loss", env=None, gen_seed=0, mm=None):
+def _run(ops, x0, H, cot="loss", env=None, gen_seed=0, mm=None, cot_mask=None):
     """forward + backward through the fused autograd.Function; returns dict of cpu tensors."""
     from prob_mbrl_b200.rollout import FusedRolloutFunction
     old = {}
@@ -44,6 +44,8 @@ def _run(ops, x0, H, cot="loss", env=None, gen_seed=0, mm=None):
             gS = torch.randn(H + 1, N, o.D, generator=g, dtype=torch.float64)
             gA = torch.randn(H, N, o.U, generator=g, dtype=torch.float64)
             gR = torch.randn(H, N, generator=g, dtype=torch.float64)
+            if cot_mask is not None:     # particles whose cotangents are zeroed: they contribute to no gradient
+                gS, gA, gR = gS * cot_mask[None, :, None], gA * cot_mask[None, :, None], gR * cot_mask[None, :]
             obj = (S * gS.float().cuda()).sum() + (A * gA.float().cuda()).sum() + (R * gR.float().cuda()).sum()
             cots = (gS, gA, gR)
         grads = torch.autograd.grad(obj, params + [x])
@@ -62,13 +64,16 @@ def _run(ops, x0, H, cot="loss", env=None, gen_seed=0, mm=None):
 # sweep variants behind the same C ABI: "ring" = streaming sweeps (hidden x hidden weights through a TMA ring),
 # "cluster" = cluster-resident sweeps (weights in the shared memory of a thread-block cluster; two hidden layers)
 # "tc" = tensor-core cluster sweeps (tcgen05 3xTF32 hidden x hidden layers, 16-CTA cluster per 128-particle tile)
-SWEEPS = {"ring": {"PMB_STREAM_MODE": 2}, "cluster": {"PMB_STREAM_MODE": 3}, "tc": {"PMB_STREAM_MODE": 4}}
+# "cw" = wide cluster-resident sweeps (two-hidden-layer nets up to 512 wide resident in a 16-CTA cluster, up to 36
+#        particles per cluster, masks and gates as bit words)
+SWEEPS = {"ring": {"PMB_STREAM_MODE": 2}, "cluster": {"PMB_STREAM_MODE": 3}, "tc": {"PMB_STREAM_MODE": 4},
+          "cw": {"PMB_STREAM_MODE": 5}}
 
 
-@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc"])
+@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc", "cw"])
 @pytest.mark.parametrize("name", ["cartpole_200x2_n25_h40", "dcartpole_48x3_n24_h30", "cartpole_37x2_n7_h12"])
 def test_rollout_and_gradient_match_reference_golden(name, sweeps):
-    if sweeps == "cluster" and "x3" in name:
+    if sweeps in ("cluster", "cw") and "x3" in name:
         pytest.skip("three hidden layers: streaming sweeps only")
     ops, g = gu.load(name)
     H = int(g["H"])
@@ -81,7 +86,7 @@ def test_rollout_and_gradient_match_reference_golden(name, sweeps):
     assert gu.rel_l2(r["dx0"], g["nomm_dx0"]) < 1e-5
 
 
-@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc"])
+@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc", "cw"])
 def test_c2_full_size_matches_reference_golden(sweeps):
     """BASELINE.json configs[1]: Cartpole 2x[200], 100 particles, H=400."""
     ops, g = gu.load("cartpole_200x2_n100_h400")
@@ -102,7 +107,8 @@ def test_c2_full_size_matches_reference_golden(sweeps):
 @pytest.mark.parametrize("name,sweeps", [("cartpole_37x2_n7_h12", "ring"), ("cartpole_37x2_n7_h12", "cluster"),
                                          ("cartpole_200x2_n25_h40", "cluster"), ("dcartpole_48x3_n24_h30", "ring"),
                                          ("cartpole_37x2_n7_h12", "tc"), ("cartpole_200x2_n25_h40", "tc"),
-                                         ("dcartpole_48x3_n24_h30", "tc")])
+                                         ("dcartpole_48x3_n24_h30", "tc"), ("cartpole_37x2_n7_h12", "cw"),
+                                         ("cartpole_200x2_n25_h40", "cw")])
 def test_generic_cotangents_match_oracle_autograd(name, sweeps):
     """Arbitrary cotangents on states/actions/rewards (value-function tails, CVaR, callbacks)."""
     ops, g = gu.load(name)
@@ -189,7 +195,7 @@ def test_planner_runs_the_bench_workload_on_the_cluster_resident_sweeps(monkeypa
     assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16
 
 
-@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc"])
+@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc", "cw"])
 @pytest.mark.parametrize("D,U", [(3, 2), (4, 3)])
 def test_multi_dimensional_actions_match_oracle(D, U, sweeps):
     """The reference's environments all have one action dimension; the kernels are written for U >= 1.  Random nets
@@ -219,7 +225,7 @@ def test_multi_dimensional_actions_match_oracle(D, U, sweeps):
     assert gu.rel_l2(rc["dx0"], auto[-1]) < 2e-5
 
 
-@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc"])
+@pytest.mark.parametrize("sweeps", ["ring", "cluster", "tc", "cw"])
 @pytest.mark.parametrize("pol_density,dyn_density", [(False, True), (True, False), (False, False)])
 def test_nets_without_output_density_match_oracle(pol_density, dyn_density, sweeps):
     """Deterministic policy (plain Linear output, models/core.py:243 applies tanh to it) and / or a dynamics model
@@ -238,15 +244,57 @@ def test_nets_without_output_density_match_oracle(pol_density, dyn_density, swee
     assert gu.rel_l2(r["dx0"], ref["dx0"]) < 2e-5
 
 
-def test_sweep_variants_agree():
+@pytest.mark.parametrize("other", ["cluster", "cw"])
+def test_sweep_variants_agree(other):
     """The streaming and the cluster-resident sweeps give the same trajectory and gradient to fp32 rounding."""
     ops, g = gu.load("cartpole_200x2_n25_h40")
     ref = gu.policy_grad_list(g, "nomm", ops)
     a = _run(ops, g["x0"], int(g["H"]), env=SWEEPS["ring"])
-    b = _run(ops, g["x0"], int(g["H"]), env=SWEEPS["cluster"])
+    b = _run(ops, g["x0"], int(g["H"]), env=SWEEPS[other])
     assert (a["S"] - b["S"]).abs().max() < 1e-6 and (a["R"] - b["R"]).abs().max() < 1e-6
     assert gu.rel_l2(a["grads"], b["grads"]) < 5e-6
     assert gu.rel_l2(a["grads"], ref) < 1e-5 and gu.rel_l2(b["grads"], ref) < 1e-5
+
+
+@pytest.mark.parametrize("hid,N,H", [((512, 512), 80, 12), ((300, 404), 41, 9), ((512, 512), 250, 5)])
+def test_wide_nets_on_the_wide_cluster_sweeps_match_streaming_and_oracle(hid, N, H):
+    """c5-shaped nets (2x[512]), ragged widths and particle counts, 36 particles per cluster: the planner picks the wide
+    cluster-resident sweeps on its own; trajectory against the streaming sweeps and the fp64 oracle, gradients against
+    the oracle's autograd for random cotangents.  With ~10^6 hidden units per rollout some ReLU inputs are within fp32
+    rounding of zero, where the gate (hence that particle's gradient, by O(1/width)) legitimately depends on the
+    summation order: those particles get zero cotangents."""
+    from prob_mbrl_b200 import _lib
+    kw = dict(D=4, U=1, hid=hid, N=N)
+    ops, x0 = gu.synthetic_ops(**kw)
+    ops64, x064 = gu.synthetic_ops(dtype=torch.float64, **kw)
+    o = _ops_cuda(ops)
+    prob, _keep = _lib.make_problem(o, N, H)
+    info = _lib.describe_plan(prob, _lib.make_tuning())
+    assert info["variant"] == 3 and info["cluster_size"] == 16 and info["threads_per_cta"] == 512
+    if N == 250:
+        assert info["particles_per_group"] == 36
+    a = _run(ops, x0, H, env=SWEEPS["ring"])
+    b = _run(ops, x0, H)
+    assert (a["S"] - b["S"]).abs().max() < 2e-6 and (a["R"] - b["R"]).abs().max() < 2e-6
+    ref = orc.loss_and_grads(ops64, x064, H)
+    assert (b["S"].double() - torch.stack(ref["states"])).abs().max() < 5e-6
+    assert (b["A"].double() - torch.stack(ref["actions"])).abs().max() < 2e-5
+    assert abs(float(b["obj"]) - float(ref["loss"])) < 2e-6
+    safe = (gu.min_abs_preactivation(ops64, x064, H, per_particle=True) > 5e-6).double()
+    assert safe.sum() > 0.6 * N
+    keys = orc.policy_param_keys(ops64)
+    for sweeps in (None, SWEEPS["ring"]):
+        rc = _run(ops, x0, H, cot="generic", env=sweeps, cot_mask=safe)
+        d = dict(ops64)
+        for k in keys:
+            d[k] = d[k].clone().requires_grad_(True)
+        x = x064.clone().requires_grad_(True)
+        S, A, R = orc.rollout(d, x, H)
+        gS, gA, gR = rc["cots"]
+        obj = (torch.stack(S) * gS).sum() + (torch.stack(A) * gA).sum() + (torch.stack(R).squeeze(-1) * gR).sum()
+        auto = torch.autograd.grad(obj, [d[k] for k in keys] + [x])
+        assert gu.rel_l2(rc["grads"], list(auto[:-1])) < 2e-5
+        assert gu.rel_l2(rc["dx0"], auto[-1]) < 2e-5
 
 
 def test_determinism():
