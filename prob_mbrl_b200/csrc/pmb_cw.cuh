@@ -217,6 +217,9 @@ __device__ __forceinline__ float cw_gather(const float *mbox, int lp, int o) {
     return v[0];
 }
 
+// per-warp arrival marks (lane 0 of every warp) of cluster 0 / rank 0 at step H/2: dbg[i * 16 + warp]
+#define CW_MARK(i) do { if (dbg_step && (threadIdx.x & 31) == 0) prm.dbg[(i) * 16 + (threadIdx.x >> 5)] = clock64(); } while (0)
+
 cudaError_t launch_cw_fwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
 cudaError_t launch_cw_bwd(const ClusterParams &prm, int nclusters, cudaStream_t stream);
 int cw_max_active();

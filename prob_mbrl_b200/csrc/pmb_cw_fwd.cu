@@ -75,7 +75,7 @@ template <int TK>
 __device__ __forceinline__ void cw_net_forward(const ClusterParams &prm, const CNet &n, const CwThin<TK> &T, CwWideFwd &W,
                                                float *smem, const float *x, float *act, int rank, int nval, int n0, int t,
                                                int net, bool keep_act, uint32_t mbox_saddr, uint32_t bar_saddr,
-                                               uint32_t wstride) {
+                                               uint32_t wstride, bool dbg_step, int mark0) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // ---- thin (full width, every CTA); the warp whose 32 columns carry this CTA's rank stores them ----
     if (T.on) {
@@ -89,14 +89,17 @@ __device__ __forceinline__ void cw_net_forward(const ClusterParams &prm, const C
             g[CW_TW] = g1;
         }
     }
+    CW_MARK(mark0);
     __syncthreads();
     // ---- wide: this CTA's 32 columns of hidden 1, k-split over the 16 warps ----
     {
         float2 acc[9][2];
         cw_wide_accum(smem + n.s_ww, n.tW, act, acc);
+        CW_MARK(mark0 + 1);
         __syncthreads();                 // every warp is done reading the activation tile
         cw_wide_park(act, acc);
     }
+    CW_MARK(mark0 + 2);
     __syncthreads();
     // ---- epilogue (warp = particle, lane = column) + narrow partial sums -> owner ----
 #pragma unroll
@@ -111,6 +114,7 @@ __device__ __forceinline__ void cw_net_forward(const ClusterParams &prm, const C
         if (lane == 0 && W.send[r]) prm.g2[(((size_t)t * prm.N + n0 + p) * 2 + net) * CW_C + rank] = gate;
         cw_narrow_send(v, smem + n.s_nwt, n.nN, W.send[r], p, rank, mbox_saddr, bar_saddr, wstride);
     }
+    CW_MARK(mark0 + 3);
 }
 
 template <int TKP, int TKD>
@@ -207,14 +211,17 @@ __global__ void __launch_bounds__(CW_NT, 1) cw_fwd_kernel(const __grid_constant_
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const uint32_t par = (uint32_t)(t & 1);
+        const bool dbg_step = prm.dbg != nullptr && blockIdx.x == 0 && t == H / 2;
+        CW_MARK(0);
         if (pol.zstride != 0 && oa && pol.has_density) zA = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)on_ * U + e);
         if (dyn.zstride != 0 && os && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)on_ * D + e);
 
         // ================= policy =================
-        cw_net_forward<TKP>(prm, pol, Tp, Wp, smem, xpol, act, rank, nval, n0, t, 0, true, mbp_saddr, bar0, wstride);
+        cw_net_forward<TKP>(prm, pol, Tp, Wp, smem, xpol, act, rank, nval, n0, t, 0, true, mbp_saddr, bar0, wstride, dbg_step, 1);
         if (owner) {
             // ---- Gaussian action sample + tanh squash (densities.py:95-119, core.py:243), once per particle ----
             mbar_wait(&xbar[0], par);
+            CW_MARK(5);
             float xs = 0.f;
             if (e < U) {
                 const float mu = a_nbm + cw_gather(mb_pol, w, e);
@@ -240,15 +247,18 @@ __global__ void __launch_bounds__(CW_NT, 1) cw_fwd_kernel(const __grid_constant_
                     cw_st_async_f32(xdyn0 + dst_off + (uint32_t)(((D + u) * CW_PS + op) * 4), v, bar1_0 + dst_off);
             }
         }
+        CW_MARK(6);
         mbar_wait(&xbar[1], par);
+        CW_MARK(7);
         if (tid == 0) mbar_expect_tx(&xbar[1], bytes_act);
         __syncthreads();
 
         // ================= dynamics =================
-        cw_net_forward<TKD>(prm, dyn, Td, Wd, smem, xdyn, act, rank, nval, n0, t, 1, false, mbd_saddr, bar2, wstride);
+        cw_net_forward<TKD>(prm, dyn, Td, Wd, smem, xdyn, act, rank, nval, n0, t, 1, false, mbd_saddr, bar2, wstride, dbg_step, 8);
         if (owner) {
             // ---- Gaussian state sample, s' = s + delta (densities.py:100-119, core.py:293,298) ----
             mbar_wait(&xbar[2], par);
+            CW_MARK(12);
             float xs = 0.f;
             if (e < D) {
                 const float mu = b_nbm + cw_gather(mb_dyn, w, e);
@@ -277,7 +287,9 @@ __global__ void __launch_bounds__(CW_NT, 1) cw_fwd_kernel(const __grid_constant_
                 else cw_st_async_f32(xdyn0 + dst_off + (uint32_t)((d * CW_PS + op) * 4), vs, bar3_0 + dst_off);
             }
         }
+        CW_MARK(13);
         mbar_wait(&xbar[3], par);
+        CW_MARK(14);
         if (tid == 0) mbar_expect_tx(&xbar[3], bytes_st);
         __syncthreads();
     }
