@@ -10,6 +10,7 @@
 #include "pmb_internal.cuh"
 #include "pmb_mm.cuh"
 #include "pmb_cluster.cuh"
+#include "pmb_cluster_mm.cuh"
 #include "pmb_cw.cuh"
 #include "pmb_tc.cuh"
 #include "pmb_tc_mm.cuh"
@@ -47,7 +48,7 @@ struct Plan {
     long long job_dst_off[MAX_PACK_JOBS];
     long long wpack_fwd_off, wpack_bwd_off;
     long long part_off;
-    long long s1pre_off, mmstat_off, mmrec_off, mmctr_off, rpre_off, rstat_off, geff_off;
+    long long s1pre_off, mmstat_off, mmrec_off, mmctr_off, rpre_off, rstat_off, geff_off, cmm_gbuf_off;
     int mm_G;
     long long nparam;
     long long ws_floats;
@@ -297,7 +298,8 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
 // widths <= 256, D+U <= 16, outputs <= 16, no moment matching of the states.
 // ---------------------------------------------------------------------------------------------
 static bool cluster_eligible(const pmb_problem *p, int C) {
-    if (p->mm_states) return false;
+    // moment matching of the states: one matching group (the whole particle set) of <= 128 particles
+    if (p->mm_states && (p->mm_groups > 1 || p->N > CMM_NMAX || p->N < 2)) return false;
     const pmb_net *nets[2] = {&p->pol, &p->dyn};
     for (int i = 0; i < 2; ++i) {
         const pmb_net &n = *nets[i];
@@ -370,6 +372,8 @@ static int cluster_carve(ClusterParams &P, bool reverse) {
     P.off_red = take(CL_KS * CL_PS * 32);
     P.off_inbox = take(2 * 2 * P.C * CL_MBOX);        // [tile][exchange][sender rank][4 slots x 16]
     P.off_misc = take(reverse ? (4 + 2 * 6) * CL_PS * SD + 32 : CL_PS * SD);
+    P.off_mm = off;
+    if (P.mm_states) take(2 * CMM_FLOATS);
     P.smem_floats = off;
     return off;
 }
@@ -391,6 +395,7 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         ClusterParams &P = pass ? pl.cbwd : pl.cfwd;
         memset(&P, 0, sizeof(P));
         P.N = S.N; P.H = S.H; P.D = S.D; P.U = S.U; P.C = C;
+        P.mm_states = p->mm_states; P.z_mm = p->z_mm;
         cluster_net(S.pol, pass == 1, true, C, P.pol);
         cluster_net(S.dyn, pass == 1, false, C, P.dyn);
         P.act_scale = S.act_scale; P.act_bias = S.act_bias; P.mx = S.mx; P.iSx = S.iSx; P.my = S.my; P.Sy = S.Sy;
@@ -417,6 +422,22 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         PG = (p->N + maxc - 1) / maxc;
         if (PG > CL_PS) PG = CL_PS;
         if (PG < 1) PG = 1;
+    }
+    if (p->mm_states) {
+        // every cluster must be resident (the per-step exchange is a grid-wide barrier): spread over at most the
+        // co-resident clusters
+        static int mmc[32];
+        static bool mmc_init = false;
+        if (!mmc_init) { for (auto &c : mmc) c = -1; mmc_init = true; }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+        if (mmc[dev] < 0) mmc[dev] = cluster_max_active(C, max(pl.cfwd.smem_floats, pl.cbwd.smem_floats) * 4, true);
+        const int maxc = mmc[dev] > 0 ? mmc[dev] : (C == 8 ? 15 : 30);
+        if ((p->N + PG - 1) / PG > maxc) PG = (p->N + maxc - 1) / maxc;
+        if (PG > CL_PS) {
+            if (mode == 3) return fail(PMB_E_UNSUPPORTED, "mm_states with N=%d particles does not fit the co-resident clusters", p->N);
+            return PMB_OK;
+        }
     }
     pl.cfwd.PG = pl.cbwd.PG = PG;
     {
@@ -773,6 +794,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.rpre_off = ws.take(HN);
         pl.rstat_off = ws.take((long long)p->H * G * 4);
         pl.geff_off = ws.take(HN);
+        pl.cmm_gbuf_off = ws.take(2LL * p->N * SD);
     }
     if ((rc = plan_tc(p, tune, pl, ws)) != PMB_OK) return rc;
     const long long ws_before_cw = ws.top;
@@ -847,6 +869,15 @@ static void resolve(Plan &pl, float *ws) {
         }
     }
     pl.cfwd.ws = pl.cbwd.ws = ws;
+    if (pl.cluster && pl.cfwd.mm_states) {
+        for (int pass = 0; pass < 2; ++pass) {
+            ClusterParams &P = pass ? pl.cbwd : pl.cfwd;
+            P.s1pre = ws + pl.s1pre_off;
+            P.mmstat = ws + pl.mmstat_off;
+            P.mmctr = reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + pass;   // one counter per sweep
+            P.gbuf = ws + pl.cmm_gbuf_off;
+        }
+    }
     pl.cbwd.pre = ws + pl.cl_pre_off;
     pl.cfwd.wpack = ws + pl.wpack_fwd_off;
     pl.cbwd.wpack = ws + pl.wpack_bwd_off;
@@ -983,6 +1014,7 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     } else if (pl.cluster) {
         ClusterParams &CF = pl.cfwd;
         CF.x0 = x0; CF.states = states; CF.actions = actions; CF.rewards = F.rewards; CF.dbg = F.dbg;
+        CF.status = status_dev;
         if (phases & 2) PMB_CUDA(launch_cluster_fwd(CF, pl.cl_nclusters, st));
     } else if (phases & 2) {
         PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));

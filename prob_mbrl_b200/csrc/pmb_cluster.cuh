@@ -72,6 +72,14 @@ struct ClusterParams {
     float *pre;                 // backward: [H][N][2D + 3U] step-local adjoint factors (bwd_pre_kernel)
     const float *s1pre;         // next states BEFORE moment matching [H][N][D] (the reward acts on them), nullptr = states[t+1]
     long long *dbg;             // clock64() marks of cluster 0 / rank 0 at step H/2 (nullable)
+    // moment matching of the states inside the cluster-resident sweeps (pmb_cluster_mm.cuh)
+    int mm_states;              // != 0: one matching group = all N particles (N <= 128)
+    const float *z_mm;          // [>= N][D]
+    float *mmstat;              // [H][3*SD + SD*SD] mean, z mean, 1/z std, Cholesky factor of every step
+    unsigned *mmctr;            // arrival counter of this sweep (zeroed before the launch)
+    float *gbuf;                // reverse: [2][N][SD] adjoints of the matched particles (double-buffered by step parity)
+    int *status;                // forward: 1 + first step whose covariance was not positive definite
+    int off_mm;                 // shared memory: two CMM blocks (one per particle tile)
     unsigned *g1, *g2;          // wide cluster-resident sweeps (pmb_cw.cuh): ReLU/dropout gate bit words of hidden 0 / 1
     int ncl;                    // ... clusters of the launch
     int off_cst, off_xa, off_xb, off_act, off_red, off_inbox, off_misc;

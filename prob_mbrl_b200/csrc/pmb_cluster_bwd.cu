@@ -10,6 +10,7 @@
 // and the ReLU/dropout gates ONE STEP AHEAD into registers, so the serial chain never waits on global memory
 // and holds no transcendental arithmetic.
 #include "pmb_cluster.cuh"
+#include "pmb_cluster_mm.cuh"
 #include "pmb_host.h"
 
 namespace pmb {
@@ -315,11 +316,19 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     if (xact) odel_ptr = prm.ws + pol.odel_off + ((size_t)(H - 1) * N + x_n) * pol.nraw + (x_k - D);
     const size_t odel_step = (size_t)N * pol.nraw;
 
+    // moment matching of the states: scratch of this tile, arrivals per step, z statistics (constants of the launch)
+    const bool mm = prm.mm_states != 0;
+    CMM M;
+    M.carve(smem + prm.off_mm + g * CMM_FLOATS);
+    const unsigned mm_tiles = mm ? cmm_active_tiles(N, PG, C) : 0u;
+    const bool b_own = roleB && b_p < nvg && ((g * CL_TS + b_p) % C) == rank;
+
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
 
     const bool pingpong = prm.pingpong != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
+    if (mm) cmm_z_statistics(prm, M, g, gtid);
     if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
     // ---- prologue: everything step H-1 needs ----
     float c_rs, c_fd, c_gs, c_ra, c_tp, c_fp;
@@ -335,6 +344,12 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         CL_TMARK(32);
         // ---- one step ahead: factors and gates of step t-1 ----
         if (t > 0) prefetch(t - 1);
+        if (mm) {
+            // ---- adjoint of the moment matching: cotangent of the matched s_{t+1} -> cotangent of the pre-matching
+            //      particles (one exchange over all tiles of the grid, rollout.py:121-128) ----
+            cmm_backward_prefetch(prm, M, g, gtid, t, roleB, b_p, b_d, b_n);
+            cmm_backward(prm, M, g, gtid, t, (unsigned)(it + 1) * mm_tiles, gs, roleB, b_p, b_d, b_n, b_own);
+        }
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
         if (roleB) {
@@ -418,7 +433,7 @@ cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStre
         if (e0 != cudaSuccess) return e0;
     }
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = prm.C;
     attr[0].val.clusterDim.y = 1;
@@ -429,6 +444,11 @@ cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStre
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (prm.mm_states) {        // the per-step exchange spins on a global counter: every cluster must be resident
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e;
     switch (prm.C) {
         case 8:

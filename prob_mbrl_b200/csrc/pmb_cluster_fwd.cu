@@ -7,6 +7,7 @@
 // (envs/cartpole/env.py:41-86 et al.).  Same workspace layout as the streaming sweep (pmb_rollout_fwd.cu),
 // so the reverse sweep and the weight-gradient kernels of either variant can follow.
 #include "pmb_cluster.cuh"
+#include "pmb_cluster_mm.cuh"
 #include "pmb_host.h"
 
 namespace pmb {
@@ -204,11 +205,19 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     const size_t act_step = (size_t)N * U, rawp_step = (size_t)N * pol.nraw, st_step = (size_t)N * D,
                  rawd_step = (size_t)N * dyn.nraw;
 
+    // moment matching of the states: scratch of this tile, arrivals per step, z statistics (constants of the launch)
+    const bool mm = prm.mm_states != 0;
+    CMM M;
+    M.carve(smem + prm.off_mm + g * CMM_FLOATS);
+    const unsigned mm_tiles = mm ? cmm_active_tiles(N, PG, C) : 0u;
+    const bool mm_leader = blockIdx.x == 0 && g == 0;
+
     __syncthreads();
     cl_sync();          // every CTA's barriers are initialised and armed before any peer may signal them
 
     const bool pingpong = prm.pingpong != 0 && nval - nv0 > 0;   // both tiles populated: alternate on the LSU phases
     if (nvg > 0) {
+    if (mm) cmm_z_statistics(prm, M, g, gtid);
     if (pingpong && g == 1) CT_LSU_RELEASE(1);      // tile 0 goes first
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
@@ -218,6 +227,11 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         // per-step noise (only when the caller pre-drew [H, N, .] tables): issue the loads early
         if (pol.zstride != 0 && roleA && pol.has_density) zA = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)a_n * U + a_u);
         if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
+        if (mm && roleB) {      // z row of the matching step: z_mm[(t + n) mod N] (rollout.py:53-59); read after >= 4 tile barriers
+            int r = t + b_n;
+            r -= (r / N) * N;
+            M.zrow[b_p * SD + b_d] = __ldg(prm.z_mm + (size_t)r * D + b_d);
+        }
 
         // ================= policy =================
         ct_net_forward<C, TK>(prm, pol, Rp, smem, xpol, act, red, g, gtid, mbox_pol_saddr, bar_pol, wstride, dbg_step, 1, pingpong);
@@ -262,12 +276,23 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
                 delta = mu * b_sy + b_my;
             }
             s_reg += delta;
-            xpol[b_d * CL_TS + b_p] = s_reg;
-            xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
+            if (!mm) {
+                xpol[b_d * CL_TS + b_p] = s_reg;
+                xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
+            }
             if (b_own) {
-                *st_ptr = s_reg;
+                if (!mm) *st_ptr = s_reg;
                 rawd_ptr[0] = mu;
                 if (dyn.has_density) rawd_ptr[D] = ls;
+            }
+        }
+        if (mm) {
+            // ---- moment matching: every tile of the grid exchanges its pre-matching particles (rollout.py:121-128) ----
+            cmm_forward(prm, M, g, gtid, t, (unsigned)(t + 1) * mm_tiles, roleB, b_p, b_d, b_n, b_own, s_reg, mm_leader);
+            if (roleB) {
+                xpol[b_d * CL_TS + b_p] = s_reg;
+                xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
+                if (b_own) *st_ptr = s_reg;
             }
         }
         st_ptr += st_step;
@@ -281,7 +306,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     for (int i = gtid; i < H * CL_TS; i += CL_GT) {
         const int tt = i / CL_TS, p = i - tt * CL_TS;
         if (p >= nvg || ((g * CL_TS + p) % C) != rank) continue;
-        const float *s1 = prm.states + ((size_t)(tt + 1) * N + n0g + p) * D;
+        // with moment matching the reward sees the next state BEFORE the matching (models/core.py:293 runs inside dynamics())
+        const float *s1 = mm ? prm.s1pre + ((size_t)tt * N + n0g + p) * D : prm.states + ((size_t)(tt + 1) * N + n0g + p) * D;
         const float *a = prm.actions + ((size_t)tt * N + n0g + p) * U;
         float dl[PMB_MAX_REWARD_ROWS];
         for (int r = 0; r < prm.KR; ++r) {
@@ -316,7 +342,7 @@ static cudaError_t cluster_launch_cfg(const void *fn, int C, int smem_bytes) {
 cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStream_t stream) {
     const int smem_bytes = prm.smem_floats * 4;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = prm.C;
     attr[0].val.clusterDim.y = 1;
@@ -327,6 +353,11 @@ cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStre
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (prm.mm_states) {        // the per-step exchange spins on a global counter: every cluster must be resident
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e;
     const int tkm = max(prm.pol.tK, prm.dyn.tK);
     const int tk = tkm <= 6 ? 6 : tkm <= 8 ? 8 : 16;

@@ -132,7 +132,9 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     tc = _lib.make_tuning(stream_mode=4)
     for kw, tiles, tp in ((dict(N=100, H=400, mm=True), 1, 100), (dict(N=125, H=600, D=8, hid=(400, 400, 400)), 1, 125),
                           (dict(N=250, H=1000, hid=(512, 512)), 2, 125), (dict(N=1000, H=40), 8, 125)):
-        assert _lib.describe_plan(_fake_problem(**kw), auto)["variant"] == (1 if kw["N"] == 1000 else 0), kw
+        # auto: 2x[200] nets run on the 8-CTA cluster-resident sweeps, with moment matching as well (one group of
+        # <= 128 particles spread over the co-resident clusters); wider / deeper nets stream
+        assert _lib.describe_plan(_fake_problem(**kw), auto)["variant"] == (1 if "hid" not in kw else 0), kw
         info = _lib.describe_plan(_fake_problem(**kw), tc)
         assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16 * tiles, kw
         assert info["particles_per_group"] == tp and info["threads_per_cta"] == 384
@@ -161,6 +163,12 @@ def test_planner_picks_the_sweep_variant(lib, monkeypatch):
     assert _lib.describe_plan(_fake_problem(binary=True), auto)["variant"] == 1
     assert _lib.describe_plan(_fake_problem(N=125, H=600, D=8, hid=(400, 400, 400), binary=True), auto)["variant"] == 0
     assert _lib.describe_plan(_fake_problem(N=100, H=100, hid=(300, 300), binary=True, mm=True), auto)["variant"] == 0
+    # moment matching on the cluster-resident sweeps: every cluster co-resident (<= 15 x 8 CTAs), one matching group
+    c3 = _lib.describe_plan(_fake_problem(N=100, H=400, mm=True), auto)
+    assert c3["variant"] == 1 and c3["ctas"] <= 15 * 8 and c3["ctas"] // 8 * c3["particles_per_group"] >= 100
+    assert c3["smem_fwd_bytes"] <= 232448 - 1024 and c3["smem_bwd_bytes"] <= 232448 - 1024
+    assert _lib.describe_plan(_fake_problem(N=100, H=400, mm=True, groups=2), auto)["variant"] == 0
+    assert _lib.describe_plan(_fake_problem(N=200, H=40, mm=True), auto)["variant"] == 0
     wide = _lib.make_tuning(stream_mode=5)
     assert _lib.describe_plan(_fake_problem(binary=True), wide)["variant"] == 3          # c2 on request
     for kw in (dict(hid=(512, 512)), dict(hid=(400, 400, 400), binary=True), dict(hid=(600, 600), binary=True)):
