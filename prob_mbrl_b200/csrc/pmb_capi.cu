@@ -396,6 +396,7 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         memset(&P, 0, sizeof(P));
         P.N = S.N; P.H = S.H; P.D = S.D; P.U = S.U; P.C = C;
         P.mm_states = p->mm_states; P.z_mm = p->z_mm;
+        P.mm_dbg = tune ? (tune->reserved[0] >> 8) : 0;
         cluster_net(S.pol, pass == 1, true, C, P.pol);
         cluster_net(S.dyn, pass == 1, false, C, P.dyn);
         P.act_scale = S.act_scale; P.act_bias = S.act_bias; P.mx = S.mx; P.iSx = S.iSx; P.my = S.my; P.Sy = S.Sy;
@@ -794,7 +795,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.rpre_off = ws.take(HN);
         pl.rstat_off = ws.take((long long)p->H * G * 4);
         pl.geff_off = ws.take(HN);
-        pl.cmm_gbuf_off = ws.take(2LL * p->N * SD);
+        pl.cmm_gbuf_off = ws.take(2LL * 2 * CMM_TILES * CMM_NQ);     // doubles: [2][tiles][CMM_NQ] records of the cluster sweeps
     }
     if ((rc = plan_tc(p, tune, pl, ws)) != PMB_OK) return rc;
     const long long ws_before_cw = ws.top;
@@ -875,7 +876,7 @@ static void resolve(Plan &pl, float *ws) {
             P.s1pre = ws + pl.s1pre_off;
             P.mmstat = ws + pl.mmstat_off;
             P.mmctr = reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + pass;   // one counter per sweep
-            P.gbuf = ws + pl.cmm_gbuf_off;
+            P.mmrec = reinterpret_cast<double *>(ws + pl.cmm_gbuf_off);
         }
     }
     pl.cbwd.pre = ws + pl.cl_pre_off;
@@ -986,7 +987,7 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
         return fail(PMB_E_WORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, (size_t)pl.ws_floats * 4);
     cudaStream_t st = (cudaStream_t)stream;
     resolve(pl, (float *)workspace);
-    const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 1 pack, 2 sweep
+    const int phases = (tune && (tune->reserved[0] & 255)) ? (tune->reserved[0] & 255) : 7;   // profiling aid: 1 pack, 2 sweep
     if (status_dev) PMB_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
     if (phases & 1) {
         if (pl.tc) {
@@ -1054,7 +1055,7 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     }
     if (p->mm_states && !pl.tc) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
-    const int phases = (tune && tune->reserved[0]) ? tune->reserved[0] : 7;   // profiling aid: 2 sweep, 4 wgrad
+    const int phases = (tune && (tune->reserved[0] & 255)) ? (tune->reserved[0] & 255) : 7;   // profiling aid: 2 sweep, 4 wgrad
     if (pl.tc) {
         TcParams &T = pl.tbwd;
         T.states = B.states; T.actions = B.actions; T.rewards = B.rewards;

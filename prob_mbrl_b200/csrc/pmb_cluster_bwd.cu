@@ -195,7 +195,7 @@ __device__ __forceinline__ void ct_net_backward(const ClusterParams &prm, const 
     CL_TMARK(mark0 + 2);
 }
 
-template <int C>
+template <int C, bool MM = false>
 __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_constant__ ClusterParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t xbar[2][2];       // [group][0 dynamics exchange, 1 policy exchange]
@@ -317,11 +317,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     const size_t odel_step = (size_t)N * pol.nraw;
 
     // moment matching of the states: scratch of this tile, arrivals per step, z statistics (constants of the launch)
-    const bool mm = prm.mm_states != 0;
+    constexpr bool mm = MM;
     CMM M;
     M.carve(smem + prm.off_mm + g * CMM_FLOATS);
-    const unsigned mm_tiles = mm ? cmm_active_tiles(N, PG, C) : 0u;
-    const bool b_own = roleB && b_p < nvg && ((g * CL_TS + b_p) % C) == rank;
+    const unsigned mm_ncl = mm ? cmm_clusters(N, PG) : 0u;
 
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             // ---- adjoint of the moment matching: cotangent of the matched s_{t+1} -> cotangent of the pre-matching
             //      particles (one exchange over all tiles of the grid, rollout.py:121-128) ----
             cmm_backward_prefetch(prm, M, g, gtid, t, roleB, b_p, b_d, b_n);
-            cmm_backward(prm, M, g, gtid, t, (unsigned)(it + 1) * mm_tiles, gs, roleB, b_p, b_d, b_n, b_own);
+            cmm_backward(prm, M, g, gtid, rank, t, (unsigned)(it + 1) * mm_ncl, nvg, gs, roleB, b_p, b_d);
         }
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
@@ -408,6 +407,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     }
     if (prm.dx0 && roleB && b_p < nvg && ((g * CL_TS + b_p) % C) == rank)
         prm.dx0[(size_t)(n0g + b_p) * D + b_d] = gs[b_p * SD + b_d];
+    } else if (mm) {
+        // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
+        for (int it = 0; it < H; ++it) cmm_idle_step(prm, g, gtid, rank, H - 1 - it, (unsigned)(it + 1) * mm_ncl);
     }
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
@@ -452,9 +454,17 @@ cudaError_t launch_cluster_bwd(const ClusterParams &prm, int nclusters, cudaStre
     cudaError_t e;
     switch (prm.C) {
         case 8:
+            if (prm.mm_states) {
+                if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<8, true>, 8, smem_bytes)) != cudaSuccess) return e;
+                return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<8, true>, prm);
+            }
             if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<8>, 8, smem_bytes)) != cudaSuccess) return e;
             return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<8>, prm);
         case 4:
+            if (prm.mm_states) {
+                if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<4, true>, 4, smem_bytes)) != cudaSuccess) return e;
+                return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<4, true>, prm);
+            }
             if ((e = cluster_launch_cfg_b((const void *)cluster_bwd_kernel<4>, 4, smem_bytes)) != cudaSuccess) return e;
             return cudaLaunchKernelEx(&cfg, cluster_bwd_kernel<4>, prm);
         default:

@@ -119,7 +119,9 @@ __device__ __forceinline__ void ct_net_forward(const ClusterParams &prm, const C
     CL_TMARK(mark0 + 2);
 }
 
-template <int C, int TK>
+// MM: moment matching of the states compiled in (a separate instantiation: the plain sweeps keep their code size --
+// they live off the instruction cache -- and their registers)
+template <int C, int TK, bool MM = false>
 __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_constant__ ClusterParams prm) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t xbar[2][2];       // [group][0 policy exchange, 1 dynamics exchange]
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
                  rawd_step = (size_t)N * dyn.nraw;
 
     // moment matching of the states: scratch of this tile, arrivals per step, z statistics (constants of the launch)
-    const bool mm = prm.mm_states != 0;
+    constexpr bool mm = MM;
     CMM M;
     M.carve(smem + prm.off_mm + g * CMM_FLOATS);
-    const unsigned mm_tiles = mm ? cmm_active_tiles(N, PG, C) : 0u;
+    const unsigned mm_ncl = mm ? cmm_clusters(N, PG) : 0u;
     const bool mm_leader = blockIdx.x == 0 && g == 0;
 
     __syncthreads();
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         }
         if (mm) {
             // ---- moment matching: every tile of the grid exchanges its pre-matching particles (rollout.py:121-128) ----
-            cmm_forward(prm, M, g, gtid, t, (unsigned)(t + 1) * mm_tiles, roleB, b_p, b_d, b_n, b_own, s_reg, mm_leader);
+            cmm_forward(prm, M, g, gtid, rank, t, (unsigned)(t + 1) * mm_ncl, nvg, roleB, b_p, b_d, b_n, b_own, s_reg, mm_leader,
+                        dbg_step ? prm.dbg + 24 * 8 : nullptr);
             if (roleB) {
                 xpol[b_d * CL_TS + b_p] = s_reg;
                 xdyn[b_d * CL_TS + b_p] = (s_reg - b_mx) * b_isx;
@@ -328,6 +331,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         }
         prm.rewards[(size_t)tt * N + n0g + p] = prm.rew_scale * expf(-0.5f * cost) + prm.rew_offset;
     }
+    } else if (mm) {
+        // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
+        for (int t = 0; t < H; ++t) cmm_idle_step(prm, g, gtid, rank, t, (unsigned)(t + 1) * mm_ncl);
     }
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
@@ -362,10 +368,15 @@ cudaError_t launch_cluster_fwd(const ClusterParams &prm, int nclusters, cudaStre
     const int tkm = max(prm.pol.tK, prm.dyn.tK);
     const int tk = tkm <= 6 ? 6 : tkm <= 8 ? 8 : 16;
 #define PMB_CL_FWD(CC, TT)                                                                                      \
-    if (prm.C == CC && tk == TT) {                                                                              \
+    if (prm.C == CC && tk == TT && !prm.mm_states) {                                                            \
         if ((e = cluster_launch_cfg((const void *)cluster_fwd_kernel<CC, TT>, CC, smem_bytes)) != cudaSuccess)  \
             return e;                                                                                           \
         return cudaLaunchKernelEx(&cfg, cluster_fwd_kernel<CC, TT>, prm);                                       \
+    }                                                                                                           \
+    if (prm.C == CC && tk == TT && prm.mm_states) {                                                             \
+        if ((e = cluster_launch_cfg((const void *)cluster_fwd_kernel<CC, TT, true>, CC, smem_bytes)) != cudaSuccess) \
+            return e;                                                                                           \
+        return cudaLaunchKernelEx(&cfg, cluster_fwd_kernel<CC, TT, true>, prm);                                 \
     }
     PMB_CL_FWD(8, 6)
     PMB_CL_FWD(8, 8)

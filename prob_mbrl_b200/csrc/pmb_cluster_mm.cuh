@@ -1,12 +1,12 @@
 // Moment matching of the states inside the cluster-resident sweeps (reference utils/rollout.py:20-29,121-145):
 //   x' = m + zhat chol(S)^T,  m = mean_n x,  S = (x-m)^T (x-m)/(N-1) + 1e-12 I,
 //   zhat = (z - mean z) / std_unbiased(z) per column, z = z_mm[(t + n) mod N] (rollout.py:53-59).
-// The particles live in <= 15 clusters, so every step needs ONE cross-cluster exchange: the owner CTA of a particle
-// writes it to global memory, every particle tile (warp group) of every CTA arrives on a global counter, and after
-// the barrier every tile reads ALL particles back (N x D floats out of L2) and forms the statistics itself, in a
-// fixed order -- deterministic and identical everywhere, no per-block records to combine.  One matching group only
-// (the whole particle set), N <= 128: with a single group the z rows of a step are a rotation of the same set, so
-// their mean / std are constants of the launch.  The reverse step is the hand-derived adjoint of
+// The particles live in <= 15 clusters, so every step needs ONE cross-cluster exchange: one CTA per cluster
+// (rank 0 of the cluster) publishes the raw moments of each of its two particle tiles (sum x, sum x x^T in double:
+// products of two floats are exact), every cluster arrives on a global counter (hardware cluster barrier + one
+// atomic per cluster + one poller per CTA), and after the barrier every tile adds the <= 30 records in tile order --
+// deterministic and identical everywhere.  One matching group only (the whole particle set), N <= 128: with a single
+// group the z rows of a step are a rotation of the same set, so their mean / std are constants of the launch.  The reverse step is the hand-derived adjoint of
 // oracle/rollout_oracle.py::mm_backward (same formulas as pmb_mm.cuh).
 #pragma once
 #include "pmb_cluster.cuh"
@@ -14,215 +14,293 @@
 namespace pmb {
 
 constexpr int CMM_NMAX = 128;                 // particles (<= 8 x the co-resident clusters)
-constexpr int CMM_PART = 256;                 // doubles: chunked partial sums
-// shared memory of ONE particle tile (floats): xs, zs [128][SD]; partial sums; m, zm, zistd; L, A, X, Sb; dm; own rows
-constexpr int CMM_FLOATS = 2 * CMM_NMAX * SD + 2 * CMM_PART + 2 * 2 * SD + 3 * SD + 4 * SD * SD + SD + 2 * CL_TS * SD;
+constexpr int CMM_NQ = SD + SD * (SD + 1) / 2;  // reduced quantities (max): D sums + D (D + 1) / 2 products
+constexpr int CMM_TILES = 2 * 32;             // particle tiles of the grid (max): two per cluster
+// shared memory of ONE particle tile (floats): staged records (doubles); totals, means (doubles); (i, j) table;
+// m, zm, zistd; L, A, X, Sb; dm; rows of the tile's slots (two sets)
+constexpr int CMM_FLOATS = 2 * CMM_TILES * 16 + 2 * CMM_NQ + 2 * SD + CMM_NQ + 3 * SD + 4 * SD * SD + SD + 2 * CL_TS * SD + 24;
 
 struct CMM {
-    float *xs, *zs;          // [N][SD] all particles (forward: pre-matching states; reverse: adjoints) / standardised z rows
-    double *part;            // [CMM_PART]
-    double *dmean;           // [SD] means in double, [SD] scratch
+    double *stage;           // [tiles][nq] records of the step (when they fit: tiles * nq <= CMM_TILES * 16), else read in place
+    double *red;             // [NQ] totals
+    double *dmean;           // [SD]
+    int *qtab;               // [NQ] (i << 8 | j) of the lower-triangle quantity q
     float *st;               // m[SD], zm[SD], zistd[SD]
     float *L, *A, *X, *Sb;   // [SD*SD]
     float *dm;               // [SD]
-    float *zrow;             // [4][SD] z rows of the tile's slots (forward) / pre-matching states of the slots (reverse)
-    float *aux;              // [4][SD]
+    float *zrow;             // [4][SD] z rows of the tile's slots (forward: raw; reverse: standardised)
+    float *xrow;             // [4][SD] pre-matching states of the tile's slots
     __device__ __forceinline__ void carve(float *base) {
-        xs = base;
-        zs = xs + CMM_NMAX * SD;
-        part = reinterpret_cast<double *>(zs + CMM_NMAX * SD);
-        dmean = part + CMM_PART;
-        st = reinterpret_cast<float *>(dmean + 2 * SD);
+        stage = reinterpret_cast<double *>(base);
+        red = stage + CMM_TILES * 16;
+        dmean = red + CMM_NQ;
+        qtab = reinterpret_cast<int *>(dmean + SD);
+        st = reinterpret_cast<float *>(qtab + CMM_NQ);
         L = st + 3 * SD;
         A = L + SD * SD;
         X = A + SD * SD;
         Sb = X + SD * SD;
         dm = Sb + SD * SD;
         zrow = dm + SD;
-        aux = zrow + CL_TS * SD;
+        xrow = zrow + CL_TS * SD;
     }
 };
 
-// every active particle tile of the grid meets here; `target` = arrivals expected so far
-__device__ __forceinline__ void cmm_barrier(unsigned *ctr, unsigned target, int g, int gtid) {
-    __threadfence();
-    CT_SYNC(g);
-    if (gtid == 0) {
-        atomicAdd(ctr, 1u);
+// Every cluster of the grid meets here, once per step: all threads of the cluster (both particle tiles of its 8 CTAs)
+// join a hardware cluster barrier, rank 0 arrives on the global counter for the cluster, one thread per CTA polls it
+// (`target` = arrivals expected so far = clusters x steps).
+__device__ __forceinline__ void cmm_barrier(unsigned *ctr, unsigned target, int rank) {
+    // release pattern: the record writers' stores are ordered before the cluster barrier (its arrive.release is a
+    // gpu-level membar in SASS; the explicit acq_rel fence keeps the PTX model honest and is cheaper than the
+    // sequentially consistent __threadfence()), rank 0 then publishes with a release reduction
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    cl_sync();
+    if (threadIdx.x == 0) {
+        if (rank == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned v, spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             if (++spins > (1u << 26)) __trap();
         } while (v < target);
-        __threadfence();
     }
-    CT_SYNC(g);
+    __syncwarp();               // the polling lane rejoins its warp before the (aligned) CTA barrier
+    __syncthreads();
 }
 
-// One reduced quantity: sum_n (P[n][i] - cp[i]) * (Q[n][j] - cq[j]);  j < 0: sum_n (P[n][i] - cp[i])
-struct CmmQ {
-    int i, j;
-};
 // lower-triangle index q = i (i + 1) / 2 + j  ->  (i, j)
-__device__ __forceinline__ CmmQ cmm_tri(int q) {
-    int i = 0;
-    while ((i + 1) * (i + 2) / 2 <= q) ++i;
-    return CmmQ{i, q - i * (i + 1) / 2};
-}
-// out[q] for q < nq, in double: chunked over the tile's 128 threads, combined in a fixed order (identical on every tile)
-template <typename QF>
-__device__ __forceinline__ void cmm_reduce(int nq, int N, QF qf, const float *P, const double *cp, const float *Q, const double *cq,
-                                           double *part, double *out, int g, int gtid) {
-    const int ch = max(1, min(8, CMM_PART / max(nq, 1)));
-    for (int idx = gtid; idx < nq * ch; idx += CL_GT) {
-        const int q = idx / ch, c = idx - q * ch;
-        const CmmQ s = qf(q);
-        const double ci = cp ? cp[s.i] : 0.0, cj = (cq && s.j >= 0) ? cq[s.j] : 0.0;
-        double a = 0.0;
-        if (s.j < 0) {
-            for (int n = c; n < N; n += ch) a += (double)P[n * SD + s.i] - ci;
-        } else {
-            for (int n = c; n < N; n += ch) a += ((double)P[n * SD + s.i] - ci) * ((double)Q[n * SD + s.j] - cj);
-        }
-        part[idx] = a;
+__device__ __forceinline__ void cmm_init_qtab(const CMM &M, int D, int gtid) {
+    for (int q = gtid; q < D * (D + 1) / 2; q += CL_GT) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= q) ++i;
+        M.qtab[q] = (i << 8) | (q - i * (i + 1) / 2);
     }
-    CT_SYNC(g);
+}
+__device__ __forceinline__ unsigned cmm_clusters(int N, int PG) { return (unsigned)((N + PG - 1) / PG); }
+
+// totals of the step: M.red[q] = sum over the particle tiles of the grid of their records, in tile order (identical on
+// every tile).  Records: rec[tile = 2 cluster + g][q], written by rank 0 of the cluster.
+__device__ __forceinline__ void cmm_combine(const CMM &M, const double *rec, int ntiles, int nq, int g, int gtid) {
+    const bool staged = ntiles * nq <= CMM_TILES * 16;
+    if (staged) {
+        // all loads of a thread in flight at once (<= 8 per thread): one L2 round trip, not one per record
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = gtid + k * CL_GT;
+            v[k] = i < ntiles * nq ? __ldcg(rec + (size_t)(i / nq) * CMM_NQ + (i % nq)) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = gtid + k * CL_GT;
+            if (i < ntiles * nq) M.stage[i] = v[k];
+        }
+        CT_SYNC(g);
+    }
     for (int q = gtid; q < nq; q += CL_GT) {
-        double a = 0.0;
-        for (int c = 0; c < ch; ++c) a += part[q * ch + c];
-        out[q] = a;
+        double a0 = 0.0, a1 = 0.0;
+        int c = 0;
+        for (; c + 1 < ntiles; c += 2) {
+            a0 += staged ? M.stage[c * nq + q] : __ldcg(rec + (size_t)c * CMM_NQ + q);
+            a1 += staged ? M.stage[(c + 1) * nq + q] : __ldcg(rec + (size_t)(c + 1) * CMM_NQ + q);
+        }
+        if (c < ntiles) a0 += staged ? M.stage[c * nq + q] : __ldcg(rec + (size_t)c * CMM_NQ + q);
+        M.red[q] = a0 + a1;
     }
     CT_SYNC(g);
 }
 
-// active particle tiles of the launch (arrivals per step)
-__device__ __forceinline__ unsigned cmm_active_tiles(int N, int PG, int C) {
-    unsigned n = 0;
-    for (int n0 = 0; n0 < N; n0 += PG) {
-        const int nval = min(PG, N - n0);
-        n += (unsigned)C * (1u + ((nval - ((nval + 1) >> 1)) > 0 ? 1u : 0u));
-    }
-    return n;
+// an idle tile (no particles) still takes part in the per-step exchange: an all-zero record, the barriers
+__device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, int g, int gtid, int rank, int t, unsigned target) {
+    const int nq = prm.D + prm.D * (prm.D + 1) / 2;
+    const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG);
+    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
+    if (rank == 0 && gtid < nq) rec[(size_t)(2 * (blockIdx.x / prm.C) + g) * CMM_NQ + gtid] = 0.0;
+    cmm_barrier(prm.mmctr, target, rank);
 }
 
 // constants of the launch: mean and 1 / unbiased std of the z_mm rows (all N rows take part in every step)
 __device__ __forceinline__ void cmm_z_statistics(const ClusterParams &prm, const CMM &M, int g, int gtid) {
     const int D = prm.D, N = prm.N;
-    for (int i = gtid; i < N * D; i += CL_GT) M.zs[(i / D) * SD + (i % D)] = __ldg(prm.z_mm + i);
-    CT_SYNC(g);
-    double *mean = M.dmean, *sq = M.dmean + SD;
-    cmm_reduce(D, N, [](int q) { return CmmQ{q, -1}; }, M.zs, nullptr, nullptr, nullptr, M.part, mean, g, gtid);
-    if (gtid < D) mean[gtid] = mean[gtid] / N;
-    CT_SYNC(g);
-    cmm_reduce(D, N, [](int q) { return CmmQ{q, q}; }, M.zs, mean, M.zs, mean, M.part, sq, g, gtid);
+    cmm_init_qtab(M, D, gtid);
     if (gtid < D) {
-        M.st[SD + gtid] = (float)mean[gtid];
-        M.st[2 * SD + gtid] = 1.f / sqrtf((float)(sq[gtid] / (double)(N - 1)));
+        double a = 0.0;
+        for (int n = 0; n < N; ++n) a += (double)__ldg(prm.z_mm + (size_t)n * D + gtid);
+        const double mean = a / N;
+        double b = 0.0;
+        for (int n = 0; n < N; ++n) {
+            const double d = (double)__ldg(prm.z_mm + (size_t)n * D + gtid) - mean;
+            b += d * d;
+        }
+        M.st[SD + gtid] = (float)mean;
+        M.st[2 * SD + gtid] = 1.f / sqrtf((float)(b / (double)(N - 1)));
     }
     CT_SYNC(g);
 }
 
-// ---- forward: the tile's pre-matching states (role-B registers) -> the matched ones.  Called by all 128 threads of
-//      the tile; M.zrow[slot][j] holds z_mm[(t + n) mod N][j] of the tile's slots. ----
-__device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM &M, int g, int gtid, int t, unsigned target,
-                                            bool roleB, int b_p, int b_d, int b_n, bool b_own, float &s_reg, bool leader) {
-    const int D = prm.D, N = prm.N;
-    float *s1pre = const_cast<float *>(prm.s1pre);
-    if (roleB && b_own) s1pre[((size_t)t * N + b_n) * D + b_d] = s_reg;
-    cmm_barrier(prm.mmctr, target, g, gtid);
-    for (int i = gtid; i < N * D; i += CL_GT) {
-        const int n = i / D, d = i - n * D;
-        M.xs[n * SD + d] = __ldcg(s1pre + (size_t)t * N * D + i);
-    }
-    CT_SYNC(g);
-    double *sum = M.dmean;
-    cmm_reduce(D, N, [](int q) { return CmmQ{q, -1}; }, M.xs, nullptr, nullptr, nullptr, M.part, sum, g, gtid);
-    if (gtid < D) sum[gtid] = sum[gtid] / N;
-    CT_SYNC(g);
-    // lower triangle of the centred scatter, quantity q = i (i + 1) / 2 + j
-    const int nq = D * (D + 1) / 2;
-    double *cov = reinterpret_cast<double *>(M.X);       // SD*SD floats = 128 doubles >= 120
-    cmm_reduce(nq, N, [](int q) { return cmm_tri(q); }, M.xs, sum, M.xs, sum, M.part, cov, g, gtid);
-    for (int q = gtid; q < nq; q += CL_GT) {
-        const CmmQ s = cmm_tri(q);
-        // unbiased covariance + jitter (rollout.py:24), handed to the fp32 Cholesky
-        M.A[s.i * SD + s.j] = (float)(cov[q] / (double)(N - 1)) + (s.i == s.j ? 1e-12f : 0.f);
-    }
-    if (gtid < D) M.st[gtid] = (float)sum[gtid];
-    CT_SYNC(g);
-    if (gtid == 0) {
-        bool ok = true;
-        for (int i = 0; i < D; ++i) {
-            for (int j = 0; j <= i; ++j) {
-                float s = M.A[i * SD + j];
-                for (int k = 0; k < j; ++k) s -= M.L[i * SD + k] * M.L[j * SD + k];
-                if (i == j) {
-                    if (!(s > 0.f)) { ok = false; s = 1.f; }
-                    M.L[i * SD + i] = sqrtf(s);
-                } else {
-                    M.L[i * SD + j] = s / M.L[j * SD + j];
-                }
+// Cholesky factor of the D x D matrix A (lower triangle), fp32 like the reference's, by one thread: in registers for
+// D <= DD, else through shared memory
+template <int DD>
+__device__ __forceinline__ bool cmm_cholesky_reg(const CMM &M, int D) {
+    float a[DD][DD];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < DD; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i][j] = (i < D) ? M.A[i * SD + j] : (i == j ? 1.f : 0.f);
+#pragma unroll
+    for (int i = 0; i < DD; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = a[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k];
+            if (i == j) {
+                if (!(s > 0.f)) { ok = false; s = 1.f; }
+                a[i][i] = sqrtf(s);
+            } else {
+                a[i][j] = s / a[j][j];
             }
-            for (int j = i + 1; j < D; ++j) M.L[i * SD + j] = 0.f;
         }
-        if (!ok && prm.status) atomicCAS(prm.status, 0, 1 + t);
+    }
+#pragma unroll
+    for (int i = 0; i < DD; ++i)
+#pragma unroll
+        for (int j = 0; j < DD; ++j)
+            if (i < D && j < D) M.L[i * SD + j] = j <= i ? a[i][j] : 0.f;
+    return ok;
+}
+__device__ __forceinline__ bool cmm_cholesky(const CMM &M, int D) {
+    if (D <= 4) return cmm_cholesky_reg<4>(M, D);
+    bool ok = true;
+#pragma unroll 1
+    for (int i = 0; i < D; ++i) {
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            float s = M.A[i * SD + j];
+#pragma unroll 1
+            for (int k = 0; k < j; ++k) s -= M.L[i * SD + k] * M.L[j * SD + k];
+            if (i == j) {
+                if (!(s > 0.f)) { ok = false; s = 1.f; }
+                M.L[i * SD + i] = sqrtf(s);
+            } else {
+                M.L[i * SD + j] = s / M.L[j * SD + j];
+            }
+        }
+#pragma unroll 1
+        for (int j = i + 1; j < D; ++j) M.L[i * SD + j] = 0.f;
+    }
+    return ok;
+}
+
+// ---- forward: the tile's pre-matching states (role-B registers) -> the matched ones.  M.zrow[slot][j] holds
+//      z_mm[(t + n) mod N][j] of the tile's slots; nvg = particles of this tile. ----
+__device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM &M, int g, int gtid, int rank, int t, unsigned target,
+                                            int nvg, bool roleB, int b_p, int b_d, int b_n, bool b_own, float &s_reg, bool leader,
+                                            long long *dbgp) {
+#define CMM_MARK(i) do { if (dbgp && (threadIdx.x & 31) == 0) dbgp[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+    const int D = prm.D, N = prm.N;
+    const int nq = D + D * (D + 1) / 2;
+    const int ntiles = 2 * (int)cmm_clusters(N, prm.PG);
+    float *s1pre = const_cast<float *>(prm.s1pre);
+    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
+    if (roleB) {
+        M.xrow[b_p * SD + b_d] = s_reg;
+        if (b_own) s1pre[((size_t)t * N + b_n) * D + b_d] = s_reg;
     }
     CT_SYNC(g);
-    if (leader) {       // (m, L, z statistics) of this step for the reverse sweep
+    // record of this tile (raw moments in double: products of two floats are exact): sum x_q, sum x_i x_j
+    if (rank == 0 && gtid < nq && !(prm.mm_dbg & 64)) {
+        double a = 0.0;
+        if (gtid < D) {
+            for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + gtid];
+        } else {
+            const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
+            for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + i] * (double)M.xrow[p * SD + j];
+        }
+        rec[(size_t)(2 * (blockIdx.x / prm.C) + g) * CMM_NQ + gtid] = a;
+    }
+    CMM_MARK(0);
+    if (!(prm.mm_dbg & 1)) cmm_barrier(prm.mmctr, target, rank);
+    CMM_MARK(1);
+    if (!(prm.mm_dbg & 8)) cmm_combine(M, rec, ntiles, nq, g, gtid);
+    if (gtid < D) {
+        M.dmean[gtid] = M.red[gtid] / N;
+        M.st[gtid] = (float)M.dmean[gtid];
+    }
+    CT_SYNC(g);
+    CMM_MARK(2);
+    if (gtid >= D && gtid < nq) {
+        const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
+        // unbiased covariance + jitter (rollout.py:24), handed to the fp32 Cholesky
+        const double c = (M.red[gtid] - (double)N * M.dmean[i] * M.dmean[j]) / (double)(N - 1);
+        M.A[i * SD + j] = (float)c + (i == j ? 1e-12f : 0.f);
+    }
+    CT_SYNC(g);
+    CMM_MARK(3);
+    if (gtid == 0) {
+        const bool ok = cmm_cholesky(M, D);
+        if (!ok && prm.status && !prm.mm_dbg) atomicCAS(prm.status, 0, 1 + t);
+    }
+    CMM_MARK(5);
+    CT_SYNC(g);
+    CMM_MARK(6);
+    if (leader && !(prm.mm_dbg & 16)) {       // (m, L, z statistics) of this step for the reverse sweep
         float *ms = prm.mmstat + (size_t)t * (3 * SD + SD * SD);
         for (int i = gtid; i < 3 * SD; i += CL_GT) ms[i] = M.st[i];
         for (int i = gtid; i < SD * SD; i += CL_GT) ms[3 * SD + i] = M.L[i];
     }
-    if (roleB) {
+    if (roleB && !(prm.mm_dbg & 32)) {
         float x = M.st[b_d];
         for (int j = 0; j <= b_d; ++j)
             x = fmaf((M.zrow[b_p * SD + j] - M.st[SD + j]) * M.st[2 * SD + j], M.L[b_d * SD + j], x);
         s_reg = x;
     }
+    CMM_MARK(4);
+#undef CMM_MARK
 }
 
 // ---- reverse: the cotangent of the matched particles (gs[slot][d], in place) -> the cotangent of the pre-matching
-//      ones.  cmm_backward_prefetch (before the barrier, constant inputs): standardised z rows of ALL particles,
-//      (m, L) of step t, the pre-matching states of the tile's slots. ----
+//      ones.  cmm_backward_prefetch (constant inputs of the step): (m, L) of step t, the standardised z rows and the
+//      pre-matching states of the tile's slots. ----
 __device__ __forceinline__ void cmm_backward_prefetch(const ClusterParams &prm, const CMM &M, int g, int gtid, int t, bool roleB,
                                                       int b_p, int b_d, int b_n) {
     const int D = prm.D, N = prm.N;
     const float *ms = prm.mmstat + (size_t)t * (3 * SD + SD * SD);
     for (int i = gtid; i < D; i += CL_GT) M.st[i] = __ldcg(ms + i);
     for (int i = gtid; i < SD * SD; i += CL_GT) M.L[i] = __ldcg(ms + 3 * SD + i);
-    for (int i = gtid; i < N * D; i += CL_GT) {
-        const int n = i / D, j = i - n * D;
-        int r = t + n;
+    if (roleB) {
+        int r = t + b_n;
         r -= (r / N) * N;
-        M.zs[n * SD + j] = (__ldg(prm.z_mm + (size_t)r * D + j) - M.st[SD + j]) * M.st[2 * SD + j];
+        M.zrow[b_p * SD + b_d] = (__ldg(prm.z_mm + (size_t)r * D + b_d) - M.st[SD + b_d]) * M.st[2 * SD + b_d];
+        M.xrow[b_p * SD + b_d] = __ldcg(prm.s1pre + ((size_t)t * N + b_n) * D + b_d);
     }
-    if (roleB) M.zrow[b_p * SD + b_d] = __ldcg(prm.s1pre + ((size_t)t * N + b_n) * D + b_d);
 }
-__device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM &M, int g, int gtid, int t, unsigned target,
-                                             float *gs, bool roleB, int b_p, int b_d, int b_n, bool b_own) {
+__device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM &M, int g, int gtid, int rank, int t, unsigned target,
+                                             int nvg, float *gs, bool roleB, int b_p, int b_d) {
     const int D = prm.D, N = prm.N;
-    float *gbuf = prm.gbuf + (size_t)(t & 1) * N * SD;
-    if (roleB && b_own) gbuf[(size_t)b_n * SD + b_d] = gs[b_p * SD + b_d];
-    cmm_barrier(prm.mmctr, target, g, gtid);
-    for (int i = gtid; i < N * D; i += CL_GT) {
-        const int n = i / D, d = i - n * D;
-        M.xs[n * SD + d] = __ldcg(gbuf + (size_t)n * SD + d);
-    }
-    CT_SYNC(g);
-    // dm = sum_n g_n (q < D);  dL = tril(sum_n g_n zhat_n^T) (q = D + i (i + 1) / 2 + j)
     const int nq = D + D * (D + 1) / 2;
-    double *acc = reinterpret_cast<double *>(M.A);       // A and X are contiguous: 2 * SD*SD floats = 256 doubles >= 135
-    cmm_reduce(nq, N, [D](int q) {
-        if (q < D) return CmmQ{q, -1};
-        return cmm_tri(q - D);
-    }, M.xs, nullptr, M.zs, nullptr, M.part, acc, g, gtid);
-    // stage dL in Sb (A / X are overwritten next), dm in dm
+    const int ntiles = 2 * (int)cmm_clusters(N, prm.PG);
+    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
+    CT_SYNC(g);         // the prefetched rows are in place
+    // record of this tile: dm = sum_p g_p (q < D);  dL = tril(sum_p g_p zhat_p^T) (q = D + i (i + 1) / 2 + j)
+    if (rank == 0 && gtid < nq) {
+        double a = 0.0;
+        if (gtid < D) {
+            for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + gtid];
+        } else {
+            const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
+            for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + i] * (double)M.zrow[p * SD + j];
+        }
+        rec[(size_t)(2 * (blockIdx.x / prm.C) + g) * CMM_NQ + gtid] = a;
+    }
+    cmm_barrier(prm.mmctr, target, rank);
+    cmm_combine(M, rec, ntiles, nq, g, gtid);
     for (int q = gtid; q < nq; q += CL_GT) {
         if (q < D) {
-            M.dm[q] = (float)acc[q];
+            M.dm[q] = (float)M.red[q];
         } else {
-            const CmmQ s = cmm_tri(q - D);
-            M.Sb[s.i * SD + s.j] = (float)acc[q];
+            const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
+            M.Sb[i * SD + j] = (float)M.red[q];   // dL staged in Sb (rewritten below, after its last use)
         }
     }
     CT_SYNC(g);
@@ -261,7 +339,7 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
     if (roleB) {
         float a = 0.f;
         for (int j = 0; j < D; ++j)
-            a = fmaf(0.5f * (M.Sb[b_d * SD + j] + M.Sb[j * SD + b_d]), M.zrow[b_p * SD + j] - M.st[j], a);
+            a = fmaf(0.5f * (M.Sb[b_d * SD + j] + M.Sb[j * SD + b_d]), M.xrow[b_p * SD + j] - M.st[j], a);
         gs[b_p * SD + b_d] = M.dm[b_d] / (float)N + (2.f / (float)(N - 1)) * a;
     }
     CT_SYNC(g);

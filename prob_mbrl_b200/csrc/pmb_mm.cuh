@@ -60,6 +60,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &epoch) {
         } while (v < epoch);
         __threadfence();
     }
+    __syncwarp();       // the polling lane rejoins its warp before the (aligned) barrier
     CTA_SYNC();
 }
 

@@ -11,7 +11,7 @@ n = bench.CONFIGS[cfg][5]
 dyn, pol, x0, H, mm = bench.build_workload(cfg, n, "cuda")
 opt = torch.optim.Adam(pol.parameters(), 1e-4)
 g_r = torch.full((H, n), -1.0 / (H * n), device="cuda")
-eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0)
+eng = pm.FusedIteration(dyn, pol, x0.cuda(), H, opt, g_r, 1.0, mm)
 eng.step(x0.cuda()); eng.step(x0.cuda())
 dbg = torch.zeros(512, dtype=torch.int64, device="cuda")
 ptr = dbg.data_ptr()
@@ -44,7 +44,10 @@ if os.environ.get("PMB_STREAM_MODE", "0") in ("0", "3"):
              4: "squash role done", 5: "dyn thin done", 6: "dyn wide accum done", 15: "  dyn reduce+epilogue done",
              13: "  dyn butterfly+gather done", 7: "dyn epilogue+narrow+send done", 21: "  dyn exchange arrived",
              8: "density role done"}
-    order = [0, 1, 2, 11, 9, 3, 20, 4, 5, 6, 15, 13, 7, 21, 8]
+    names.update({24: "mm: tile record written", 25: "mm: grid barrier passed", 26: "mm: records combined, mean",
+                  27: "mm: covariance done", 29: "mm: Cholesky done (thread 0)", 30: "mm: tile barrier passed",
+                  28: "mm: statistics stored, resampled"})
+    order = [0, 1, 2, 11, 9, 3, 20, 4, 5, 6, 15, 13, 7, 21, 24, 25, 26, 27, 29, 30, 28, 8]
     t0 = min(x for x in d[0:8] if x)
     for k in order:
         v = [x - t0 if x else -1 for x in d[8 * k: 8 * k + 8]]

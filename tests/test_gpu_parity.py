@@ -190,7 +190,10 @@ def test_planner_runs_the_bench_workload_on_the_cluster_resident_sweeps(monkeypa
     assert info["variant"] == 1 and info["cluster_size"] == 8
     assert info["ctas"] <= 148 and info["ctas"] // 8 * info["particles_per_group"] >= 100
     mm = _lib.make_problem(o, 100, int(g["H"]), mm_states=True, z_mm=torch.zeros(500, o.D, device="cuda"))[0]
-    assert _lib.describe_plan(mm, _lib.make_tuning())["variant"] == 0      # moment matching: streaming sweeps
+    info = _lib.describe_plan(mm, _lib.make_tuning())      # moment matching (c3): cluster-resident as well, every cluster
+    assert info["variant"] == 1 and info["ctas"] <= 148     # co-resident (the per-step exchange is a grid-wide barrier)
+    assert info["ctas"] // 8 * info["particles_per_group"] >= 100
+    assert _lib.describe_plan(mm, _lib.make_tuning(stream_mode=2))["variant"] == 0      # streaming sweeps on request
     info = _lib.describe_plan(mm, _lib.make_tuning(stream_mode=4))          # ... or, opt-in, the tensor-core cluster sweeps
     assert info["variant"] == 2 and info["cluster_size"] == 16 and info["ctas"] == 16
 
