@@ -30,6 +30,7 @@ struct CMM {
     float *dm;               // [SD]
     float *zrow;             // [4][SD] z rows of the tile's slots (forward: raw; reverse: standardised)
     float *xrow;             // [4][SD] pre-matching states of the tile's slots
+    float *rinv;             // [SD] reciprocal pivots of L
     __device__ __forceinline__ void carve(float *base) {
         stage = reinterpret_cast<double *>(base);
         red = stage + CMM_TILES * 16;
@@ -43,6 +44,7 @@ struct CMM {
         dm = Sb + SD * SD;
         zrow = dm + SD;
         xrow = zrow + CL_TS * SD;
+        rinv = xrow + CL_TS * SD;
     }
 };
 
@@ -140,9 +142,12 @@ __device__ __forceinline__ void cmm_z_statistics(const ClusterParams &prm, const
     CT_SYNC(g);
 }
 
-// Cholesky factor of the D x D matrix A (lower triangle), fp32 like the reference's, by one thread with compact loops.
-// Measured for D = 4 (cycles per step): this version 4.4 k, fully unrolled in registers 4.4 k, one warp with lane = row
-// and shuffles 6.2 k -- short dependent scalar code runs at ~10 cycles per instruction whatever its form.
+// Cholesky factor of the D x D matrix A (lower triangle) in fp32, by one thread with compact loops.  Short dependent
+// scalar code runs at ~10 cycles per instruction here (measured for D = 4 with IEEE sqrtf and divisions: 4.4 k cycles per
+// step as loops, 4.4 k fully unrolled in registers, 6.2 k as one warp with lane = row and shuffles), so the instruction
+// count is what matters: one rsqrtf per pivot (MUFU.RSQ, <= 2 ulp) replaces the IEEE square root and the column's
+// divisions -- a deliberate deviation of a few ulp in L, the size of the reordering error between any two fp32
+// Cholesky implementations.
 __device__ __forceinline__ bool cmm_cholesky(const CMM &M, int D) {
     bool ok = true;
 #pragma unroll 1
@@ -154,9 +159,11 @@ __device__ __forceinline__ bool cmm_cholesky(const CMM &M, int D) {
             for (int k = 0; k < j; ++k) s -= M.L[i * SD + k] * M.L[j * SD + k];
             if (i == j) {
                 if (!(s > 0.f)) { ok = false; s = 1.f; }
-                M.L[i * SD + i] = sqrtf(s);
+                const float r = rsqrtf(s);
+                M.L[i * SD + i] = s * r;
+                M.rinv[i] = r;                      // 1 / L_ii for the rest of the column
             } else {
-                M.L[i * SD + j] = s / M.L[j * SD + j];
+                M.L[i * SD + j] = s * M.rinv[j];
             }
         }
 #pragma unroll 1
@@ -276,6 +283,7 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
             M.Sb[i * SD + j] = (float)M.red[q];   // dL staged in Sb (rewritten below, after its last use)
         }
     }
+    if (gtid < D) M.rinv[gtid] = 1.f / M.L[gtid * SD + gtid];
     CT_SYNC(g);
     // A = Phi(L^T dL): lower triangle, diagonal halved
     for (int idx = gtid; idx < D * D; idx += CL_GT) {
@@ -288,23 +296,27 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
         M.A[i * SD + j] = a;
     }
     CT_SYNC(g);
-    // X = L^-T A  (back substitution, one column per thread)
+    // X = L^-T A  (back substitution, one column per thread; reciprocal pivots M.rinv formed once per step above)
     if (gtid < D) {
         const int j = gtid;
+#pragma unroll 1
         for (int r = D - 1; r >= 0; --r) {
             float s = M.A[r * SD + j];
+#pragma unroll 1
             for (int k = r + 1; k < D; ++k) s -= M.L[k * SD + r] * M.X[k * SD + j];
-            M.X[r * SD + j] = s / M.L[r * SD + r];
+            M.X[r * SD + j] = s * M.rinv[r];
         }
     }
     CT_SYNC(g);
     // Sb = X L^-1  (one row per thread)
     if (gtid < D) {
         const int i = gtid;
+#pragma unroll 1
         for (int c = D - 1; c >= 0; --c) {
             float s = M.X[i * SD + c];
+#pragma unroll 1
             for (int k = c + 1; k < D; ++k) s -= M.Sb[i * SD + k] * M.L[k * SD + c];
-            M.Sb[i * SD + c] = s / M.L[c * SD + c];
+            M.Sb[i * SD + c] = s * M.rinv[c];
         }
     }
     CT_SYNC(g);
