@@ -409,8 +409,9 @@ class Harness:
         peak = peaks["bf16_tflops"]
         plan = _lib.describe_plan(eng.prob, eng.tune)       # sweep variant + launch geometry the planner chose
         ctas = plan["ctas"]
-        vname = {0: "streaming", 1: "cluster-resident", 2: "tensor-core cluster"}.get(plan["variant"], str(plan["variant"]))
-        kprefix = {0: "rollout_", 1: "cluster_", 2: "tc_"}.get(plan["variant"], "")
+        vname = {0: "streaming", 1: "cluster-resident", 2: "tensor-core cluster",
+                 3: "wide cluster-resident"}.get(plan["variant"], str(plan["variant"]))
+        kprefix = {0: "rollout_", 1: "cluster_", 2: "tc_", 3: "cw_"}.get(plan["variant"], "")
         kname = kprefix + ("bwd_kernel" if dom == "bwd_sweep_ms" else "fwd_kernel")
         traffic = None
         for tname in ("r02_dram_traffic.json", "r01_dram_traffic.json"):   # dram__bytes_read+write per launch, from
@@ -422,6 +423,7 @@ class Harness:
                 if traffic is not None:
                     break
         sms = min(ctas, 148)
+        simt_peak = sms * 128 * 2 * 1.9e9 / 1e12         # fp32 FMA lanes of the occupied SMs at the nominal boost clock
         return {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16 burst (kernel timed alone)" % peaks["source"], "traffic": traffic,
@@ -431,9 +433,10 @@ class Harness:
                            "smem_bytes_per_cta": plan["smem_bwd_bytes" if dom == "bwd_sweep_ms" else "smem_fwd_bytes"]},
                 "sms_occupied": sms,
                 "frac_of_occupied_sm_peak": achieved / (peak * sms / 148.0),
+                "frac_of_fp32_simt_peak_of_occupied_sms": achieved / simt_peak,
                 "arithmetic": ("3xTF32 split on tcgen05 (fp32 accumulate in TMEM) for the hidden x hidden layers, fp32 FFMA elsewhere"
                                if plan["variant"] == 2 else "fp32 FFMA2 (CUDA cores)")
-                              + "; fp32 SIMT peak of the occupied SMs = %.2f TFLOP/s" % (sms * 128 * 2 * 1.9e9 / 1e12)}
+                              + "; fp32 SIMT peak of the occupied SMs = %.2f TFLOP/s" % simt_peak}
 
     def launches_per_iter(self, w):
         from prob_mbrl_b200 import _lib

@@ -34,6 +34,10 @@ launch_summary(os.path.join(G, "launches.csv"), os.path.join(out, tag + "_launch
                "ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python scripts/profile_target.py c2 3",
                "(3 un-graphed fused iterations of the bench workload; per-launch times are cold-cache and serialised)")
 shutil.copy(os.path.join(G, "launches.csv"), os.path.join(out, tag + "_launches.csv"))
+if os.path.exists(os.path.join(G, "launches_c3.csv")):
+    launch_summary(os.path.join(G, "launches_c3.csv"), os.path.join(out, tag + "_launches_c3_summary.txt"),
+                   "ncu --metrics gpu__time_duration.sum --clock-control none -c 60 python scripts/profile_target.py c3 2",
+                   "(c3: moment matching on the cluster-resident sweeps; the cooperative cluster launches are listed when ncu can time them)")
 if os.path.exists(os.path.join(G, "launches_fit.csv")):
     launch_summary(os.path.join(G, "launches_fit.csv"), os.path.join(out, tag + "_launches_fit_summary.txt"),
                    "ncu --metrics gpu__time_duration.sum --clock-control none -c 120 python scripts/fit_target.py 4",
@@ -56,8 +60,8 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__pcsamp_warps_issue_stalled_membar", "smsp__pcsamp_warps_issue_stalled_sleeping"]
 traffic = {}
 for cfg, rep, cmd in (("c2", "prof_c2", "-k 'regex:cluster_(fwd|bwd)_kernel' -s 2 -c 2 python scripts/profile_target.py c2 2"),
-                      ("c3", "prof_c3", "-k 'regex:rollout_(fwd|bwd)' -s 2 -c 2 python scripts/profile_target.py c3 2"),
-                      ("c5", "prof_c5", "-k 'regex:rollout_(fwd|bwd)' -s 2 -c 2 python scripts/profile_target.py c5 2"),
+                      ("c4", "prof_c4", "-k 'regex:rollout_(fwd|bwd)' -s 2 -c 2 python scripts/profile_target.py c4 2"),
+                      ("c5", "prof_c5", "-k 'regex:cw_(fwd|bwd)_kernel' -s 2 -c 2 python scripts/profile_target.py c5 2"),
                       ("c5tc", "prof_c5tc", "PMB_STREAM_MODE=4 ... -k 'regex:tc_(fwd|bwd)_kernel' -s 2 -c 2 python scripts/profile_target.py c5 2")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
