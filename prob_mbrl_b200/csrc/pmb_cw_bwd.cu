@@ -309,6 +309,8 @@ cudaError_t launch_cw_bwd(const ClusterParams &prm, int nclusters, cudaStream_t 
         return cudaLaunchKernelEx(&cfg, cw_bwd_kernel<PP, DD>, prm);                                                    \
     }
     PMB_CW_BWD(2, 8)
+    PMB_CW_BWD(2, 12)
+    PMB_CW_BWD(4, 16)
     PMB_CW_BWD(8, 16)
     PMB_CW_BWD(16, 16)
 #undef PMB_CW_BWD

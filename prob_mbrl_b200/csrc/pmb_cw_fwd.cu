@@ -355,7 +355,9 @@ cudaError_t launch_cw_fwd(const ClusterParams &prm, int nclusters, cudaStream_t 
         return cudaLaunchKernelEx(&cfg, cw_fwd_kernel<PP, DD>, prm);                               \
     }
     PMB_CW_FWD(4, 6)
+    PMB_CW_FWD(6, 6)
     PMB_CW_FWD(8, 8)
+    PMB_CW_FWD(8, 12)
     PMB_CW_FWD(16, 16)
 #undef PMB_CW_FWD
     return cudaErrorInvalidValue;
