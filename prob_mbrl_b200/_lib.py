@@ -263,7 +263,7 @@ def make_problem(ops: RolloutOperands, N, H, mm_states=False, mm_rewards=False, 
 
 def make_tuning(particles_per_cta=0, stream_mode=0, wgrad_splits=0, phases=0):
     t = PmbTuning()
-    t.reserved[0] = int(phases) | (int(os.environ.get("PMB_MM_DBG", "0")) << 8)     # bits 8+: timing experiments
+    t.reserved[0] = int(phases)
     t.reserved[1] = int(os.environ.get("PMB_STAGES", "0"))
     t.reserved[4] = int(os.environ.get("PMB_WGRAD_UMMA", "0"))
     t.particles_per_cta = int(particles_per_cta or int(os.environ.get("PMB_PARTICLES_PER_CTA", "0")))

@@ -396,7 +396,6 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         memset(&P, 0, sizeof(P));
         P.N = S.N; P.H = S.H; P.D = S.D; P.U = S.U; P.C = C;
         P.mm_states = p->mm_states; P.z_mm = p->z_mm;
-        P.mm_dbg = tune ? (tune->reserved[0] >> 8) : 0;
         cluster_net(S.pol, pass == 1, true, C, P.pol);
         cluster_net(S.dyn, pass == 1, false, C, P.dyn);
         P.act_scale = S.act_scale; P.act_bias = S.act_bias; P.mx = S.mx; P.iSx = S.iSx; P.my = S.my; P.Sy = S.Sy;

@@ -80,7 +80,6 @@ struct ClusterParams {
     double *mmrec;              // [2][tiles][CMM_NQ] per-tile records of a step (double-buffered by step parity)
     int *status;                // forward: 1 + first step whose covariance was not positive definite
     int off_mm;                 // shared memory: two CMM blocks (one per particle tile)
-    int mm_dbg;                 // timing experiments (wrong results): 1 no exchange, 2 no statistics, 4 no Cholesky
     unsigned *g1, *g2;          // wide cluster-resident sweeps (pmb_cw.cuh): ReLU/dropout gate bit words of hidden 0 / 1
     int ncl;                    // ... clusters of the launch
     int off_cst, off_xa, off_xb, off_act, off_red, off_inbox, off_misc;

@@ -119,7 +119,8 @@ __device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, int g, i
     const int nq = prm.D + prm.D * (prm.D + 1) / 2;
     const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG);
     double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
-    if (rank == 0 && gtid < nq) rec[(2 * (blockIdx.x / prm.C) + g) * nq + gtid] = 0.0;
+    if (rank == 0)
+        for (int q = gtid; q < nq; q += CL_GT) rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = 0.0;
     cmm_barrier(prm.mmctr, target, rank);
 }
 
@@ -189,47 +190,49 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
     }
     CT_SYNC(g);
     // record of this tile (raw moments in double: products of two floats are exact): sum x_q, sum x_i x_j
-    if (rank == 0 && gtid < nq && !(prm.mm_dbg & 64)) {
-        double a = 0.0;
-        if (gtid < D) {
-            for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + gtid];
-        } else {
-            const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
-            for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + i] * (double)M.xrow[p * SD + j];
+    if (rank == 0) {
+        for (int q = gtid; q < nq; q += CL_GT) {        // nq <= 135: one or two quantities per thread
+            double a = 0.0;
+            if (q < D) {
+                for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + q];
+            } else {
+                const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
+                for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + i] * (double)M.xrow[p * SD + j];
+            }
+            rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = a;
         }
-        rec[(2 * (blockIdx.x / prm.C) + g) * nq + gtid] = a;
     }
     CMM_MARK(0);
-    if (!(prm.mm_dbg & 1)) cmm_barrier(prm.mmctr, target, rank);
+    cmm_barrier(prm.mmctr, target, rank);
     CMM_MARK(1);
-    if (!(prm.mm_dbg & 8)) cmm_combine(M, rec, ntiles, nq, g, gtid);
+    cmm_combine(M, rec, ntiles, nq, g, gtid);
     if (gtid < D) {
         M.dmean[gtid] = M.red[gtid] / N;
         M.st[gtid] = (float)M.dmean[gtid];
     }
     CT_SYNC(g);
     CMM_MARK(2);
-    if (gtid >= D && gtid < nq) {
-        const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
+    for (int q = D + gtid; q < nq; q += CL_GT) {
+        const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
         // unbiased covariance + jitter (rollout.py:24), handed to the fp32 Cholesky
-        const double c = (M.red[gtid] - (double)N * M.dmean[i] * M.dmean[j]) / (double)(N - 1);
+        const double c = (M.red[q] - (double)N * M.dmean[i] * M.dmean[j]) / (double)(N - 1);
         M.A[i * SD + j] = (float)c + (i == j ? 1e-12f : 0.f);
     }
     CT_SYNC(g);
     CMM_MARK(3);
     if (gtid == 0) {
         const bool ok = cmm_cholesky(M, D);
-        if (!ok && prm.status && !prm.mm_dbg) atomicCAS(prm.status, 0, 1 + t);
+        if (!ok && prm.status) atomicCAS(prm.status, 0, 1 + t);
     }
     CMM_MARK(5);
     CT_SYNC(g);
     CMM_MARK(6);
-    if (leader && !(prm.mm_dbg & 16)) {       // (m, L, z statistics) of this step for the reverse sweep
+    if (leader) {       // (m, L, z statistics) of this step for the reverse sweep
         float *ms = prm.mmstat + (size_t)t * (3 * SD + SD * SD);
         for (int i = gtid; i < 3 * SD; i += CL_GT) ms[i] = M.st[i];
         for (int i = gtid; i < SD * SD; i += CL_GT) ms[3 * SD + i] = M.L[i];
     }
-    if (roleB && !(prm.mm_dbg & 32)) {
+    if (roleB) {
         float x = M.st[b_d];
         for (int j = 0; j <= b_d; ++j)
             x = fmaf((M.zrow[b_p * SD + j] - M.st[SD + j]) * M.st[2 * SD + j], M.L[b_d * SD + j], x);
@@ -263,15 +266,17 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
     double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
     CT_SYNC(g);         // the prefetched rows are in place
     // record of this tile: dm = sum_p g_p (q < D);  dL = tril(sum_p g_p zhat_p^T) (q = D + i (i + 1) / 2 + j)
-    if (rank == 0 && gtid < nq) {
-        double a = 0.0;
-        if (gtid < D) {
-            for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + gtid];
-        } else {
-            const int ij = M.qtab[gtid - D], i = ij >> 8, j = ij & 255;
-            for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + i] * (double)M.zrow[p * SD + j];
+    if (rank == 0) {
+        for (int q = gtid; q < nq; q += CL_GT) {
+            double a = 0.0;
+            if (q < D) {
+                for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + q];
+            } else {
+                const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
+                for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + i] * (double)M.zrow[p * SD + j];
+            }
+            rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = a;
         }
-        rec[(2 * (blockIdx.x / prm.C) + g) * nq + gtid] = a;
     }
     cmm_barrier(prm.mmctr, target, rank);
     cmm_combine(M, rec, ntiles, nq, g, gtid);

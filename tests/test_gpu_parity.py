@@ -502,6 +502,35 @@ def test_moment_matching_single_flag_matches_oracle(which, sweeps):
     assert gu.rel_l2(r["dx0"], X64) < max(2e-3, 3 * gu.rel_l2(X32, X64))
 
 
+@pytest.mark.parametrize("D,U,N", [(8, 2, 64), (7, 2, 33)])
+def test_moment_matching_many_state_dims_cluster_equals_streaming(D, U, N):
+    """State dimensions beyond the fixtures' (up to the cluster sweeps' limit of 2 D <= 16 raw outputs) and ragged
+    particle counts: the cluster-resident sweeps with the in-kernel matching against the streaming sweeps and the fp64
+    oracle."""
+    H = 5
+    kw = dict(D=D, U=U, hid=(24, 20), N=N)
+    ops, x0 = gu.synthetic_ops(**kw)
+    ops64, x064 = gu.synthetic_ops(dtype=torch.float64, **kw)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(H + N, D, generator=g, dtype=torch.float64)
+    zz = z[:N] - z[:N].mean(0, keepdim=True)                      # whitened rows: a bounded matched rollout (SURVEY 8d)
+    L = torch.linalg.cholesky(zz.T @ zz / (N - 1))
+    z[:N] = torch.linalg.solve_triangular(L, zz.T, upper=False).T
+    z_rr = torch.randn(H + N, 1, generator=g, dtype=torch.float64)
+    mm = dict(mm_states=True, mm_rewards=False, mm_groups=None, z_mm=z.float(), z_rr=z_rr.float())
+    a = _run(ops, x0, H, mm=mm, env=SWEEPS["ring"])
+    b = _run(ops, x0, H, mm=mm, env=SWEEPS["cluster"])
+    assert a["status"] == 0 and b["status"] == 0
+    ref = orc.loss_and_grads(ops64, x064, H, mm_states=True, mm_rewards=False, z_mm=z, z_rr=z_rr)
+    keys = orc.policy_param_keys(ops64)
+    S64 = torch.stack(ref["states"])
+    for r in (a, b):
+        assert (r["S"].double() - S64).abs().max() < 2e-4
+        assert gu.rel_l2(r["grads"], [ref["grads"][k] for k in keys]) < 2e-3
+        assert gu.rel_l2(r["dx0"], ref["dx0"]) < 2e-3
+    assert (a["S"] - b["S"]).abs().max() < 1e-4
+
+
 def test_moment_matching_rank_deficient_raises_runtime_error():
     """8 particles per group in 8 state dims: the covariance is singular; the reference raises from
     cholesky() (RuntimeError) at step 0 -- the fused path must report the same way."""
