@@ -65,8 +65,10 @@ __device__ __forceinline__ void cmm_barrier(unsigned *ctr, unsigned target, int 
             if (++spins > (1u << 26)) __trap();
         } while (v < target);
     }
-    __syncwarp();               // the polling lane rejoins its warp before the (aligned) CTA barrier
-    __syncthreads();
+    __syncwarp();               // the polling lane rejoins its warp
+    // both particle tiles of the CTA (active or idle, i.e. from different call sites) meet on a named barrier:
+    // __syncthreads() would have to be reached through identical control flow by the whole block
+    asm volatile("barrier.sync 6, 256;" ::: "memory");
 }
 
 // lower-triangle index q = i (i + 1) / 2 + j  ->  (i, j)
