@@ -753,7 +753,11 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     pl.stream_mode = tune && tune->stream_mode ? tune->stream_mode : 2;
     if (pl.stream_mode < 1 || pl.stream_mode > 5) return fail(PMB_E_INVALID, "stream_mode must be 0..5");
     if (pl.stream_mode >= 3) pl.stream_mode = 2;
-    pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : 64;
+    // split-K slices of the batched weight gradient: 64, or as many as keep a slice <= 1024 rows (the bound up to which
+    // the tcgen05 kernel's TMEM accumulation stays inside the gradient budget; c5: 250 k rows -> 256 slices)
+    int auto_split = 64;
+    while (auto_split < 1024 && ((long long)p->H * p->N + auto_split - 1) / auto_split > 1024) auto_split <<= 1;
+    pl.nsplit = tune && tune->wgrad_splits ? tune->wgrad_splits : auto_split;
     if (pl.nsplit < 1 || pl.nsplit > 1024) return fail(PMB_E_INVALID, "wgrad_splits outside [1,1024]");
 
     Alloc wf, wb, ws;

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restr
                                                             const float *__restrict__ B, int ldb, int Nc,
                                                             long long R, int nsplit, float *__restrict__ w_out,
                                                             float *__restrict__ bias_out, long long part_stride,
-                                                            int n16) {
+                                                            int n16, int ncw) {
     extern __shared__ __align__(128) float usm[];
     __shared__ __align__(8) uint64_t stage_free[2], done_bar;
     __shared__ uint32_t tmem_base_s;
@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restr
     const int b_kb = n16 * 8;                // floats per k-block of B
     const int stage_floats = UKB * 2 * (a_kb + b_kb);
     const int ncols = Nc + (bias_out ? 1 : 0);
+    // column chunk of this CTA (blockIdx.z): global columns n_off .. n_off + ncw - 1 of [B | 1]; the accumulator holds
+    // <= 256 columns, wider layers (c4: 400, c5: 512 inputs) take several chunks
+    const int n_off = blockIdx.z * ncw;
 
     if (tid == 0) {
         mbar_init(&stage_free[0], 1);
@@ -226,7 +229,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restr
             const int n = b_n[j];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                vb[j][e] = (b_rq[j] < 2 * UKB && r + e < r1) ? (n < Nc ? __ldg(B + (r + e) * ldb + n) : ((n == Nc && bias_out) ? 1.f : 0.f)) : 0.f;
+                vb[j][e] = (b_rq[j] < 2 * UKB && r + e < r1 && n < ncw)
+                               ? (n_off + n < Nc ? __ldg(B + (r + e) * ldb + n_off + n) : ((n_off + n == Nc && bias_out) ? 1.f : 0.f))
+                               : 0.f;
         }
         if (s >= 2) mbar_wait(&stage_free[b], ((s >> 1) - 1) & 1);   // the MMAs that read this buffer retired
 #pragma unroll
@@ -269,9 +274,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restr
     float *wo = w_out + (long long)blockIdx.y * part_stride;
     float *bo = bias_out ? bias_out + (long long)blockIdx.y * part_stride : nullptr;
     if (s == 0) {           // empty slice: contribute zeros
-        for (int i = tid; i < UM * ncols; i += 256) {
-            const int m = m0 + i / ncols, n = i % ncols;
-            if (m < M) { if (n < Nc) wo[(long long)m * Nc + n] = 0.f; else bo[m] = 0.f; }
+        for (int i = tid; i < UM * ncw; i += 256) {
+            const int m = m0 + i / ncw, n = n_off + i % ncw;
+            if (m < M && n < ncols) { if (n < Nc) wo[(long long)m * Nc + n] = 0.f; else bo[m] = 0.f; }
         }
     } else {
         mbar_wait(&done_bar, 0);
@@ -288,7 +293,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_umma_kernel(const float *__restr
                 if (m < M) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int n = c + e;
+                        const int n = n_off + c + e;
+                        if (c + e >= ncw) continue;
                         if (n < Nc) wo[(long long)m * Nc + n] = __uint_as_float(v[e]);
                         else if (n == Nc && bo) bo[m] = __uint_as_float(v[e]);
                     }
@@ -316,17 +322,20 @@ cudaError_t launch_wgrad(const float *A, int lda, int M, const float *B, int ldb
                          int nsplit, float *w_part, float *bias_part, long long part_stride, cudaStream_t stream,
                          int use_umma) {
     const int ncols = Nc + (bias_part ? 1 : 0);
-    const int n16 = (ncols + 15) & ~15;
     // mode 0 (auto): tensor cores while one split-K slice accumulates <= 1024 rows in TMEM -- the tensor core's
     // fp32 accumulation rounds coarser than FFMA (measured 2.1e-6 vs 3.7e-7 gradient error at 625 rows per
     // slice against a 1e-5 budget); 1: always; 2: never.
     const bool umma = use_umma == 1 || (use_umma == 0 && (R + nsplit - 1) / nsplit <= 1024);
-    if (umma && M > 16 && Nc > 16 && n16 <= 256) {
+    if (umma && M > 16 && Nc > 16) {
+        // <= 256 accumulator columns per CTA: wider layers are cut into equal column chunks (grid.z)
+        const int nchunks = (ncols + 255) / 256;
+        const int ncw = (((ncols + nchunks - 1) / nchunks) + 7) & ~7;
+        const int n16 = (ncw + 15) & ~15;
         const int smem = 2 * UKB * 2 * (UM * 8 + n16 * 8) * (int)sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        dim3 grid((M + UM - 1) / UM, nsplit);
-        wgrad_umma_kernel<<<grid, 256, smem, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, w_part, bias_part, part_stride, n16);
+        dim3 grid((M + UM - 1) / UM, nsplit, (ncols + ncw - 1) / ncw);
+        wgrad_umma_kernel<<<grid, 256, smem, stream>>>(A, lda, M, B, ldb, Nc, R, nsplit, w_part, bias_part, part_stride, n16, ncw);
         return cudaGetLastError();
     }
     dim3 grid(((M + BM - 1) / BM) * ((ncols + BN - 1) / BN), nsplit);
