@@ -318,7 +318,7 @@ class Harness:
         row0 = sharder.row0
         x0_dev = x0_all[row0:row0 + n_per].contiguous().to(self.dev)
         g_r = torch.full((H, n_per), -1.0 / (H * n_global), device=self.dev)
-        sync = dist.allreduce_gradient if world > 1 else None
+        sync = "auto" if world > 1 else None       # peer-memory exchange (PMB_GRAD_SYNC=nccl: NCCL all-reduce)
         eng = pm.FusedIteration(dyn, pol, x0_dev, H, opt, g_r, 1.0, mm, sync)
         return dict(eng=eng, dyn=dyn, pol=pol, opt=opt, x0_all=x0_all, x0_dev=x0_dev, H=H, mm=mm, sharder=sharder,
                     n_per=n_per, n_global=n_global, world=world)

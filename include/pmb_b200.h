@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PMB_ABI_VERSION 4
+#define PMB_ABI_VERSION 5
 #define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
 #define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
 #define PMB_MAX_REWARD_ROWS 16 /* rows of the distance map C (2 for the env tip rewards, D for losses.quadratic_*) */
@@ -227,6 +227,30 @@ const char *pmb_fit_last_error(void);
  * the minibatch (the progress-bar value, :143).  Follow with pmb_clip_adam_step(max_norm = 0) for optimizer.step(). */
 int pmb_fit_gradient(const pmb_fit_problem *p, const long long *idx_dev, float *grad_flat, float *loglik_dev,
                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: the one collective of a particle-sharded iteration -- the sum of every rank's flat
+ * policy gradient (+ loss) -- over NVLink / NVSwitch peer memory, stream-ordered and capturable in the iteration's CUDA
+ * graph (the reference has no distributed code; this replaces the torch.distributed.all_reduce a port would call).
+ * One process per GPU: every rank allocates an exchange buffer (pmb_peer_alloc), the 64-byte handles travel over the
+ * host-side process group, every rank opens the other ranks' buffers (pmb_peer_open).
+ * ------------------------------------------------------------------------------------------- */
+const char *pmb_peer_last_error(void);
+/* Bytes of one rank's exchange buffer for vectors of n floats: [2 parities][world][n] floats + [world] flags. */
+size_t pmb_peer_buffer_bytes(long long n, int world);
+/* cudaMalloc + zero + cudaIpcGetMemHandle (handle64: 64 bytes out). */
+int pmb_peer_alloc(size_t bytes, void **ptr, void *handle64);
+/* cudaIpcOpenMemHandle of another rank's buffer (enables peer access lazily) / its close / free of the own buffer. */
+int pmb_peer_open(const void *handle64, void **ptr);
+int pmb_peer_close(void *ptr);
+int pmb_peer_free(void *ptr);
+/* dst[i] = sum over ranks of src[i] (i < n), the world slots added in rank order: deterministic and bitwise identical on
+ * every rank.  peer_bufs: HOST array of `world` device pointers (entry `rank` = the own buffer, the others as opened
+ * with pmb_peer_open, all sized pmb_peer_buffer_bytes(n, world)); state_dev: 3 zero-initialised uint64 in local device
+ * memory (exchange epoch and block counters).  src == dst is allowed.  Every rank must issue the same sequence of
+ * calls on its buffer set; a rank that never arrives traps the waiting kernel after ~2^31 polls. */
+int pmb_peer_allreduce(const float *src, float *dst, long long n, int world, int rank, void *const *peer_bufs,
+                       unsigned long long *state_dev, void *stream);
 
 #ifdef __cplusplus
 }

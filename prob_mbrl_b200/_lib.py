@@ -17,7 +17,7 @@ PMB_MAX_LINEAR = 6
 PMB_MAX_WIDTH = 1024
 PMB_MAX_STATE = 16
 PMB_MAX_REWARD_ROWS = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _fp = C.POINTER(C.c_float)
 
@@ -87,7 +87,9 @@ class PmbPlanInfo(C.Structure):
 EXPORTS = ("pmb_abi_version", "pmb_last_error", "pmb_check_problem", "pmb_workspace_bytes", "pmb_policy_param_count",
            "pmb_plan_describe",
            "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step",
-           "pmb_fit_workspace_bytes", "pmb_fit_param_count", "pmb_fit_last_error", "pmb_fit_gradient")
+           "pmb_fit_workspace_bytes", "pmb_fit_param_count", "pmb_fit_last_error", "pmb_fit_gradient",
+           "pmb_peer_last_error", "pmb_peer_buffer_bytes", "pmb_peer_alloc", "pmb_peer_open", "pmb_peer_close",
+           "pmb_peer_free", "pmb_peer_allreduce")
 
 _lib = None
 
@@ -142,6 +144,20 @@ def load():
     lib.pmb_fit_workspace_bytes.argtypes = [C.POINTER(PmbFitProblem)]
     lib.pmb_fit_param_count.restype = C.c_size_t
     lib.pmb_fit_param_count.argtypes = [C.POINTER(PmbFitProblem)]
+    lib.pmb_peer_last_error.restype = C.c_char_p
+    lib.pmb_peer_buffer_bytes.restype = C.c_size_t
+    lib.pmb_peer_buffer_bytes.argtypes = [C.c_longlong, C.c_int]
+    lib.pmb_peer_alloc.restype = C.c_int
+    lib.pmb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.pmb_peer_open.restype = C.c_int
+    lib.pmb_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.pmb_peer_close.restype = C.c_int
+    lib.pmb_peer_close.argtypes = [C.c_void_p]
+    lib.pmb_peer_free.restype = C.c_int
+    lib.pmb_peer_free.argtypes = [C.c_void_p]
+    lib.pmb_peer_allreduce.restype = C.c_int
+    lib.pmb_peer_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                       C.c_void_p, C.c_void_p]
     lib.pmb_fit_last_error.restype = C.c_char_p
     lib.pmb_fit_gradient.restype = C.c_int
     lib.pmb_fit_gradient.argtypes = [C.POINTER(PmbFitProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

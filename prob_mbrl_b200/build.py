@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpmb_b200.so")
 SOURCES = ["pmb_capi.cu", "pmb_rollout_fwd.cu", "pmb_rollout_bwd.cu", "pmb_cluster_fwd.cu", "pmb_cluster_bwd.cu",
-           "pmb_wgrad.cu", "pmb_mm.cu", "pmb_tc_fwd.cu", "pmb_tc_bwd.cu", "pmb_fit.cu", "pmb_cw_fwd.cu", "pmb_cw_bwd.cu"]
+           "pmb_wgrad.cu", "pmb_mm.cu", "pmb_tc_fwd.cu", "pmb_tc_bwd.cu", "pmb_fit.cu", "pmb_cw_fwd.cu", "pmb_cw_bwd.cu", "pmb_peer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

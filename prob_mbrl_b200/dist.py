@@ -76,3 +76,79 @@ def allreduce_gradient(flat, loss=None):
     torch.distributed.all_reduce(flat)
     if loss is not None:
         torch.distributed.all_reduce(loss)
+
+
+class PeerAllReduce:
+    """The gradient all-reduce over NVLink peer memory (``pmb_peer_allreduce``): stream-ordered kernels, no NCCL call,
+    capturable in the iteration's CUDA graph, results bitwise identical on every rank.  Construction is collective
+    (every rank of the default process group, same ``n``): exchange buffers are cudaMalloc'ed by the library, their
+    CUDA IPC handles travel through ``all_gather_object``."""
+
+    def __init__(self, n, device):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = world()
+        self.n = int(n)
+        if self.world > 16:
+            raise ValueError("the peer-memory exchange serves one node (<= 16 GPUs)")
+        with torch.cuda.device(device):
+            nbytes = self.lib.pmb_peer_buffer_bytes(self.n, self.world)
+            own, handle = C.c_void_p(), C.create_string_buffer(64)
+            self._check(self.lib.pmb_peer_alloc(nbytes, C.byref(own), handle))
+            self.own = own.value
+            handles = [None] * self.world
+            torch.distributed.all_gather_object(handles, bytes(handle.raw))
+            self.opened = []
+            self.ptrs = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = self.own
+                else:
+                    p = C.c_void_p()
+                    self._check(self.lib.pmb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                    self.opened.append(p.value)
+                    self.ptrs[r] = p.value
+            self.state = torch.zeros(3, dtype=torch.int64, device=device)
+            torch.cuda.synchronize()
+        torch.distributed.barrier()         # every buffer is zeroed and mapped before the first push
+
+    def _check(self, rc):
+        if rc != 0:
+            from . import _lib
+            raise _lib.LibraryError(rc, self.lib.pmb_peer_last_error().decode("utf-8", "replace"))
+
+    def __call__(self, flat, loss=None):
+        """In-place sum of ``flat`` (float32, ``n`` elements, contiguous) over the ranks, on the current stream."""
+        from . import _lib
+        assert flat.numel() == self.n and flat.dtype == torch.float32 and flat.is_contiguous()
+        self._check(self.lib.pmb_peer_allreduce(flat.data_ptr(), flat.data_ptr(), self.n, self.world, self.rank,
+                                                self.ptrs, self.state.data_ptr(), _lib.current_stream_ptr()))
+        if loss is not None:
+            torch.distributed.all_reduce(loss)
+
+    def close(self):
+        if getattr(self, "own", None) is None:
+            return
+        torch.cuda.synchronize()
+        for p in self.opened:
+            self.lib.pmb_peer_close(p)
+        self.lib.pmb_peer_free(self.own)
+        self.own, self.opened = None, []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gradient_sync(n, device):
+    """What a sharded iteration uses for its one collective: the peer-memory exchange (default), or the NCCL all-reduce
+    with ``PMB_GRAD_SYNC=nccl``.  None in a single-process run."""
+    import os
+    if world()[1] <= 1:
+        return None
+    if os.environ.get("PMB_GRAD_SYNC", "peer") == "nccl":
+        return allreduce_gradient
+    return PeerAllReduce(n, device)

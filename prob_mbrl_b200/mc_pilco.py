@@ -75,6 +75,12 @@ class FusedIteration:
         self.nparam = int(self.lib.pmb_policy_param_count(C.byref(self.prob)))
         # flat policy gradient + the loss in one buffer: ONE all-reduce per iteration when sharded
         self.reduced = torch.zeros(self.nparam + 1, **f32)
+        if self.grad_sync == "auto":
+            # sharded run: the gradient all-reduce over NVLink peer memory (in-stream kernels, part of the iteration's
+            # CUDA graph), or NCCL with PMB_GRAD_SYNC=nccl; a collective construction on every rank
+            from . import dist as _dist
+            self.grad_sync = _dist.gradient_sync(self.nparam + 1, self.dev)
+        self.sync_in_graph = type(self.grad_sync).__name__ == "PeerAllReduce"
         self.grad_flat = self.reduced[:self.nparam]
         self.dx0 = torch.empty(N, D, **f32)
         self.scratch = torch.zeros(1024, **f32)
@@ -265,17 +271,19 @@ class FusedIteration:
             self._hyper = self._hyper_now()
             self.lr, self.b1, self.b2, self.eps = self._hyper
             self.graph = None
-        # Single GPU: the whole iteration replays from ONE CUDA graph.  Sharded: two graphs (sweeps / clip+Adam)
-        # around the NCCL all-reduce, which stays an ordinary stream-ordered call (capturing the collective itself
-        # hung with torch 2.11 / NCCL 2.28 on 2xB200).  PMB_CUDA_GRAPH=0: plain launches.
+        # The whole iteration replays from ONE CUDA graph -- on one GPU, and sharded with the peer-memory gradient
+        # exchange (two kernels on the stream).  With the NCCL all-reduce (PMB_GRAD_SYNC=nccl): two graphs (sweeps /
+        # clip+Adam) around the collective, which stays an ordinary stream-ordered call (capturing it hung with torch
+        # 2.11 / NCCL 2.28 on 2xB200).  PMB_CUDA_GRAPH=0: plain launches.
         if os.environ.get("PMB_CUDA_GRAPH", "1") != "0":
+            one_graph = self.grad_sync is None or self.sync_in_graph
             if self.graph is None:
-                if self.grad_sync is None:
+                if one_graph:
                     self.graph = self._capture([self._enqueue])
                 else:
                     self.graph = self._capture([self._enqueue_sweeps, self._enqueue_update])
             self.graph[0].replay()
-            if self.grad_sync is not None:
+            if not one_graph:
                 self.grad_sync(self.reduced, None)
                 self.graph[1].replay()
         else:
@@ -426,7 +434,7 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
                 else:
                     g_r = torch.tensor(weights, dtype=torch.float32, device=dev)
                     g_r = (g_r / (Nloc * world))[:, None].expand(H, Nloc).contiguous()
-                    sync = dist.allreduce_gradient if world > 1 else None
+                    sync = "auto" if world > 1 else None
                     engine = FusedIteration(dynamics, policy, x0_, H, opt, g_r, clip_grad,
                                             dict(mm_states=mm_states, mm_rewards=mm_rewards, mm_groups=mm_groups,
                                                  z_mm=z_mm if mm_states else None,

@@ -39,7 +39,14 @@ p_shard, l_shard = run(True)
 err = float((p_single - p_shard).abs().max())
 moved = float((p_single - torch.cat([ops[k].flatten() for k in ("pol_W0", "pol_b0", "pol_W1", "pol_b1", "pol_W2", "pol_b2", "pol_W3", "pol_b3")]).to(dev)).abs().max())
 t = torch.tensor([err], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# every rank ends with the same parameters: bitwise with the peer-memory exchange (slots added in rank order everywhere)
+lo, hi = p_shard.clone(), p_shard.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+spread = float((hi - lo).abs().max())
+sync = os.environ.get("PMB_GRAD_SYNC", "peer")
 if rank == 0:
     ok = float(t) < 5e-7 and moved > 1e-4 and max(abs(a - b) for a, b in zip(l_single, l_shard)) < 1e-6
-    print("DIST", "PASS" if ok else "FAIL", "max|dparam| %.2e  moved %.2e" % (float(t), moved), l_single, l_shard)
+    ok = ok and (spread == 0.0 if sync == "peer" else spread < 1e-7)
+    print("DIST", "PASS" if ok else "FAIL", "sync=%s max|dparam| %.2e  moved %.2e  rank spread %.1e" % (sync, float(t), moved, spread),
+          l_single, l_shard)
 dist.destroy_process_group()

@@ -14,21 +14,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(nranks, script_args, timeout):
-    port = 29600 + (os.getpid() + 7 * nranks) % 300
+def _torchrun(nranks, script_args, timeout, **extra_env):
+    port = 29600 + (os.getpid() + 7 * nranks + 13 * len(extra_env)) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
-    env = dict(os.environ, PMB_NO_PBAR="1")
+    env = dict(os.environ, PMB_NO_PBAR="1", **extra_env)
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
-@pytest.mark.parametrize("nranks", [2, 4])
-def test_sharded_iteration_equals_single_gpu(nranks):
+@pytest.mark.parametrize("nranks,sync", [(2, "peer"), (2, "nccl"), (4, "peer")])
+def test_sharded_iteration_equals_single_gpu(nranks, sync):
+    """The gradient exchange over NVLink peer memory (default: `pmb_peer_allreduce`, inside the iteration's CUDA graph)
+    and the NCCL all-reduce (PMB_GRAD_SYNC=nccl) both reproduce the single-GPU parameters; with the peer exchange the
+    parameters are bitwise identical on every rank."""
     if torch.cuda.device_count() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
-    out = _torchrun(nranks, [os.path.join(ROOT, "scripts", "dist_check.py")], 420)
+    out = _torchrun(nranks, [os.path.join(ROOT, "scripts", "dist_check.py")], 420, PMB_GRAD_SYNC=sync)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert "DIST PASS" in out.stdout, out.stdout[-1500:]
+    assert ("sync=%s" % sync) in out.stdout
 
 
 @pytest.mark.parametrize("nranks", [2, 4])
