@@ -248,7 +248,7 @@ int pmb_peer_free(void *ptr);
  * every rank.  peer_bufs: HOST array of `world` device pointers (entry `rank` = the own buffer, the others as opened
  * with pmb_peer_open, all sized pmb_peer_buffer_bytes(n, world)); state_dev: 3 zero-initialised uint64 in local device
  * memory (exchange epoch and block counters).  src == dst is allowed.  Every rank must issue the same sequence of
- * calls on its buffer set; a rank that never arrives traps the waiting kernel after ~2^31 polls. */
+ * calls on its buffer set; a rank that never arrives traps the waiting kernel after ~2^28 polls. */
 int pmb_peer_allreduce(const float *src, float *dst, long long n, int world, int rank, void *const *peer_bufs,
                        unsigned long long *state_dev, void *stream);
 

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) peer_pull_kernel(float *__restrict__ dst,
             unsigned long long spins = 0;
             do {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pp.flag[rank] + r) : "memory");
-                if (++spins > (1ull << 31)) __trap();      // a rank that never arrives must not hang the GPU forever
+                if (++spins > (1ull << 28)) __trap();      // a rank that never arrives must not hang the GPU forever (~minutes)
             } while (v < e);
         }
     }
