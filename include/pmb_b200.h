@@ -27,10 +27,11 @@
 extern "C" {
 #endif
 
-#define PMB_ABI_VERSION 5
+#define PMB_ABI_VERSION 6
 #define PMB_MAX_LINEAR 6      /* linear layers per network (hidden + output projection) */
 #define PMB_MAX_WIDTH 1024    /* widest hidden layer the fused sweep accepts */
-#define PMB_MAX_REWARD_ROWS 16 /* rows of the distance map C (2 for the env tip rewards, D for losses.quadratic_*) */
+#define PMB_MAX_REWARD_ROWS 16
+#define PMB_MAX_PEERS 16         /* GPUs of one node in a peer-memory exchange */ /* rows of the distance map C (2 for the env tip rewards, D for losses.quadratic_*) */
 #define PMB_MAX_STATE 16      /* D + U <= 16 */
 
 enum {
@@ -81,11 +82,20 @@ typedef struct pmb_problem {
     int mm_groups;                /* 0/1 = one group; G = independent contiguous blocks of N/G rows */
     const float *z_mm;            /* [>= N][D]  rows 0..N-1 are used, rotated by the step index (rollout.py:53-59) */
     const float *z_rr;            /* [>= N][1] */
-    int n_global;                 /* reserved for sharded moment matching; set to N */
+    int n_global;                 /* particles of ALL ranks when the matching spans several GPUs (mm_world > 1: the ranks
+                                     hold equal contiguous shards, this one the rows mm_rank * N ..); otherwise N */
     int masks_binary;             /* 1 = every dropout mask value is exactly 0 or 1 (true for BDropout noise and for
                                      CDropout's concrete_noise = (b - probs).detach() + probs, which rounds to b exactly
                                      in fp32; reference models/modules.py:61,113-116).  Lets the planner keep the masks
                                      as bit words (wide cluster-resident sweeps); 0 = unknown (those sweeps are not used) */
+    /* Moment matching across the GPUs of one node (the reference is single-process): the
+     * per-step statistics are exchanged over NVLink peer memory inside the sweeps.  mm_world <= 1: off. */
+    int mm_world, mm_rank;
+    void *mm_peer_rec[PMB_MAX_PEERS];     /* [rank]: that rank's exchange area for the per-step records of the states
+                                             (pmb_mm_exchange_bytes()[0] bytes, zeroed once, entry mm_rank = the own one,
+                                             the others mapped with pmb_peer_open) */
+    void *mm_peer_gather[PMB_MAX_PEERS];  /* [rank]: ... for the whole-horizon exchange of the rewards ([1] bytes) */
+    void *mm_local_state;                 /* local device memory ([2] bytes, zeroed once): exchange epochs */
 } pmb_problem;
 
 /* Tunables (0 = library default). */
@@ -236,6 +246,9 @@ int pmb_fit_gradient(const pmb_fit_problem *p, const long long *idx_dev, float *
  * host-side process group, every rank opens the other ranks' buffers (pmb_peer_open).
  * ------------------------------------------------------------------------------------------- */
 const char *pmb_peer_last_error(void);
+/* Sizes of the three exchange areas a sharded moment-matched rollout needs (pmb_problem.mm_peer_rec / mm_peer_gather /
+ * mm_local_state); out[0..2] bytes.  PMB_E_UNSUPPORTED when the problem is outside the cluster-resident sweeps. */
+int pmb_mm_exchange_bytes(const pmb_problem *p, const pmb_tuning *tune, size_t out[3]);
 /* Bytes of one rank's exchange buffer for vectors of n floats: [2 parities][world][n] floats + [world] flags. */
 size_t pmb_peer_buffer_bytes(long long n, int world);
 /* cudaMalloc + zero + cudaIpcGetMemHandle (handle64: 64 bytes out). */

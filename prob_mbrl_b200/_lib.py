@@ -17,7 +17,7 @@ PMB_MAX_LINEAR = 6
 PMB_MAX_WIDTH = 1024
 PMB_MAX_STATE = 16
 PMB_MAX_REWARD_ROWS = 16
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _fp = C.POINTER(C.c_float)
 
@@ -50,6 +50,11 @@ class PmbProblem(C.Structure):
         ("z_mm", C.c_void_p), ("z_rr", C.c_void_p),
         ("n_global", C.c_int),
         ("masks_binary", C.c_int),
+        ("mm_world", C.c_int),
+        ("mm_rank", C.c_int),
+        ("mm_peer_rec", C.c_void_p * 16),
+        ("mm_peer_gather", C.c_void_p * 16),
+        ("mm_local_state", C.c_void_p),
     ]
 
 
@@ -89,7 +94,7 @@ EXPORTS = ("pmb_abi_version", "pmb_last_error", "pmb_check_problem", "pmb_worksp
            "pmb_rollout_forward", "pmb_rollout_backward", "pmb_clip_adam_step",
            "pmb_fit_workspace_bytes", "pmb_fit_param_count", "pmb_fit_last_error", "pmb_fit_gradient",
            "pmb_peer_last_error", "pmb_peer_buffer_bytes", "pmb_peer_alloc", "pmb_peer_open", "pmb_peer_close",
-           "pmb_peer_free", "pmb_peer_allreduce")
+           "pmb_peer_free", "pmb_peer_allreduce", "pmb_mm_exchange_bytes")
 
 _lib = None
 
@@ -158,6 +163,8 @@ def load():
     lib.pmb_peer_allreduce.restype = C.c_int
     lib.pmb_peer_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                        C.c_void_p, C.c_void_p]
+    lib.pmb_mm_exchange_bytes.restype = C.c_int
+    lib.pmb_mm_exchange_bytes.argtypes = [C.POINTER(PmbProblem), C.POINTER(PmbTuning), C.POINTER(C.c_size_t)]
     lib.pmb_fit_last_error.restype = C.c_char_p
     lib.pmb_fit_gradient.restype = C.c_int
     lib.pmb_fit_gradient.argtypes = [C.POINTER(PmbFitProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -245,8 +252,10 @@ def _fill_net(dst, net, n_rows, out_dims, keepalive):
 
 
 def make_problem(ops: RolloutOperands, N, H, mm_states=False, mm_rewards=False, mm_groups=None,
-                 z_mm=None, z_rr=None):
-    """Operand bundle -> (pmb_problem, keepalive list).  Tensors in `keepalive` must outlive the call."""
+                 z_mm=None, z_rr=None, shard=None):
+    """Operand bundle -> (pmb_problem, keepalive list).  Tensors in `keepalive` must outlive the call.
+    shard = (rank, world): N is this rank's equal share of a batch of N * world particles that is moment-matched as a
+    whole (the exchange areas are bound later, FusedIteration._bind_exchange)."""
     keep = []
     p = PmbProblem()
     p.N, p.H, p.D, p.U = int(N), int(H), int(ops.D), int(ops.U)
@@ -273,6 +282,9 @@ def make_problem(ops: RolloutOperands, N, H, mm_states=False, mm_rewards=False, 
         keep.append(z)
         p.z_rr = z.data_ptr()
     p.n_global = int(N)
+    if shard is not None and shard[1] > 1 and (mm_states or mm_rewards):
+        p.mm_rank, p.mm_world = int(shard[0]), int(shard[1])
+        p.n_global = int(N) * int(shard[1])
     p.masks_binary = int(bool(ops.pol.masks_binary and ops.dyn.masks_binary))
     return p, keep
 

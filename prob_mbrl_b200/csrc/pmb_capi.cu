@@ -49,6 +49,10 @@ struct Plan {
     long long wpack_fwd_off, wpack_bwd_off;
     long long part_off;
     long long s1pre_off, mmstat_off, mmrec_off, mmctr_off, rpre_off, rstat_off, geff_off, cmm_gbuf_off;
+    // moment matching across GPUs: full-width [H][n_global] copies of the pre-matching rewards, the matched rewards,
+    // their cotangents and the cotangents of the pre-matching rewards
+    int mm_world;
+    long long rfull_off, routfull_off, gfull_off, gefffull_off;
     int mm_G;
     long long nparam;
     long long ws_floats;
@@ -299,7 +303,7 @@ static int plan_sweep(SweepParams &S, const NetSweep *order[2], bool reverse, in
 // ---------------------------------------------------------------------------------------------
 static bool cluster_eligible(const pmb_problem *p, int C) {
     // moment matching of the states: one matching group (the whole particle set) of <= 128 particles
-    if (p->mm_states && (p->mm_groups > 1 || p->N > CMM_NMAX || p->N < 2)) return false;
+    if (p->mm_states && (p->mm_groups > 1 || p->N > CMM_NMAX || (p->mm_world > 1 ? p->n_global : p->N) < 2)) return false;
     const pmb_net *nets[2] = {&p->pol, &p->dyn};
     for (int i = 0; i < 2; ++i) {
         const pmb_net &n = *nets[i];
@@ -396,6 +400,10 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
         memset(&P, 0, sizeof(P));
         P.N = S.N; P.H = S.H; P.D = S.D; P.U = S.U; P.C = C;
         P.mm_states = p->mm_states; P.z_mm = p->z_mm;
+        P.mm_world = p->mm_world > 1 ? p->mm_world : 1;
+        P.mm_rank = p->mm_world > 1 ? p->mm_rank : 0;
+        P.n_global = p->mm_world > 1 ? p->n_global : p->N;
+        P.n_off = P.mm_rank * p->N;
         cluster_net(S.pol, pass == 1, true, C, P.pol);
         cluster_net(S.dyn, pass == 1, false, C, P.dyn);
         P.act_scale = S.act_scale; P.act_bias = S.act_bias; P.mx = S.mx; P.iSx = S.iSx; P.my = S.my; P.Sy = S.Sy;
@@ -727,7 +735,8 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         if (p->mm_rewards && !p->z_rr) return fail(PMB_E_INVALID, "mm_rewards needs z_rr");
         if (p->N % G != 0) return fail(PMB_E_INVALID, "N=%d is not divisible by mm_groups=%d", p->N, G);
         if (p->N / G < 2) return fail(PMB_E_INVALID, "moment matching needs at least 2 particles per group");
-        if (p->n_global != p->N) return fail(PMB_E_UNSUPPORTED, "moment matching across devices is not supported");
+        if (p->n_global != p->N && !(p->mm_world > 1))
+            return fail(PMB_E_INVALID, "n_global=%d differs from N=%d without mm_world > 1", p->n_global, p->N);
     }
 
     memset(&pl, 0, sizeof(pl));
@@ -799,6 +808,14 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.rstat_off = ws.take((long long)p->H * G * 4);
         pl.geff_off = ws.take(HN);
         pl.cmm_gbuf_off = ws.take(2LL * 2 * CMM_TILES * CMM_NQ);     // doubles: [2][tiles][CMM_NQ] records of the cluster sweeps
+        pl.mm_world = p->mm_world > 1 ? p->mm_world : 1;
+        if (pl.mm_world > 1 && p->mm_rewards) {
+            const long long HNg = (long long)p->H * p->n_global;
+            pl.rfull_off = ws.take(HNg);
+            pl.routfull_off = ws.take(HNg);
+            pl.gfull_off = ws.take(HNg);
+            pl.gefffull_off = ws.take(HNg);
+        }
     }
     if ((rc = plan_tc(p, tune, pl, ws)) != PMB_OK) return rc;
     const long long ws_before_cw = ws.top;
@@ -823,6 +840,15 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
     pl.ws_floats = ws.top;
     if (pl.cw) { pl.cluster = 0; return PMB_OK; }
     if ((rc = plan_cluster(p, tune, pl)) != PMB_OK) return rc;
+    if (p->mm_world > 1 && mm) {
+        if (p->mm_world > PMB_MAX_PEERS || p->mm_rank < 0 || p->mm_rank >= p->mm_world || p->n_global != p->N * p->mm_world)
+            return fail(PMB_E_INVALID, "mm_world=%d mm_rank=%d n_global=%d do not describe equal shards of N=%d", p->mm_world,
+                        p->mm_rank, p->n_global, p->N);
+        if (G > 1) return fail(PMB_E_UNSUPPORTED, "moment matching across GPUs supports one matching group");
+        if (p->mm_states && !pl.cluster)
+            return fail(PMB_E_UNSUPPORTED, "moment matching of the states across GPUs runs on the cluster-resident sweeps "
+                                           "(two hidden layers <= 256 wide, <= 120 particles per GPU)");
+    }
     if (pl.cluster) return PMB_OK;
     const int nst = tune ? tune->reserved[1] : 0;
     if ((rc = plan_sweep(F, fo, false, P, pl.stream_mode, nst, p->mm_states != 0)) < 0) return rc;
@@ -880,6 +906,10 @@ static void resolve(Plan &pl, float *ws) {
             P.mmstat = ws + pl.mmstat_off;
             P.mmctr = reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + pass;   // one counter per sweep
             P.mmrec = reinterpret_cast<double *>(ws + pl.cmm_gbuf_off);
+            P.mmrec_peer[0] = P.mmrec;
+            P.mmctr_peer[0] = P.mmctr;
+            P.mm_base = nullptr;
+            P.mm_base_next = nullptr;
         }
     }
     pl.cbwd.pre = ws + pl.cl_pre_off;
@@ -894,6 +924,48 @@ static void resolve(Plan &pl, float *ws) {
             S.mmctr = reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + pass;   // one counter per sweep
         }
     }
+}
+
+// ---- moment matching across GPUs: geometry of the exchange areas and their binding to the sweep parameters ----
+struct MmExchange {
+    int nq, ntiles_total;
+    size_t sweep_doubles;      // [2 parities][ntiles_total * nq] doubles of one sweep
+    size_t ctr_off;            // byte offset of the two arrival counters inside a rank's record area
+    size_t rec_bytes, gather_bytes, state_bytes;
+};
+static MmExchange mm_exchange(const pmb_problem *p, const Plan &pl) {
+    MmExchange x;
+    x.nq = p->D + p->D * (p->D + 1) / 2;
+    x.ntiles_total = 2 * (pl.cluster ? pl.cl_nclusters : 1) * (p->mm_world > 1 ? p->mm_world : 1);
+    x.sweep_doubles = (size_t)2 * x.ntiles_total * x.nq;
+    x.ctr_off = (2 * x.sweep_doubles * sizeof(double) + 255) & ~(size_t)255;
+    x.rec_bytes = x.ctr_off + 256;
+    x.gather_bytes = pmb_peer_buffer_bytes((long long)p->H * p->N, p->mm_world > 1 ? p->mm_world : 1);
+    x.state_bytes = 64;
+    return x;
+}
+// after resolve(): point the cluster sweeps at the peer-mapped record areas / counters (mm_world > 1)
+static int bind_peers(Plan &pl, const pmb_problem *p) {
+    if (!(p->mm_world > 1 && (p->mm_states || p->mm_rewards))) return PMB_OK;
+    if (!p->mm_local_state) return fail(PMB_E_INVALID, "mm_local_state is NULL");
+    for (int r = 0; r < p->mm_world; ++r)
+        if ((p->mm_states && !p->mm_peer_rec[r]) || (p->mm_rewards && !p->mm_peer_gather[r]))
+            return fail(PMB_E_INVALID, "exchange area of rank %d is NULL", r);
+    if (!p->mm_states) return PMB_OK;
+    const MmExchange x = mm_exchange(p, pl);
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(p->mm_local_state);
+    for (int pass = 0; pass < 2; ++pass) {
+        ClusterParams &P = pass ? pl.cbwd : pl.cfwd;
+        for (int r = 0; r < p->mm_world; ++r) {
+            P.mmrec_peer[r] = reinterpret_cast<double *>(p->mm_peer_rec[r]) + pass * x.sweep_doubles;
+            P.mmctr_peer[r] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(p->mm_peer_rec[r]) + x.ctr_off) + pass;
+        }
+        P.mmrec = P.mmrec_peer[p->mm_rank];
+        P.mmctr = P.mmctr_peer[p->mm_rank];
+        P.mm_base = st + pass;
+        P.mm_base_next = st + pass;
+    }
+    return PMB_OK;
 }
 
 }  // namespace pmb
@@ -921,6 +993,16 @@ size_t pmb_workspace_bytes(const pmb_problem *p, const pmb_tuning *tune) {
     Plan pl;
     if (build_plan(p, tune, pl) != PMB_OK) return 0;
     return (size_t)pl.ws_floats * sizeof(float);
+}
+
+int pmb_mm_exchange_bytes(const pmb_problem *p, const pmb_tuning *tune, size_t out[3]) {
+    if (!out) return fail(PMB_E_INVALID, "out is NULL");
+    Plan pl;
+    int rc = build_plan(p, tune, pl);
+    if (rc != PMB_OK) return rc;
+    const MmExchange x = mm_exchange(p, pl);
+    out[0] = x.rec_bytes; out[1] = x.gather_bytes; out[2] = x.state_bytes;
+    return PMB_OK;
 }
 
 int pmb_plan_describe(const pmb_problem *p, const pmb_tuning *tune, pmb_plan_info *info) {
@@ -990,6 +1072,8 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
         return fail(PMB_E_WORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, (size_t)pl.ws_floats * 4);
     cudaStream_t st = (cudaStream_t)stream;
     resolve(pl, (float *)workspace);
+    if ((rc = bind_peers(pl, p)) != PMB_OK) return rc;
+    const bool sharded_mm = p->mm_world > 1 && (p->mm_states || p->mm_rewards);
     const int phases = (tune && (tune->reserved[0] & 255)) ? (tune->reserved[0] & 255) : 7;   // profiling aid: 1 pack, 2 sweep
     if (status_dev) PMB_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
     if (phases & 1) {
@@ -1005,7 +1089,8 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     F.x0 = x0; F.states = states; F.actions = actions; F.status = status_dev;
     // with mm_rewards the sweep writes the pre-matching rewards; a whole-horizon kernel matches them
     F.rewards = p->mm_rewards ? wsf + pl.rpre_off : rewards;
-    if (p->mm_states && !pl.tc) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
+    // (across GPUs the arrival counters live in peer-mapped memory and are never reset: a peer may already be a launch ahead)
+    if (p->mm_states && !pl.tc && !sharded_mm) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
     F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     if (pl.tc) {
         TcParams &T = pl.tfwd;
@@ -1023,9 +1108,19 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     } else if (phases & 2) {
         PMB_CUDA(launch_rollout_fwd(F, pl.P, pl.smem_fwd_bytes, st));
     }
-    if (p->mm_rewards)
+    if (p->mm_rewards && sharded_mm) {
+        // the rewards of ALL ranks are matched together: all-gather the pre-matching rewards over peer memory, match the
+        // full [H][n_global] array (every rank computes the same statistics), keep this rank's columns
+        unsigned long long *gst = reinterpret_cast<unsigned long long *>(p->mm_local_state) + 2;
+        PMB_CUDA(launch_peer_gather(wsf + pl.rpre_off, wsf + pl.rfull_off, p->H, p->N, p->mm_world, p->mm_rank, p->mm_peer_gather,
+                                    gst, st));
+        PMB_CUDA(launch_reward_mm_fwd(wsf + pl.rfull_off, wsf + pl.routfull_off, p->z_rr, wsf + pl.rstat_off, p->n_global, p->H,
+                                      1, status_dev, st));
+        PMB_CUDA(launch_take_columns(wsf + pl.routfull_off, rewards, p->H, p->n_global, p->N, p->mm_rank * p->N, st));
+    } else if (p->mm_rewards) {
         PMB_CUDA(launch_reward_mm_fwd(wsf + pl.rpre_off, rewards, p->z_rr, wsf + pl.rstat_off, p->N, p->H, pl.mm_G,
                                       status_dev, st));
+    }
     return PMB_OK;
 }
 
@@ -1042,6 +1137,8 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
     cudaStream_t st = (cudaStream_t)stream;
     float *ws = (float *)workspace;
     resolve(pl, ws);
+    if ((rc = bind_peers(pl, p)) != PMB_OK) return rc;
+    const bool sharded_mm = p->mm_world > 1 && (p->mm_states || p->mm_rewards);
     SweepParams &B = pl.bwd;
     B.states = const_cast<float *>(states); B.actions = const_cast<float *>(actions);
     B.rewards = const_cast<float *>(rewards);
@@ -1050,13 +1147,23 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
         // adjoint of the reward matching runs first, off the serial chain; the sweep then sees the
         // pre-matching rewards and their cotangent
         B.rewards = ws + pl.rpre_off;
-        if (g_rewards) {
+        if (g_rewards && sharded_mm) {
+            // adjoint of the matching over all ranks' rewards: all-gather the cotangents, run the adjoint on the full
+            // [H][n_global] arrays (the gathered pre-matching rewards are still in place), keep this rank's columns
+            unsigned long long *gst = reinterpret_cast<unsigned long long *>(p->mm_local_state) + 2;
+            PMB_CUDA(launch_peer_gather(g_rewards, ws + pl.gfull_off, p->H, p->N, p->mm_world, p->mm_rank, p->mm_peer_gather, gst, st));
+            PMB_CUDA(launch_reward_mm_bwd(ws + pl.gfull_off, ws + pl.rfull_off, p->z_rr, ws + pl.rstat_off, ws + pl.gefffull_off,
+                                          p->n_global, p->H, 1, st));
+            PMB_CUDA(launch_take_columns(ws + pl.gefffull_off, ws + pl.geff_off, p->H, p->n_global, p->N, p->mm_rank * p->N, st));
+            B.g_rewards = ws + pl.geff_off;
+        } else if (g_rewards) {
             PMB_CUDA(launch_reward_mm_bwd(g_rewards, ws + pl.rpre_off, p->z_rr, ws + pl.rstat_off, ws + pl.geff_off,
                                           p->N, p->H, pl.mm_G, st));
             B.g_rewards = ws + pl.geff_off;
         }
     }
-    if (p->mm_states && !pl.tc) PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
+    if (p->mm_states && !pl.tc && !sharded_mm)
+        PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && (tune->reserved[0] & 255)) ? (tune->reserved[0] & 255) : 7;   // profiling aid: 2 sweep, 4 wgrad
     if (pl.tc) {

@@ -78,6 +78,14 @@ struct ClusterParams {
     float *mmstat;              // [H][3*SD + SD*SD] mean, z mean, 1/z std, Cholesky factor of every step
     unsigned *mmctr;            // arrival counter of this sweep (zeroed before the launch)
     double *mmrec;              // [2][tiles][CMM_NQ] per-tile records of a step (double-buffered by step parity)
+    // ... across GPUs (particles sharded over mm_world ranks of one node): every rank's record area and
+    // arrival counter are mapped into every other rank (CUDA IPC); records and arrivals go to ALL ranks over NVLink
+    int mm_world, mm_rank;      // 1, 0: single GPU
+    int n_global, n_off;        // particles of all ranks / first global particle index of this rank
+    double *mmrec_peer[16];     // [rank]: that rank's record area of THIS sweep (entry mm_rank == mmrec)
+    unsigned *mmctr_peer[16];   // [rank]: that rank's arrival counter of THIS sweep (entry mm_rank == mmctr)
+    const unsigned long long *mm_base;   // arrivals before this launch (counters across GPUs are never reset), or nullptr = 0
+    unsigned long long *mm_base_next;    // where the launch leaves the arrivals after it (same word), or nullptr
     int *status;                // forward: 1 + first step whose covariance was not positive definite
     int off_mm;                 // shared memory: two CMM blocks (one per particle tile)
     unsigned *g1, *g2;          // wide cluster-resident sweeps (pmb_cw.cuh): ReLU/dropout gate bit words of hidden 0 / 1

@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
     constexpr bool mm = MM;
     CMM M;
     M.carve(smem + prm.off_mm + g * CMM_FLOATS);
-    const unsigned mm_ncl = mm ? cmm_clusters(N, PG) : 0u;
+    const unsigned mm_ncl = mm ? cmm_arrivals(prm) : 0u;
+    const unsigned mm_base = mm ? cmm_base(prm) : 0u;
 
     __syncthreads();
     cl_sync();                  // every CTA's barriers are initialised and armed before any peer may signal them
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
             // ---- adjoint of the moment matching: cotangent of the matched s_{t+1} -> cotangent of the pre-matching
             //      particles (one exchange over all tiles of the grid, rollout.py:121-128) ----
             cmm_backward_prefetch(prm, M, g, gtid, t, roleB, b_p, b_d, b_n);
-            cmm_backward(prm, M, g, gtid, rank, t, (unsigned)(it + 1) * mm_ncl, nvg, gs, roleB, b_p, b_d);
+            cmm_backward(prm, M, g, gtid, rank, t, mm_base + (unsigned)(it + 1) * mm_ncl, nvg, gs, roleB, b_p, b_d);
         }
         // ---- total dL/ds_{t+1} (carried + reward) and the dynamics density adjoint:
         //      s' = s + mu*Sy + my + z*exp(lstd) ----
@@ -409,8 +410,9 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         prm.dx0[(size_t)(n0g + b_p) * D + b_d] = gs[b_p * SD + b_d];
     } else if (mm) {
         // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
-        for (int it = 0; it < H; ++it) cmm_idle_step(prm, g, gtid, rank, H - 1 - it, (unsigned)(it + 1) * mm_ncl);
+        for (int it = 0; it < H; ++it) cmm_idle_step(prm, g, gtid, rank, H - 1 - it, mm_base + (unsigned)(it + 1) * mm_ncl);
     }
+    if (mm && prm.mm_base_next && blockIdx.x == 0 && tid == 0) *prm.mm_base_next = (unsigned long long)(mm_base + (unsigned)H * mm_ncl);
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
 

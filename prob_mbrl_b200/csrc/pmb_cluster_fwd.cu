@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     constexpr bool mm = MM;
     CMM M;
     M.carve(smem + prm.off_mm + g * CMM_FLOATS);
-    const unsigned mm_ncl = mm ? cmm_clusters(N, PG) : 0u;
+    const unsigned mm_ncl = mm ? cmm_arrivals(prm) : 0u;         // arrivals per step: the clusters of all ranks
+    const unsigned mm_base = mm ? cmm_base(prm) : 0u;
     const bool mm_leader = blockIdx.x == 0 && g == 0;
 
     __syncthreads();
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         if (pol.zstride != 0 && roleA && pol.has_density) zA = __ldg(pol.z + (size_t)t * pol.zstride + (size_t)a_n * U + a_u);
         if (dyn.zstride != 0 && roleB && dyn.has_density) zB = __ldg(dyn.z + (size_t)t * dyn.zstride + (size_t)b_n * D + b_d);
         if (mm && roleB) {      // z row of the matching step: z_mm[(t + n) mod N] (rollout.py:53-59); read after >= 4 tile barriers
-            int r = t + b_n;
-            r -= (r / N) * N;
+            int r = t + prm.n_off + b_n;            // global particle index (the particles of all ranks are matched together)
+            r -= (r / prm.n_global) * prm.n_global;
             M.zrow[b_p * SD + b_d] = __ldg(prm.z_mm + (size_t)r * D + b_d);
         }
 
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
         }
         if (mm) {
             // ---- moment matching: every tile of the grid exchanges its pre-matching particles (rollout.py:121-128) ----
-            cmm_forward(prm, M, g, gtid, rank, t, (unsigned)(t + 1) * mm_ncl, nvg, roleB, b_p, b_d, b_n, b_own, s_reg, mm_leader,
+            cmm_forward(prm, M, g, gtid, rank, t, mm_base + (unsigned)(t + 1) * mm_ncl, nvg, roleB, b_p, b_d, b_n, b_own, s_reg, mm_leader,
                         dbg_step ? prm.dbg + 24 * 8 : nullptr);
             if (roleB) {
                 xpol[b_d * CL_TS + b_p] = s_reg;
@@ -333,8 +334,11 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     }
     } else if (mm) {
         // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
-        for (int t = 0; t < H; ++t) cmm_idle_step(prm, g, gtid, rank, t, (unsigned)(t + 1) * mm_ncl);
+        for (int t = 0; t < H; ++t) cmm_idle_step(prm, g, gtid, rank, t, mm_base + (unsigned)(t + 1) * mm_ncl);
     }
+    // across GPUs the arrival counters are never reset: leave the count this launch ends at for the next one (every CTA
+    // read the old value before its first exchange, and cluster 0 is past the last one)
+    if (mm && prm.mm_base_next && blockIdx.x == 0 && tid == 0) *prm.mm_base_next = (unsigned long long)(mm_base + (unsigned)H * mm_ncl);
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
 }
 

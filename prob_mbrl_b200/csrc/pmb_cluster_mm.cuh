@@ -51,19 +51,36 @@ struct CMM {
 // Every cluster of the grid meets here, once per step: all threads of the cluster (both particle tiles of its 8 CTAs)
 // join a hardware cluster barrier, rank 0 arrives on the global counter for the cluster, one thread per CTA polls it
 // (`target` = arrivals expected so far = clusters x steps).
-__device__ __forceinline__ void cmm_barrier(unsigned *ctr, unsigned target, int rank) {
+__device__ __forceinline__ void cmm_barrier(const ClusterParams &prm, unsigned target, int rank) {
     // release pattern: the record writers' stores are ordered before the cluster barrier (its arrive.release is a
     // gpu-level membar in SASS; the explicit acq_rel fence keeps the PTX model honest and is cheaper than the
-    // sequentially consistent __threadfence()), rank 0 then publishes with a release reduction
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    cl_sync();
-    if (threadIdx.x == 0) {
-        if (rank == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-        unsigned v, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-            if (++spins > (1u << 26)) __trap();
-        } while (v < target);
+    // sequentially consistent __threadfence()), rank 0 then publishes with a release reduction.  Across GPUs the
+    // same at system scope: the records went to every rank's memory, the arrival goes to every rank's counter.
+    unsigned *ctr = prm.mmctr;
+    if (prm.mm_world > 1) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        cl_sync();
+        if (threadIdx.x == 0) {
+            if (rank == 0)
+                for (int p = 0; p < prm.mm_world; ++p)
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.mmctr_peer[p]) : "memory");
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                if (++spins > (1u << 28)) __trap();
+            } while ((int)(v - target) < 0);
+        }
+    } else {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        cl_sync();
+        if (threadIdx.x == 0) {
+            if (rank == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                if (++spins > (1u << 26)) __trap();
+            } while ((int)(v - target) < 0);
+        }
     }
     __syncwarp();               // the polling lane rejoins its warp
     // both particle tiles of the CTA (active or idle, i.e. from different call sites) meet on a named barrier:
@@ -80,6 +97,25 @@ __device__ __forceinline__ void cmm_init_qtab(const CMM &M, int D, int gtid) {
     }
 }
 __device__ __forceinline__ unsigned cmm_clusters(int N, int PG) { return (unsigned)((N + PG - 1) / PG); }
+// arrivals per step on every rank's counter: the clusters of all ranks
+__device__ __forceinline__ unsigned cmm_arrivals(const ClusterParams &prm) {
+    return cmm_clusters(prm.N, prm.PG) * (unsigned)max(prm.mm_world, 1);
+}
+// first arrival count of this launch (0 on one GPU, where the counter is zeroed before the launch)
+__device__ __forceinline__ unsigned cmm_base(const ClusterParams &prm) {
+    return prm.mm_base ? (unsigned)__ldcg(prm.mm_base) : 0u;
+}
+// record entry q of this tile (2 cluster + g) for step parity `par`: to the own record area, or to every rank's
+__device__ __forceinline__ void cmm_publish(const ClusterParams &prm, int par, int g, int nq, int q, double a) {
+    const int tl = 2 * (int)cmm_clusters(prm.N, prm.PG);           // tiles of one rank
+    const int world = max(prm.mm_world, 1);
+    const size_t idx = ((size_t)par * world * tl + (size_t)prm.mm_rank * tl + 2 * (blockIdx.x / prm.C) + g) * nq + q;
+    if (world > 1) {
+        for (int p = 0; p < world; ++p) prm.mmrec_peer[p][idx] = a;
+    } else {
+        prm.mmrec[idx] = a;
+    }
+}
 
 // totals of the step: M.red[q] = sum over the particle tiles of the grid of their records, in tile order (identical on
 // every tile).  Records: rec[(2 cluster + g) * nq + q], written by rank 0 of the cluster.  Kept small on purpose: the
@@ -119,16 +155,14 @@ __device__ __forceinline__ void cmm_combine(const CMM &M, const double *rec, int
 // an idle tile (no particles) still takes part in the per-step exchange: an all-zero record, the barriers
 __device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, int g, int gtid, int rank, int t, unsigned target) {
     const int nq = prm.D + prm.D * (prm.D + 1) / 2;
-    const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG);
-    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
     if (rank == 0)
-        for (int q = gtid; q < nq; q += CL_GT) rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = 0.0;
-    cmm_barrier(prm.mmctr, target, rank);
+        for (int q = gtid; q < nq; q += CL_GT) cmm_publish(prm, t & 1, g, nq, q, 0.0);
+    cmm_barrier(prm, target, rank);
 }
 
 // constants of the launch: mean and 1 / unbiased std of the z_mm rows (all N rows take part in every step)
 __device__ __forceinline__ void cmm_z_statistics(const ClusterParams &prm, const CMM &M, int g, int gtid) {
-    const int D = prm.D, N = prm.N;
+    const int D = prm.D, N = prm.n_global;
     cmm_init_qtab(M, D, gtid);
     if (gtid < D) {
         double a = 0.0;
@@ -181,14 +215,14 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
                                             int nvg, bool roleB, int b_p, int b_d, int b_n, bool b_own, float &s_reg, bool leader,
                                             long long *dbgp) {
 #define CMM_MARK(i) do { if (dbgp && (threadIdx.x & 31) == 0) dbgp[(i) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
-    const int D = prm.D, N = prm.N;
+    const int D = prm.D, N = prm.n_global;          // statistics over the particles of all ranks
     const int nq = D + D * (D + 1) / 2;
-    const int ntiles = 2 * (int)cmm_clusters(N, prm.PG);
+    const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG) * max(prm.mm_world, 1);
     float *s1pre = const_cast<float *>(prm.s1pre);
-    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
+    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq;
     if (roleB) {
         M.xrow[b_p * SD + b_d] = s_reg;
-        if (b_own) s1pre[((size_t)t * N + b_n) * D + b_d] = s_reg;
+        if (b_own) s1pre[((size_t)t * prm.N + b_n) * D + b_d] = s_reg;
     }
     CT_SYNC(g);
     // record of this tile (raw moments in double: products of two floats are exact): sum x_q, sum x_i x_j
@@ -201,11 +235,11 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
                 const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
                 for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + i] * (double)M.xrow[p * SD + j];
             }
-            rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = a;
+            cmm_publish(prm, t & 1, g, nq, q, a);
         }
     }
     CMM_MARK(0);
-    cmm_barrier(prm.mmctr, target, rank);
+    cmm_barrier(prm, target, rank);
     CMM_MARK(1);
     cmm_combine(M, rec, ntiles, nq, g, gtid);
     if (gtid < D) {
@@ -249,23 +283,23 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
 //      pre-matching states of the tile's slots. ----
 __device__ __forceinline__ void cmm_backward_prefetch(const ClusterParams &prm, const CMM &M, int g, int gtid, int t, bool roleB,
                                                       int b_p, int b_d, int b_n) {
-    const int D = prm.D, N = prm.N;
+    const int D = prm.D, N = prm.n_global;
     const float *ms = prm.mmstat + (size_t)t * (3 * SD + SD * SD);
     for (int i = gtid; i < D; i += CL_GT) M.st[i] = __ldcg(ms + i);
     for (int i = gtid; i < SD * SD; i += CL_GT) M.L[i] = __ldcg(ms + 3 * SD + i);
     if (roleB) {
-        int r = t + b_n;
+        int r = t + prm.n_off + b_n;
         r -= (r / N) * N;
         M.zrow[b_p * SD + b_d] = (__ldg(prm.z_mm + (size_t)r * D + b_d) - M.st[SD + b_d]) * M.st[2 * SD + b_d];
-        M.xrow[b_p * SD + b_d] = __ldcg(prm.s1pre + ((size_t)t * N + b_n) * D + b_d);
+        M.xrow[b_p * SD + b_d] = __ldcg(prm.s1pre + ((size_t)t * prm.N + b_n) * D + b_d);
     }
 }
 __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM &M, int g, int gtid, int rank, int t, unsigned target,
                                              int nvg, float *gs, bool roleB, int b_p, int b_d) {
-    const int D = prm.D, N = prm.N;
+    const int D = prm.D, N = prm.n_global;
     const int nq = D + D * (D + 1) / 2;
-    const int ntiles = 2 * (int)cmm_clusters(N, prm.PG);
-    double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * CMM_NQ;
+    const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG) * max(prm.mm_world, 1);
+    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq;
     CT_SYNC(g);         // the prefetched rows are in place
     // record of this tile: dm = sum_p g_p (q < D);  dL = tril(sum_p g_p zhat_p^T) (q = D + i (i + 1) / 2 + j)
     if (rank == 0) {
@@ -277,10 +311,10 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
                 const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
                 for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + i] * (double)M.zrow[p * SD + j];
             }
-            rec[(2 * (blockIdx.x / prm.C) + g) * nq + q] = a;
+            cmm_publish(prm, t & 1, g, nq, q, a);
         }
     }
-    cmm_barrier(prm.mmctr, target, rank);
+    cmm_barrier(prm, target, rank);
     cmm_combine(M, rec, ntiles, nq, g, gtid);
     for (int q = gtid; q < nq; q += CL_GT) {
         if (q < D) {

@@ -32,4 +32,8 @@ cudaError_t launch_clip_adam(const pmb_adam_tensor *tab, int nt, float max_norm,
                              float eps, long long step, long long *step_dev, float *scratch, const int *skip,
                              cudaStream_t stream);
 
+cudaError_t launch_peer_gather(const float *src, float *full, int H, int Nl, int world, int rank, void *const *peer_bufs,
+                               unsigned long long *state_dev, cudaStream_t stream);
+cudaError_t launch_take_columns(const float *full, float *local, int H, int Ng, int Nl, int off, cudaStream_t stream);
+
 }  // namespace pmb

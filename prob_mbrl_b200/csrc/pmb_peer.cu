@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "../../include/pmb_b200.h"
+#include "pmb_host.h"
 
 namespace pmb {
 const char *peer_err = "";
@@ -81,7 +82,84 @@ __global__ void __launch_bounds__(256) peer_pull_kernel(float *__restrict__ dst,
     }
 }
 
+// all-gather flavour of pull: wait for every rank's slot, then lay the blocks out as [H][world * Nl] (rank r's block is
+// [H][Nl]: its particles of every step)
+__global__ void __launch_bounds__(256) peer_gather_kernel(float *__restrict__ dst, int H, int Nl, int world, int rank, PeerPtrs pp,
+                                                          unsigned long long *state) {
+    const unsigned long long e = state[0] + 1ull;
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < world; ++r) {
+            unsigned long long v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pp.flag[rank] + r) : "memory");
+                if (++spins > (1ull << 28)) __trap();
+            } while (v < e);
+        }
+    }
+    __syncthreads();
+    const long long n = (long long)H * Nl;
+    const float *base = pp.buf[rank] + (long long)(e & 1ull) * world * n;
+    const long long total = n * world, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int r = (int)(i / n);
+        const long long j = i - (long long)r * n;
+        const int t = (int)(j / Nl), c = (int)(j - (long long)t * Nl);
+        dst[(long long)t * world * Nl + (long long)r * Nl + c] = __ldcg(base + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long done = atomicAdd(&state[2], 1ull) + 1ull;
+        if (done == gridDim.x) {
+            state[2] = 0ull;
+            state[0] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) take_columns_kernel(const float *__restrict__ full, float *__restrict__ local, int H, int Ng,
+                                                           int Nl, int off) {
+    const long long total = (long long)H * Nl;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / Nl), c = (int)(i - (long long)t * Nl);
+        local[i] = full[(long long)t * Ng + off + c];
+    }
+}
+
+static void fill_ptrs(PeerPtrs &pp, void *const *peer_bufs, long long n, int world) {
+    memset(&pp, 0, sizeof(pp));
+    const size_t flag_off = (((size_t)(2 * (long long)world * n) * sizeof(float)) + 255) & ~(size_t)255;
+    for (int p = 0; p < world; ++p) {
+        pp.buf[p] = (float *)peer_bufs[p];
+        pp.flag[p] = (unsigned long long *)((char *)peer_bufs[p] + flag_off);
+    }
+}
+
 }  // namespace
+
+namespace pmb {
+
+// all-gather of every rank's [H][Nl] block over peer memory into full [H][world * Nl] (whole-horizon reward matching of
+// a sharded rollout); peer_bufs sized pmb_peer_buffer_bytes(H * Nl, world)
+cudaError_t launch_peer_gather(const float *src, float *full, int H, int Nl, int world, int rank, void *const *peer_bufs,
+                               unsigned long long *state_dev, cudaStream_t stream) {
+    PeerPtrs pp;
+    const long long n = (long long)H * Nl;
+    fill_ptrs(pp, peer_bufs, n, world);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148) blocks = 148;
+    peer_push_kernel<<<blocks, 256, 0, stream>>>(src, n, world, rank, pp, state_dev);
+    peer_gather_kernel<<<blocks, 256, 0, stream>>>(full, H, Nl, world, rank, pp, state_dev);
+    return cudaGetLastError();
+}
+cudaError_t launch_take_columns(const float *full, float *local, int H, int Ng, int Nl, int off, cudaStream_t stream) {
+    int blocks = (int)(((long long)H * Nl + 255) / 256);
+    if (blocks > 148) blocks = 148;
+    take_columns_kernel<<<blocks, 256, 0, stream>>>(full, local, H, Ng, Nl, off);
+    return cudaGetLastError();
+}
+
+}  // namespace pmb
 
 extern "C" {
 
@@ -131,14 +209,10 @@ int pmb_peer_allreduce(const float *src, float *dst, long long n, int world, int
         pmb::peer_err = "bad arguments";
         return PMB_E_INVALID;
     }
-    PeerPtrs pp;
-    memset(&pp, 0, sizeof(pp));
-    const size_t flag_off = (((size_t)(2 * (long long)world * n) * sizeof(float)) + 255) & ~(size_t)255;
-    for (int p = 0; p < world; ++p) {
+    for (int p = 0; p < world; ++p)
         if (!peer_bufs[p]) { pmb::peer_err = "NULL peer buffer"; return PMB_E_INVALID; }
-        pp.buf[p] = (float *)peer_bufs[p];
-        pp.flag[p] = (unsigned long long *)((char *)peer_bufs[p] + flag_off);
-    }
+    PeerPtrs pp;
+    fill_ptrs(pp, peer_bufs, n, world);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148) blocks = 148;
     cudaStream_t st = (cudaStream_t)stream;

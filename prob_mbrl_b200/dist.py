@@ -78,6 +78,57 @@ def allreduce_gradient(flat, loss=None):
         torch.distributed.all_reduce(loss)
 
 
+class PeerBuffer:
+    """A zeroed device buffer of this rank that every rank of the node has mapped (CUDA IPC through
+    ``pmb_peer_alloc`` / ``pmb_peer_open``).  Collective construction; ``ptrs[r]`` = rank r's buffer as seen here."""
+
+    def __init__(self, nbytes, device):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = world()
+        if self.world > 16:
+            raise ValueError("the peer-memory exchange serves one node (<= 16 GPUs)")
+        with torch.cuda.device(device):
+            own, handle = C.c_void_p(), C.create_string_buffer(64)
+            self._check(self.lib.pmb_peer_alloc(int(nbytes), C.byref(own), handle))
+            self.own = own.value
+            handles = [None] * self.world
+            torch.distributed.all_gather_object(handles, bytes(handle.raw))
+            self.opened = []
+            self.ptrs = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = self.own
+                else:
+                    p = C.c_void_p()
+                    self._check(self.lib.pmb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                    self.opened.append(p.value)
+                    self.ptrs[r] = p.value
+            torch.cuda.synchronize()
+        torch.distributed.barrier()         # every buffer is zeroed and mapped before anyone writes
+
+    def _check(self, rc):
+        if rc != 0:
+            from . import _lib
+            raise _lib.LibraryError(rc, self.lib.pmb_peer_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "own", None) is None:
+            return
+        torch.cuda.synchronize()
+        for p in self.opened:
+            self.lib.pmb_peer_close(p)
+        self.lib.pmb_peer_free(self.own)
+        self.own, self.opened = None, []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PeerAllReduce:
     """The gradient all-reduce over NVLink peer memory (``pmb_peer_allreduce``): stream-ordered kernels, no NCCL call,
     capturable in the iteration's CUDA graph, results bitwise identical on every rank.  Construction is collective

@@ -142,9 +142,12 @@ class FusedIteration:
             if net.z is not None:
                 net.z = self._static_copy(tag + "_z", net.z[:N])
         mm = dict(self.mm)
+        rank, world = dist.world()
+        self.sharded_mm = world > 1 and bool(mm.get("mm_states") or mm.get("mm_rewards"))
         for k in ("z_mm", "z_rr"):
             if mm.get(k) is not None:
-                mm[k] = self._static_copy(k, mm[k][:N])
+                # rows 0 .. N-1 of the tables are used; across GPUs the N * world particles of all ranks are matched together
+                mm[k] = self._static_copy(k, mm[k][:N * world if self.sharded_mm else N])
         for name in ("act_scale", "act_bias", "mx", "iSx", "my", "Sy"):
             setattr(ops, name, self._static_copy(name, getattr(ops, name)))
         for name in ("C", "c0", "Q", "R"):
@@ -155,9 +158,26 @@ class FusedIteration:
             self.prob = None
         self.ops = ops
         if self.prob is None:
-            self.prob, self.keep = _lib.make_problem(ops, N, self.H, **mm)
+            self.prob, self.keep = _lib.make_problem(ops, N, self.H, shard=(rank, world), **mm)
             _lib.check_problem(self.prob, self.tune)
+            self._bind_exchange()
             self.graph = None
+
+    def _bind_exchange(self):
+        """Moment matching across GPUs: the exchange areas of the per-step statistics (records + arrival counters) and of
+        the whole-horizon reward exchange live in peer-mapped memory (collective allocation, once per engine)."""
+        if not self.sharded_mm:
+            return
+        if getattr(self, "mm_exchange", None) is None:
+            sizes = (C.c_size_t * 3)()
+            _lib.check(self.lib.pmb_mm_exchange_bytes(C.byref(self.prob), C.byref(self.tune), sizes))
+            self.mm_exchange = (dist.PeerBuffer(sizes[0], self.dev), dist.PeerBuffer(sizes[1], self.dev),
+                                torch.zeros(max(int(sizes[2]) // 8, 8), dtype=torch.int64, device=self.dev))
+        rec, gather, state = self.mm_exchange
+        for r in range(rec.world):
+            self.prob.mm_peer_rec[r] = rec.ptrs[r]
+            self.prob.mm_peer_gather[r] = gather.ptrs[r]
+        self.prob.mm_local_state = state.data_ptr()
 
     # -- optimiser -----------------------------------------------------------------------------
     def _hyper_now(self):
@@ -379,12 +399,16 @@ def mc_pilco(init_states, dynamics, policy, steps, opt=None, exp=None, opt_iters
     if world > 1:
         if prioritized_replay:
             raise NotEligible("prioritized replay keeps one host-side sum tree; not sharded across ranks")
-        if mm_states or mm_rewards:
-            raise NotEligible("moment matching across ranks needs a per-step reduction (SURVEY.md 8e/8f)")
+        if (mm_states or mm_rewards) and (backend() == "eager" or not pegasus or mm_groups):
+            raise NotEligible("moment matching across ranks runs on the fused engine (pegasus=True, one matching group): "
+                              "the per-step statistics are exchanged over peer memory inside the sweeps")
         sharder = dist.ShardedNoise(dynamics, policy, N_particles, rank, world)
     fast = (mode != "eager" and dev.type == "cuda"
             and _on_device_loop_ok(value_func, cvar_eps, reg_weight, prioritized_replay, opt, policy,
                                    on_rollout, debug, rollout_kwargs))
+    if world > 1 and (mm_states or mm_rewards) and not fast:
+        raise NotEligible("moment matching across ranks runs on the fused engine only (CUDA modules, plain Adam, no "
+                          "per-iteration python hooks)")
     engine = None
     readback, pending = None, None
     pbar = tqdm.tqdm(range(opt_iters), total=opt_iters, disable=os.environ.get("PMB_NO_PBAR") == "1")

@@ -36,6 +36,18 @@ def test_sharded_iteration_equals_single_gpu(nranks, sync):
 
 
 @pytest.mark.parametrize("nranks", [2, 4])
+def test_sharded_moment_matching_equals_single_gpu(nranks):
+    """moment matching of states and rewards over the particles of ALL ranks -- per-step records and arrivals
+    over NVLink peer memory inside the cluster-resident sweeps, the rewards through a peer all-gather -- reproduces the
+    single-GPU mc_pilco on the same global batch (parameters after 4 iterations incl. a PEGASUS resample)."""
+    if torch.cuda.device_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    out = _torchrun(nranks, [os.path.join(ROOT, "scripts", "dist_check.py")], 420, DIST_MM="1")
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert "DIST PASS mm=1" in out.stdout, out.stdout[-1500:]
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
 def test_bench_runs_sharded_with_a_rank_agreed_iteration_count(nranks):
     """r1's SCALE run died at N=4: a wall-clock-bounded warm-up issued a rank-dependent number of all-reduces.
     Three back-to-back short runs must all return one JSON line with rc 0."""
