@@ -454,8 +454,13 @@ class Harness:
         out = {"config": workload_config(cfg, n_per, world), "n_gpus": world, "steps": steps,
                "value": w["n_global"] * w["H"] * steps / (ms * 1e-3), "unit": "rollout-steps/s",
                "ms_per_step": ms / steps, "clocks": clk, "loss": float(w["eng"].loss)}
-        if self.rank == 0:
+        # per-kernel times are rank 0's; with moment matching across ranks the sweeps of every rank take part in the
+        # per-step exchange, so every rank has to run the same phase launches
+        if self.rank == 0 or (w["mm"] is not None and world > 1):
             kern = self.kernel_times(w)
+            if world > 1:
+                self.barrier()
+        if self.rank == 0:
             out["kernels_ms"] = kern
             out["roofline"] = self.roofline(cfg, w, kern)
         w["sharder"].widen()

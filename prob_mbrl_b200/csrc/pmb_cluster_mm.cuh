@@ -51,14 +51,16 @@ struct CMM {
 // Every cluster of the grid meets here, once per step: all threads of the cluster (both particle tiles of its 8 CTAs)
 // join a hardware cluster barrier, rank 0 arrives on the global counter for the cluster, one thread per CTA polls it
 // (`target` = arrivals expected so far = clusters x steps).
-__device__ __forceinline__ void cmm_barrier(const ClusterParams &prm, unsigned target, int rank) {
+__device__ __forceinline__ void cmm_barrier(const ClusterParams &prm, unsigned target, int rank, bool wrote) {
     // release pattern: the record writers' stores are ordered before the cluster barrier (its arrive.release is a
     // gpu-level membar in SASS; the explicit acq_rel fence keeps the PTX model honest and is cheaper than the
     // sequentially consistent __threadfence()), rank 0 then publishes with a release reduction.  Across GPUs the
     // same at system scope: the records went to every rank's memory, the arrival goes to every rank's counter.
+    // Only the threads that wrote record entries fence (`wrote`): the cluster barrier orders them before rank 0's
+    // release; a fence by all 256 threads of every CTA has to drain every outstanding trajectory store first.
     unsigned *ctr = prm.mmctr;
     if (prm.mm_world > 1) {
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (wrote) asm volatile("fence.acq_rel.sys;" ::: "memory");
         cl_sync();
         if (threadIdx.x == 0) {
             if (rank == 0)
@@ -71,7 +73,7 @@ __device__ __forceinline__ void cmm_barrier(const ClusterParams &prm, unsigned t
             } while ((int)(v - target) < 0);
         }
     } else {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (wrote) asm volatile("fence.acq_rel.gpu;" ::: "memory");
         cl_sync();
         if (threadIdx.x == 0) {
             if (rank == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -157,7 +159,7 @@ __device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, int g, i
     const int nq = prm.D + prm.D * (prm.D + 1) / 2;
     if (rank == 0)
         for (int q = gtid; q < nq; q += CL_GT) cmm_publish(prm, t & 1, g, nq, q, 0.0);
-    cmm_barrier(prm, target, rank);
+    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
 }
 
 // constants of the launch: mean and 1 / unbiased std of the z_mm rows (all N rows take part in every step)
@@ -239,7 +241,7 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
         }
     }
     CMM_MARK(0);
-    cmm_barrier(prm, target, rank);
+    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
     CMM_MARK(1);
     cmm_combine(M, rec, ntiles, nq, g, gtid);
     if (gtid < D) {
@@ -314,7 +316,7 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
             cmm_publish(prm, t & 1, g, nq, q, a);
         }
     }
-    cmm_barrier(prm, target, rank);
+    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
     cmm_combine(M, rec, ntiles, nq, g, gtid);
     for (int q = gtid; q < nq; q += CL_GT) {
         if (q < D) {
