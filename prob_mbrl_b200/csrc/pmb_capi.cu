@@ -807,7 +807,7 @@ static int build_plan(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) {
         pl.rpre_off = ws.take(HN);
         pl.rstat_off = ws.take((long long)p->H * G * 4);
         pl.geff_off = ws.take(HN);
-        pl.cmm_gbuf_off = ws.take(2LL * 2 * CMM_TILES * CMM_NQ);     // doubles: [2][tiles][CMM_NQ] records of the cluster sweeps
+        pl.cmm_gbuf_off = ws.take(2LL * 2 * 2 * CMM_TILES * CMM_NQ); // [2 parities][tiles][nq] 16-byte tagged records of the cluster sweeps
         pl.mm_world = p->mm_world > 1 ? p->mm_world : 1;
         if (pl.mm_world > 1 && p->mm_rewards) {
             const long long HNg = (long long)p->H * p->n_global;
@@ -937,7 +937,7 @@ static MmExchange mm_exchange(const pmb_problem *p, const Plan &pl) {
     MmExchange x;
     x.nq = p->D + p->D * (p->D + 1) / 2;
     x.ntiles_total = 2 * (pl.cluster ? pl.cl_nclusters : 1) * (p->mm_world > 1 ? p->mm_world : 1);
-    x.sweep_doubles = (size_t)2 * x.ntiles_total * x.nq;
+    x.sweep_doubles = (size_t)2 * x.ntiles_total * x.nq * 2;      // [2 parities][tiles][nq] 16-byte tagged entries
     x.ctr_off = (2 * x.sweep_doubles * sizeof(double) + 255) & ~(size_t)255;
     x.rec_bytes = x.ctr_off + 256;
     x.gather_bytes = pmb_peer_buffer_bytes((long long)p->H * p->N, p->mm_world > 1 ? p->mm_world : 1);
@@ -1089,8 +1089,12 @@ int pmb_rollout_forward(const pmb_problem *p, const pmb_tuning *tune, const floa
     F.x0 = x0; F.states = states; F.actions = actions; F.status = status_dev;
     // with mm_rewards the sweep writes the pre-matching rewards; a whole-horizon kernel matches them
     F.rewards = p->mm_rewards ? wsf + pl.rpre_off : rewards;
-    // (across GPUs the arrival counters live in peer-mapped memory and are never reset: a peer may already be a launch ahead)
-    if (p->mm_states && !pl.tc && !sharded_mm) PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
+    // (across GPUs the record areas live in peer-mapped memory and are never reset -- a peer may already be a launch
+    // ahead --, the tags just keep growing; on one GPU the tags restart at 1 with every launch, so the area is zeroed)
+    if (p->mm_states && !pl.tc && !sharded_mm) {
+        PMB_CUDA(cudaMemsetAsync(wsf + pl.mmctr_off, 0, 32 * sizeof(float), st));
+        if (pl.cluster) PMB_CUDA(cudaMemsetAsync(wsf + pl.cmm_gbuf_off, 0, sizeof(float) * 2 * 2 * 2 * CMM_TILES * CMM_NQ, st));
+    }
     F.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     if (pl.tc) {
         TcParams &T = pl.tfwd;
@@ -1162,8 +1166,10 @@ int pmb_rollout_backward(const pmb_problem *p, const pmb_tuning *tune, const flo
             B.g_rewards = ws + pl.geff_off;
         }
     }
-    if (p->mm_states && !pl.tc && !sharded_mm)
+    if (p->mm_states && !pl.tc && !sharded_mm) {
         PMB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned *>(ws + pl.mmctr_off) + 1, 0, sizeof(unsigned), st));
+        if (pl.cluster) PMB_CUDA(cudaMemsetAsync(ws + pl.cmm_gbuf_off, 0, sizeof(float) * 2 * 2 * 2 * CMM_TILES * CMM_NQ, st));
+    }
     B.dbg = tune ? (long long *)(((unsigned long long)(unsigned)tune->reserved[3] << 32) | (unsigned)tune->reserved[2]) : nullptr;
     const int phases = (tune && (tune->reserved[0] & 255)) ? (tune->reserved[0] & 255) : 7;   // profiling aid: 2 sweep, 4 wgrad
     if (pl.tc) {

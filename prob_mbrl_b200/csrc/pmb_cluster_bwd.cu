@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_bwd_kernel(const __grid_cons
         prm.dx0[(size_t)(n0g + b_p) * D + b_d] = gs[b_p * SD + b_d];
     } else if (mm) {
         // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
-        for (int it = 0; it < H; ++it) cmm_idle_step(prm, g, gtid, rank, H - 1 - it, mm_base + (unsigned)(it + 1) * mm_ncl);
+        for (int it = 0; it < H; ++it) cmm_idle_step(prm, M, g, gtid, rank, H - 1 - it, mm_base + (unsigned)(it + 1) * mm_ncl);
     }
     if (mm && prm.mm_base_next && blockIdx.x == 0 && tid == 0) *prm.mm_base_next = (unsigned long long)(mm_base + (unsigned)H * mm_ncl);
     cl_sync();          // no CTA leaves while a peer could still address its shared memory

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(CL_NT, 1) cluster_fwd_kernel(const __grid_cons
     }
     } else if (mm) {
         // an idle tile still takes part in the per-step exchange (cluster barrier + CTA barrier)
-        for (int t = 0; t < H; ++t) cmm_idle_step(prm, g, gtid, rank, t, mm_base + (unsigned)(t + 1) * mm_ncl);
+        for (int t = 0; t < H; ++t) cmm_idle_step(prm, M, g, gtid, rank, t, mm_base + (unsigned)(t + 1) * mm_ncl);
     }
     // across GPUs the arrival counters are never reset: leave the count this launch ends at for the next one (every CTA
     // read the old value before its first exchange, and cluster 0 is past the last one)

@@ -1,13 +1,14 @@
 // Moment matching of the states inside the cluster-resident sweeps (reference utils/rollout.py:20-29,121-145):
 //   x' = m + zhat chol(S)^T,  m = mean_n x,  S = (x-m)^T (x-m)/(N-1) + 1e-12 I,
 //   zhat = (z - mean z) / std_unbiased(z) per column, z = z_mm[(t + n) mod N] (rollout.py:53-59).
-// The particles live in <= 15 clusters, so every step needs ONE cross-cluster exchange: one CTA per cluster
+// The particles live in <= 15 clusters (per GPU), so every step needs ONE cross-cluster exchange: one CTA per cluster
 // (rank 0 of the cluster) publishes the raw moments of each of its two particle tiles (sum x, sum x x^T in double:
-// products of two floats are exact), every cluster arrives on a global counter (hardware cluster barrier + one
-// atomic per cluster + one poller per CTA), and after the barrier every tile adds the <= 30 records in tile order --
-// deterministic and identical everywhere.  One matching group only (the whole particle set), N <= 128: with a single
-// group the z rows of a step are a rotation of the same set, so their mean / std are constants of the launch.  The reverse step is the hand-derived adjoint of
-// oracle/rollout_oracle.py::mm_backward (same formulas as pmb_mm.cuh).
+// products of two floats are exact) as tagged 8-byte words, and every tile of every CTA polls the <= 30 records per
+// GPU until they carry the step's tag and adds them in tile order -- deterministic and identical everywhere, no fence,
+// counter or barrier (cmm_publish / cmm_fetch).  Across the GPUs of a node the same stores go to every rank's record
+// area over NVLink.  One matching group only (the whole particle set): with a single group the z rows of a step are a
+// rotation of the same set, so their mean / std are constants of the launch.  The reverse step is the hand-derived
+// adjoint of oracle/rollout_oracle.py::mm_backward (same formulas as pmb_mm.cuh).
 #pragma once
 #include "pmb_cluster.cuh"
 
@@ -48,48 +49,6 @@ struct CMM {
     }
 };
 
-// Every cluster of the grid meets here, once per step: all threads of the cluster (both particle tiles of its 8 CTAs)
-// join a hardware cluster barrier, rank 0 arrives on the global counter for the cluster, one thread per CTA polls it
-// (`target` = arrivals expected so far = clusters x steps).
-__device__ __forceinline__ void cmm_barrier(const ClusterParams &prm, unsigned target, int rank, bool wrote) {
-    // release pattern: the record writers' stores are ordered before the cluster barrier (its arrive.release is a
-    // gpu-level membar in SASS; the explicit acq_rel fence keeps the PTX model honest and is cheaper than the
-    // sequentially consistent __threadfence()), rank 0 then publishes with a release reduction.  Across GPUs the
-    // same at system scope: the records went to every rank's memory, the arrival goes to every rank's counter.
-    // Only the threads that wrote record entries fence (`wrote`): the cluster barrier orders them before rank 0's
-    // release; a fence by all 256 threads of every CTA has to drain every outstanding trajectory store first.
-    unsigned *ctr = prm.mmctr;
-    if (prm.mm_world > 1) {
-        if (wrote) asm volatile("fence.acq_rel.sys;" ::: "memory");
-        cl_sync();
-        if (threadIdx.x == 0) {
-            if (rank == 0)
-                for (int p = 0; p < prm.mm_world; ++p)
-                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.mmctr_peer[p]) : "memory");
-            unsigned v, spins = 0;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-                if (++spins > (1u << 28)) __trap();
-            } while ((int)(v - target) < 0);
-        }
-    } else {
-        if (wrote) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        cl_sync();
-        if (threadIdx.x == 0) {
-            if (rank == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-            unsigned v, spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-                if (++spins > (1u << 26)) __trap();
-            } while ((int)(v - target) < 0);
-        }
-    }
-    __syncwarp();               // the polling lane rejoins its warp
-    // both particle tiles of the CTA (active or idle, i.e. from different call sites) meet on a named barrier:
-    // __syncthreads() would have to be reached through identical control flow by the whole block
-    asm volatile("barrier.sync 6, 256;" ::: "memory");
-}
-
 // lower-triangle index q = i (i + 1) / 2 + j  ->  (i, j)
 __device__ __forceinline__ void cmm_init_qtab(const CMM &M, int D, int gtid) {
     for (int q = gtid; q < D * (D + 1) / 2; q += CL_GT) {
@@ -99,67 +58,96 @@ __device__ __forceinline__ void cmm_init_qtab(const CMM &M, int D, int gtid) {
     }
 }
 __device__ __forceinline__ unsigned cmm_clusters(int N, int PG) { return (unsigned)((N + PG - 1) / PG); }
-// arrivals per step on every rank's counter: the clusters of all ranks
-__device__ __forceinline__ unsigned cmm_arrivals(const ClusterParams &prm) {
-    return cmm_clusters(prm.N, prm.PG) * (unsigned)max(prm.mm_world, 1);
-}
-// first arrival count of this launch (0 on one GPU, where the counter is zeroed before the launch)
+// Exchange protocol ("LL": flag in the data): a record entry is a double cut into two 8-byte words, each carrying 32
+// data bits and the 32-bit tag of the step -- an aligned 8-byte store is single-copy atomic, so a reader that sees the
+// tag in both words has the value, with no fence, counter or barrier anywhere: the writer (rank 0 of a cluster, or of
+// any cluster of any GPU of the node) never waits, a reader only waits for writers, and the two particle tiles of a CTA
+// no longer meet.  Tags grow by one per step; entries are double-buffered by step parity because a writer can be at most
+// one step ahead of a reader (it needs the reader's next record to go further).
+__device__ __forceinline__ unsigned cmm_arrivals(const ClusterParams &) { return 1u; }     // tag increment per step
+// tag before the first step of this launch: 0 on one GPU (the record area is zeroed before every launch), the count the
+// previous launch left across GPUs (peer-mapped areas are never reset: a peer may already be a launch ahead)
 __device__ __forceinline__ unsigned cmm_base(const ClusterParams &prm) {
     return prm.mm_base ? (unsigned)__ldcg(prm.mm_base) : 0u;
 }
 // record entry q of this tile (2 cluster + g) for step parity `par`: to the own record area, or to every rank's
-__device__ __forceinline__ void cmm_publish(const ClusterParams &prm, int par, int g, int nq, int q, double a) {
+__device__ __forceinline__ void cmm_publish(const ClusterParams &prm, int par, int g, int nq, int q, double a, unsigned tag) {
     const int tl = 2 * (int)cmm_clusters(prm.N, prm.PG);           // tiles of one rank
     const int world = max(prm.mm_world, 1);
     const size_t idx = ((size_t)par * world * tl + (size_t)prm.mm_rank * tl + 2 * (blockIdx.x / prm.C) + g) * nq + q;
-    if (world > 1) {
-        for (int p = 0; p < world; ++p) prm.mmrec_peer[p][idx] = a;
-    } else {
-        prm.mmrec[idx] = a;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(a), hi = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (bits & 0xffffffffull) | hi, w1 = (bits >> 32) | hi;
+    for (int p = 0; p < world; ++p) {
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(world > 1 ? prm.mmrec_peer[p] : prm.mmrec) + idx;
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+    }
+}
+// entries i, i + 128, ... (< n, up to 4) of the record area once both words of each carry `tag`: all loads of a round in
+// flight at once (one L2 / NVLink round trip per round, not per entry)
+__device__ __forceinline__ void cmm_fetch4(const ulonglong2 *rec, int i, int n, unsigned tag, double *stage) {
+    unsigned long long w0[4], w1[4], spins = 0;
+    bool need[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) need[k] = i + k * CL_GT < n;
+    for (;;) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (need[k]) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[k]), "=l"(w1[k]) : "l"(rec + i + k * CL_GT) : "memory");
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (need[k]) {
+                if ((unsigned)(w0[k] >> 32) == tag && (unsigned)(w1[k] >> 32) == tag) {
+                    stage[i + k * CL_GT] = __longlong_as_double((long long)((w1[k] << 32) | (w0[k] & 0xffffffffull)));
+                    need[k] = false;
+                } else {
+                    any = true;
+                }
+            }
+        }
+        if (!any) break;
+        if (++spins > (1ull << 27)) __trap();          // a writer that never shows up must not hang the GPU forever
     }
 }
 
-// totals of the step: M.red[q] = sum over the particle tiles of the grid of their records, in tile order (identical on
-// every tile).  Records: rec[(2 cluster + g) * nq + q], written by rank 0 of the cluster.  Kept small on purpose: the
-// sweeps live off the instruction cache, single-warp code that is fetched from L2 runs at ~10 cycles per instruction.
-__device__ __forceinline__ void cmm_combine(const CMM &M, const double *rec, int ntiles, int nq, int g, int gtid) {
-    const int n = ntiles * nq;
-    const bool staged = n <= CMM_TILES * 16;
-    if (staged) {
-        // all loads of a thread in flight at once (<= 8 per thread): one L2 round trip, not one per record
-        double v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = gtid + k * CL_GT < n ? __ldcg(rec + gtid + k * CL_GT) : 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (gtid + k * CL_GT < n) M.stage[gtid + k * CL_GT] = v[k];
+// totals of the step: M.red[q] = sum over the particle tiles of all ranks of their records, in tile order (identical on
+// every tile).  Records: entry (2 cluster + g) * nq + q of a rank's block, written by rank 0 of the cluster.  Staged in
+// passes of whole tiles (<= CMM_TILES * 16 entries); 16 quantities at a time: thread = (quantity, chunk of tiles c,
+// c + 8, ...), then a 3-level butterfly over the 8 chunks -- a fixed tree.  Kept small on purpose: single-warp code runs
+// at ~10 cycles per instruction here.
+__device__ __forceinline__ void cmm_combine(const CMM &M, const double *recd, int ntiles, int nq, unsigned tag, int g, int gtid) {
+    const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(recd);
+    const int tpp = (CMM_TILES * 16) / nq;                 // tiles per pass
+#pragma unroll 1
+    for (int t0 = 0; t0 < ntiles; t0 += tpp) {
+        const int nt = min(tpp, ntiles - t0), n = nt * nq;
+        for (int i = gtid; i < n; i += 4 * CL_GT) cmm_fetch4(rec + t0 * nq, i, n, tag, M.stage);
+        CT_SYNC(g);
+#pragma unroll 1
+        for (int q0 = 0; q0 < nq; q0 += 16) {
+            const int q = q0 + (gtid >> 3), c = gtid & 7;
+            double a = 0.0;
+            if (q < nq) {
+#pragma unroll 1
+                for (int tl = c; tl < nt; tl += 8) a += M.stage[tl * nq + q];
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            if (q < nq && c == 0) M.red[q] = t0 ? M.red[q] + a : a;
+        }
         CT_SYNC(g);
     }
-    // 16 quantities per pass: thread = (quantity, chunk of tiles c, c + 8, ...), then a 3-level butterfly over the 8 chunks
-    // -- a fixed tree, identical on every tile; single-thread loops run at ~10 cycles per instruction here
-#pragma unroll 1
-    for (int q0 = 0; q0 < nq; q0 += 16) {
-        const int q = q0 + (gtid >> 3), c = gtid & 7;
-        double a = 0.0;
-        if (q < nq) {
-            const double *r = staged ? M.stage + q : rec + q;
-#pragma unroll 1
-            for (int tl = c; tl < ntiles; tl += 8) a += staged ? r[tl * nq] : __ldcg(r + tl * nq);
-        }
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (q < nq && c == 0) M.red[q] = a;
-    }
-    CT_SYNC(g);
 }
 
-// an idle tile (no particles) still takes part in the per-step exchange: an all-zero record, the barriers
-__device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, int g, int gtid, int rank, int t, unsigned target) {
+// an idle tile (no particles) still takes part in the per-step exchange: an all-zero record -- and it waits for the
+// step's records like everybody else, which is what keeps it from running more than one step (= one parity slot) ahead
+__device__ __forceinline__ void cmm_idle_step(const ClusterParams &prm, const CMM &M, int g, int gtid, int rank, int t, unsigned tag) {
     const int nq = prm.D + prm.D * (prm.D + 1) / 2;
+    const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG) * max(prm.mm_world, 1);
     if (rank == 0)
-        for (int q = gtid; q < nq; q += CL_GT) cmm_publish(prm, t & 1, g, nq, q, 0.0);
-    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
+        for (int q = gtid; q < nq; q += CL_GT) cmm_publish(prm, t & 1, g, nq, q, 0.0, tag);
+    cmm_combine(M, prm.mmrec + (size_t)(t & 1) * ntiles * nq * 2, ntiles, nq, tag, g, gtid);
 }
 
 // constants of the launch: mean and 1 / unbiased std of the z_mm rows (all N rows take part in every step)
@@ -221,7 +209,7 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
     const int nq = D + D * (D + 1) / 2;
     const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG) * max(prm.mm_world, 1);
     float *s1pre = const_cast<float *>(prm.s1pre);
-    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq;
+    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq * 2;      // 16-byte entries
     if (roleB) {
         M.xrow[b_p * SD + b_d] = s_reg;
         if (b_own) s1pre[((size_t)t * prm.N + b_n) * D + b_d] = s_reg;
@@ -237,13 +225,12 @@ __device__ __forceinline__ void cmm_forward(const ClusterParams &prm, const CMM 
                 const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
                 for (int p = 0; p < nvg; ++p) a += (double)M.xrow[p * SD + i] * (double)M.xrow[p * SD + j];
             }
-            cmm_publish(prm, t & 1, g, nq, q, a);
+            cmm_publish(prm, t & 1, g, nq, q, a, target);
         }
     }
     CMM_MARK(0);
-    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
+    cmm_combine(M, rec, ntiles, nq, target, g, gtid);
     CMM_MARK(1);
-    cmm_combine(M, rec, ntiles, nq, g, gtid);
     if (gtid < D) {
         M.dmean[gtid] = M.red[gtid] / N;
         M.st[gtid] = (float)M.dmean[gtid];
@@ -301,7 +288,7 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
     const int D = prm.D, N = prm.n_global;
     const int nq = D + D * (D + 1) / 2;
     const int ntiles = 2 * (int)cmm_clusters(prm.N, prm.PG) * max(prm.mm_world, 1);
-    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq;
+    const double *rec = prm.mmrec + (size_t)(t & 1) * ntiles * nq * 2;      // 16-byte entries
     CT_SYNC(g);         // the prefetched rows are in place
     // record of this tile: dm = sum_p g_p (q < D);  dL = tril(sum_p g_p zhat_p^T) (q = D + i (i + 1) / 2 + j)
     if (rank == 0) {
@@ -313,11 +300,10 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
                 const int ij = M.qtab[q - D], i = ij >> 8, j = ij & 255;
                 for (int p = 0; p < nvg; ++p) a += (double)gs[p * SD + i] * (double)M.zrow[p * SD + j];
             }
-            cmm_publish(prm, t & 1, g, nq, q, a);
+            cmm_publish(prm, t & 1, g, nq, q, a, target);
         }
     }
-    cmm_barrier(prm, target, rank, rank == 0 && gtid < nq);
-    cmm_combine(M, rec, ntiles, nq, g, gtid);
+    cmm_combine(M, rec, ntiles, nq, target, g, gtid);
     for (int q = gtid; q < nq; q += CL_GT) {
         if (q < D) {
             M.dm[q] = (float)M.red[q];
