@@ -456,9 +456,10 @@ class Harness:
                "ms_per_step": ms / steps, "clocks": clk, "loss": float(w["eng"].loss)}
         # per-kernel times are rank 0's; with moment matching across ranks the sweeps of every rank take part in the
         # per-step exchange, so every rank has to run the same phase launches
-        if self.rank == 0 or (w["mm"] is not None and world > 1):
+        all_ranks = w["mm"] is not None and world > 1
+        if self.rank == 0 or all_ranks:
             kern = self.kernel_times(w)
-            if world > 1:
+            if all_ranks:
                 self.barrier()
         if self.rank == 0:
             out["kernels_ms"] = kern
