@@ -175,7 +175,42 @@ __device__ __forceinline__ void cmm_z_statistics(const ClusterParams &prm, const
 // count is what matters: one rsqrtf per pivot (MUFU.RSQ, <= 2 ulp) replaces the IEEE square root and the column's
 // divisions -- a deliberate deviation of a few ulp in L, the size of the reordering error between any two fp32
 // Cholesky implementations.
+// ... in registers for D <= DD (the matrix never touches shared memory between the first load and the last store:
+// the loop version below spends its time in dependent LDS / STS round trips)
+template <int DD>
+__device__ __forceinline__ bool cmm_cholesky_reg(const CMM &M, int D) {
+    float a[DD][DD], rinv[DD];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < DD; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i][j] = (i < D) ? M.A[i * SD + j] : (i == j ? 1.f : 0.f);
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {          // column by column (right-looking: same subtraction order per entry)
+        float d = a[j][j];
+        if (!(d > 0.f)) { if (j < D) ok = false; d = 1.f; }
+        rinv[j] = rsqrtf(d);
+        a[j][j] = d * rinv[j];
+#pragma unroll
+        for (int i = j + 1; i < DD; ++i) a[i][j] *= rinv[j];
+#pragma unroll
+        for (int k = j + 1; k < DD; ++k)
+#pragma unroll
+            for (int i = k; i < DD; ++i) a[i][k] = fmaf(-a[i][j], a[k][j], a[i][k]);
+    }
+#pragma unroll
+    for (int i = 0; i < DD; ++i) {
+        if (i < D) {
+            M.rinv[i] = rinv[i];
+#pragma unroll
+            for (int j = 0; j < DD; ++j)
+                if (j < D) M.L[i * SD + j] = j <= i ? a[i][j] : 0.f;
+        }
+    }
+    return ok;
+}
 __device__ __forceinline__ bool cmm_cholesky(const CMM &M, int D) {
+    if (D <= 6) return cmm_cholesky_reg<6>(M, D);
     bool ok = true;
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
@@ -325,7 +360,45 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
         M.A[i * SD + j] = a;
     }
     CT_SYNC(g);
-    // X = L^-T A  (back substitution, one column per thread; reciprocal pivots M.rinv formed once per step above)
+    // X = L^-T A  (back substitution, one column per thread; reciprocal pivots M.rinv formed once per step above);
+    // in registers for D <= 6 (dependent LDS / STS round trips are what the loop version spends its time on)
+    if (D <= 6) {
+        constexpr int DD = 6;
+        float l[DD][DD], ri[DD], x[DD];
+        if (gtid < D) {
+#pragma unroll
+            for (int i = 0; i < DD; ++i) {
+                ri[i] = i < D ? M.rinv[i] : 0.f;
+#pragma unroll
+                for (int k = 0; k <= i; ++k) l[i][k] = i < D ? M.L[i * SD + k] : 0.f;
+            }
+#pragma unroll
+            for (int r = DD - 1; r >= 0; --r) {
+                float sacc = r < D ? M.A[r * SD + gtid] : 0.f;
+#pragma unroll
+                for (int k = r + 1; k < DD; ++k) sacc = fmaf(-l[k][r], x[k], sacc);
+                x[r] = sacc * ri[r];
+            }
+#pragma unroll
+            for (int r = 0; r < DD; ++r)
+                if (r < D) M.X[r * SD + gtid] = x[r];
+        }
+        CT_SYNC(g);
+        // Sb = X L^-1  (one row per thread)
+        if (gtid < D) {
+#pragma unroll
+            for (int c = DD - 1; c >= 0; --c) {
+                float sacc = c < D ? M.X[gtid * SD + c] : 0.f;
+#pragma unroll
+                for (int k = c + 1; k < DD; ++k) sacc = fmaf(-x[k], l[k][c], sacc);
+                x[c] = sacc * ri[c];
+            }
+#pragma unroll
+            for (int c = 0; c < DD; ++c)
+                if (c < D) M.Sb[gtid * SD + c] = x[c];
+        }
+        CT_SYNC(g);
+    } else {
     if (gtid < D) {
         const int j = gtid;
 #pragma unroll 1
@@ -349,6 +422,7 @@ __device__ __forceinline__ void cmm_backward(const ClusterParams &prm, const CMM
         }
     }
     CT_SYNC(g);
+    }
     // dx_n = dm/N + 2/(N-1) * sym(Sb) (x_n - m)
     if (roleB) {
         float a = 0.f;
