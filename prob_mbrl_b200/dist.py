@@ -89,24 +89,44 @@ class PeerBuffer:
         self.rank, self.world = world()
         if self.world > 16:
             raise ValueError("the peer-memory exchange serves one node (<= 16 GPUs)")
+        # Every rank takes part in every collective below whatever happens locally (a rank that raised half-way would
+        # leave the others hanging): failures are recorded in self.error and agreed on by the caller (all_ok()).
+        self.error, self.own, self.opened = None, None, []
+        self.ptrs = (C.c_void_p * self.world)()
         with torch.cuda.device(device):
             own, handle = C.c_void_p(), C.create_string_buffer(64)
-            self._check(self.lib.pmb_peer_alloc(int(nbytes), C.byref(own), handle))
-            self.own = own.value
+            try:
+                self._check(self.lib.pmb_peer_alloc(int(nbytes), C.byref(own), handle))
+                self.own = own.value
+            except _lib.LibraryError as e:
+                self.error = e
             handles = [None] * self.world
-            torch.distributed.all_gather_object(handles, bytes(handle.raw))
-            self.opened = []
-            self.ptrs = (C.c_void_p * self.world)()
+            torch.distributed.all_gather_object(handles, bytes(handle.raw) if self.error is None else b"")
+            if self.error is None and any(len(h) != 64 for h in handles):
+                self.error = _lib.LibraryError(-4, "a peer could not allocate its exchange buffer")
             for r, h in enumerate(handles):
+                if self.error is not None:
+                    break
                 if r == self.rank:
                     self.ptrs[r] = self.own
                 else:
                     p = C.c_void_p()
-                    self._check(self.lib.pmb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                    try:
+                        # fails across nodes, or between devices without peer access: the caller falls back
+                        self._check(self.lib.pmb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                    except _lib.LibraryError as e:
+                        self.error = e
+                        break
                     self.opened.append(p.value)
                     self.ptrs[r] = p.value
             torch.cuda.synchronize()
         torch.distributed.barrier()         # every buffer is zeroed and mapped before anyone writes
+
+    def all_ok(self, device):
+        """Collective: True when every rank allocated and mapped everything."""
+        flag = torch.tensor([0 if self.error is not None else 1], dtype=torch.int32, device=device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        return bool(int(flag.item()))
 
     def _check(self, rc):
         if rc != 0:
@@ -114,12 +134,13 @@ class PeerBuffer:
             raise _lib.LibraryError(rc, self.lib.pmb_peer_last_error().decode("utf-8", "replace"))
 
     def close(self):
-        if getattr(self, "own", None) is None:
+        if getattr(self, "own", None) is None and not getattr(self, "opened", None):
             return
         torch.cuda.synchronize()
         for p in self.opened:
             self.lib.pmb_peer_close(p)
-        self.lib.pmb_peer_free(self.own)
+        if self.own is not None:
+            self.lib.pmb_peer_free(self.own)
         self.own, self.opened = None, []
 
     def __del__(self):
@@ -132,66 +153,30 @@ class PeerBuffer:
 class PeerAllReduce:
     """The gradient all-reduce over NVLink peer memory (``pmb_peer_allreduce``): stream-ordered kernels, no NCCL call,
     capturable in the iteration's CUDA graph, results bitwise identical on every rank.  Construction is collective
-    (every rank of the default process group, same ``n``): exchange buffers are cudaMalloc'ed by the library, their
-    CUDA IPC handles travel through ``all_gather_object``."""
+    (every rank of the default process group, same ``n``)."""
 
     def __init__(self, n, device):
-        import ctypes as C
         from . import _lib
         self.lib = _lib.load()
-        self.rank, self.world = world()
         self.n = int(n)
-        if self.world > 16:
-            raise ValueError("the peer-memory exchange serves one node (<= 16 GPUs)")
-        with torch.cuda.device(device):
-            nbytes = self.lib.pmb_peer_buffer_bytes(self.n, self.world)
-            own, handle = C.c_void_p(), C.create_string_buffer(64)
-            self._check(self.lib.pmb_peer_alloc(nbytes, C.byref(own), handle))
-            self.own = own.value
-            handles = [None] * self.world
-            torch.distributed.all_gather_object(handles, bytes(handle.raw))
-            self.opened = []
-            self.ptrs = (C.c_void_p * self.world)()
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.ptrs[r] = self.own
-                else:
-                    p = C.c_void_p()
-                    self._check(self.lib.pmb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
-                    self.opened.append(p.value)
-                    self.ptrs[r] = p.value
-            self.state = torch.zeros(3, dtype=torch.int64, device=device)
-            torch.cuda.synchronize()
-        torch.distributed.barrier()         # every buffer is zeroed and mapped before the first push
-
-    def _check(self, rc):
-        if rc != 0:
-            from . import _lib
-            raise _lib.LibraryError(rc, self.lib.pmb_peer_last_error().decode("utf-8", "replace"))
+        self.rank, self.world = world()
+        self.buf = PeerBuffer(self.lib.pmb_peer_buffer_bytes(self.n, min(self.world, 16)), device)
+        self.state = torch.zeros(3, dtype=torch.int64, device=device)
+        self.ok = self.buf.all_ok(device)
 
     def __call__(self, flat, loss=None):
         """In-place sum of ``flat`` (float32, ``n`` elements, contiguous) over the ranks, on the current stream."""
         from . import _lib
         assert flat.numel() == self.n and flat.dtype == torch.float32 and flat.is_contiguous()
-        self._check(self.lib.pmb_peer_allreduce(flat.data_ptr(), flat.data_ptr(), self.n, self.world, self.rank,
-                                                self.ptrs, self.state.data_ptr(), _lib.current_stream_ptr()))
+        rc = self.lib.pmb_peer_allreduce(flat.data_ptr(), flat.data_ptr(), self.n, self.world, self.rank, self.buf.ptrs,
+                                         self.state.data_ptr(), _lib.current_stream_ptr())
+        if rc != 0:
+            raise _lib.LibraryError(rc, self.lib.pmb_peer_last_error().decode("utf-8", "replace"))
         if loss is not None:
             torch.distributed.all_reduce(loss)
 
     def close(self):
-        if getattr(self, "own", None) is None:
-            return
-        torch.cuda.synchronize()
-        for p in self.opened:
-            self.lib.pmb_peer_close(p)
-        self.lib.pmb_peer_free(self.own)
-        self.own, self.opened = None, []
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        self.buf.close()
 
 
 def gradient_sync(n, device):
@@ -202,4 +187,12 @@ def gradient_sync(n, device):
         return None
     if os.environ.get("PMB_GRAD_SYNC", "peer") == "nccl":
         return allreduce_gradient
-    return PeerAllReduce(n, device)
+    peer = PeerAllReduce(n, device)
+    if not peer.ok:
+        # e.g. ranks on different nodes, or devices without peer access: every rank agrees on the NCCL all-reduce
+        import warnings
+        warnings.warn("prob_mbrl_b200: peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce"
+                      % (peer.buf.error,))
+        peer.close()
+        return allreduce_gradient
+    return peer

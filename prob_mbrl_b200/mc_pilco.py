@@ -173,6 +173,10 @@ class FusedIteration:
             _lib.check(self.lib.pmb_mm_exchange_bytes(C.byref(self.prob), C.byref(self.tune), sizes))
             self.mm_exchange = (dist.PeerBuffer(sizes[0], self.dev), dist.PeerBuffer(sizes[1], self.dev),
                                 torch.zeros(max(int(sizes[2]) // 8, 8), dtype=torch.int64, device=self.dev))
+            ok = [b.all_ok(self.dev) for b in self.mm_exchange[:2]]
+            if not all(ok):
+                raise NotEligible("moment matching across ranks needs peer-mapped memory between the GPUs of one node "
+                                  "(%s)" % (self.mm_exchange[0].error or self.mm_exchange[1].error,))
         rec, gather, state = self.mm_exchange
         for r in range(rec.world):
             self.prob.mm_peer_rec[r] = rec.ptrs[r]
