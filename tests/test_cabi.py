@@ -240,3 +240,47 @@ def test_product_path_fails_loudly_without_cuda():
             _lib.load()
     finally:
         _lib.LIB_PATH, _lib._lib = real, saved
+
+
+def test_sharded_moment_matching_descriptor(lib, monkeypatch):
+    """a descriptor with mm_world > 1 (this rank's equal shard of N * world particles that are matched
+    together) plans the cluster-resident sweeps, reports the sizes of its three exchange areas, and is rejected when the
+    shard arithmetic is inconsistent or the problem is outside those sweeps (host-side planner only, no device work)."""
+    from prob_mbrl_b200 import _lib
+    from prob_mbrl_b200.operands import NotEligible
+    monkeypatch.delenv("PMB_STREAM_MODE", raising=False)
+    tune = _lib.make_tuning()
+    p = _fake_problem(N=100, H=400, mm=True)
+    p.mm_world, p.mm_rank, p.n_global = 2, 1, 200
+    info = _lib.describe_plan(p, tune)
+    assert info["variant"] == 1 and info["ctas"] <= 15 * 8
+    sizes = (C.c_size_t * 3)()
+    assert lib.pmb_mm_exchange_bytes(C.byref(p), C.byref(tune), sizes) == 0, lib.pmb_last_error()
+    nq = 5 + 15                                              # D sums + D (D + 1) / 2 products
+    tiles = 2 * (info["ctas"] // 8) * 2                      # two particle tiles per cluster, two ranks
+    assert sizes[0] >= 2 * 2 * tiles * nq * 16               # [2 sweeps][2 parities][tiles][nq] 16-byte tagged entries
+    assert sizes[1] == lib.pmb_peer_buffer_bytes(400 * 100, 2) and sizes[2] >= 40
+    # the same shard on one rank of four
+    p.mm_world, p.mm_rank, p.n_global = 4, 3, 400
+    assert lib.pmb_check_problem(C.byref(p), C.byref(tune)) == 0, lib.pmb_last_error()
+    # inconsistent shard arithmetic / rank out of range
+    p.n_global = 399
+    assert lib.pmb_check_problem(C.byref(p), C.byref(tune)) == -1      # PMB_E_INVALID
+    p.n_global, p.mm_rank = 400, 4
+    assert lib.pmb_check_problem(C.byref(p), C.byref(tune)) == -1      # PMB_E_INVALID
+    # matching groups and nets outside the cluster-resident sweeps are not sharded
+    q = _fake_problem(N=100, H=40, mm=True, groups=2)
+    q.mm_world, q.mm_rank, q.n_global = 2, 0, 200
+    with pytest.raises(NotEligible):
+        _lib.describe_plan(q, tune)
+    q = _fake_problem(N=100, H=40, mm=True, hid=(400, 400, 400))
+    q.mm_world, q.mm_rank, q.n_global = 2, 0, 200
+    with pytest.raises(NotEligible):
+        _lib.describe_plan(q, tune)
+
+
+def test_peer_exchange_sizes(lib):
+    """pmb_peer_buffer_bytes: [2 parities][world][n] floats + [world] flags; 0 for nonsense arguments."""
+    assert lib.pmb_peer_buffer_bytes(41803, 8) >= 2 * 8 * 41803 * 4 + 8 * 8
+    assert lib.pmb_peer_buffer_bytes(41803, 1) >= 2 * 41803 * 4 + 8
+    assert lib.pmb_peer_buffer_bytes(0, 2) == 0 and lib.pmb_peer_buffer_bytes(10, 17) == 0
