@@ -451,6 +451,10 @@ static int plan_cluster(const pmb_problem *p, const pmb_tuning *tune, Plan &pl) 
     {
         const int st = (tune && mode == 3) ? (tune->reserved[1] >> 8) & 0xffff : 0;
         pl.cfwd.pingpong = pl.cbwd.pingpong = st ? (st - 1) : 1;
+        // with moment matching the forward tiles wait for each other's records every step: letting them run free
+        // (instead of alternating on the shared-memory-bound phases) brings the last record 4 % earlier (c3 forward
+        // sweep 3.06 -> 2.95 ms); the reverse sweep does not care
+        if (!st && p->mm_states) pl.cfwd.pingpong = 0;
     }
     pl.cl_nclusters = (p->N + PG - 1) / PG;
     pl.cluster = C;
